@@ -1,0 +1,729 @@
+// Cosine scoring + row top-k on the 5th-gen tensor cores (sm_100a): bf16 tcgen05
+// scan of the whole index with a threshold-filter epilogue, then an EXACT fp32
+// re-score of the few survivors.  Replaces np.dot + full argsort
+// (reference sse_evaluator.py:110-111, data_utils.py:263-267) for E % 64 == 0.
+//
+// Pipeline per query batch (all on one stream, no host sync):
+//   1. prep_queries      q fp32 [Q,E] -> bf16 [Qp,E] (zero padded) + row norms
+//   2. scan<TILEMAX>     tcgen05 GEMM over a strided SAMPLE of 128-row index tiles;
+//                        epilogue = per (row, tile) max            (no divergence)
+//   3. select_tau        tau[r] = k-th largest sampled tile max - margin[r]
+//                        (a valid lower bound of the k-th best approximate score)
+//   4. scan<FILTER>      tcgen05 GEMM over ALL tiles; epilogue compares every score
+//                        with tau[r] in registers and appends the rare survivors
+//                        to a private per-(CTA,row) candidate list
+//   5. finalize          per row: sort candidates, keep those within the bf16 error
+//                        margin of the k-th best, re-score them in fp32 against the
+//                        fp32 index, sort by (score desc, idx asc), emit k
+//   6. fallback          rows whose candidate lists overflowed (pathological ties)
+//                        are recomputed by brute force in fp32
+// Exactness: |approx - exact| <= eps_r = 0.0045*|q_r|*max|t| (bf16 operand rounding,
+// fp32 accumulate).  Every exact top-k element has approx >= A_k - 2 eps >= tau, so it
+// survives 4 and 5; the final order/scores come from fp32 arithmetic only.
+//
+// GEMM mapping: queries are the A operand (M = 128 rows per m-tile, 1 or 2 m-tiles
+// resident in smem per CTA), the index streams through a TMA ring as the B operand
+// (N = 128 index rows per tile, K = E), fp32 accumulators are double-buffered in
+// TMEM; TMEM lane == query row, so each epilogue thread owns one row.
+#include "sse_common.cuh"
+#include <cuda.h>
+#include <math_constants.h>
+
+namespace sse {
+
+namespace {
+
+constexpr int TILE_N = 128;          // index rows per MMA tile
+constexpr int TILE_M = 128;          // query rows per m-tile
+constexpr int KBLK = 64;             // bf16 elements per 128-byte swizzle row
+constexpr int TILE_BYTES = 128 * KBLK * 2;   // 16 KB: one [128 x 64] bf16 SW128 tile
+constexpr int CAND_CAP = 64;         // candidates per (CTA item, row)
+constexpr int MAX_GROUPS = 32;
+constexpr int SCAN_THREADS = 384;
+constexpr int FIN_MAXC = 2048;       // candidates per row the finalize kernel can sort
+constexpr int FIN_MAXR = 256;        // candidates per row re-scored exactly
+constexpr float EPS_REL = 0.0045f;   // bf16 x bf16 dot error bound / (|q| |t|)
+
+enum { MODE_TILEMAX = 0, MODE_FILTER = 1 };
+
+struct ScanParams {
+  int n_groups;
+  int mtg;                         // m-tiles per group (smem / TMEM are sized for this)
+  int kb;                          // E / 64
+  int n_stages;
+  int group_first_item[MAX_GROUPS];
+  int group_items[MAX_GROUPS];
+  int group_mt[MAX_GROUPS];        // valid m-tiles in the group
+  int n_j;                         // tiles visited: tile = tile_base + j * tile_step, j in [0, n_j)
+  int tile_step;
+  int64_t N;                       // index rows
+  int Qp;                          // padded query rows
+  int64_t global_offset;
+  const float* tau;                // [Qp]        (FILTER)
+  float* tilemax;                  // [n_j][Qp]   (TILEMAX)
+  float* cand_s;                   // [items][mtg*128][CAND_CAP]
+  int32_t* cand_i;
+  int32_t* cand_cnt;               // [items][mtg*128]
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B smem matrix descriptor (cute::UMMA::SmemDescriptor): 8-row x 128-byte
+// swizzle atoms, SBO = 1024 B between 8-row groups, LBO unused (1), version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define TMEM_LD_32(taddr, v)                                                                                       \
+  asm volatile(                                                                                                    \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28," \
+      "%29,%30,%31}, [%32];"                                                                                       \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),     \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),    \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                  \
+      : "r"(taddr))
+
+// ------------------------------------------------------------------ the scan
+// grid = number of work items; item -> (group g, range r of the j loop).
+// warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator, warps 4..11: epilogue
+// (warp 4+e: m-tile e/4, TMEM lane quarter e%4).
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_idx,
+            const __grid_constant__ ScanParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- which item
+  const int item = blockIdx.x;
+  int g = 0;
+  while (g + 1 < P.n_groups && item >= P.group_first_item[g + 1]) ++g;
+  const int r_in_g = item - P.group_first_item[g];
+  const int R = P.group_items[g];
+  const int mt_count = P.group_mt[g];
+  const int j0 = (int)(((int64_t)P.n_j * r_in_g) / R);
+  const int j1 = (int)(((int64_t)P.n_j * (r_in_g + 1)) / R);
+  const int KB = P.kb, NS = P.n_stages;
+
+  uint8_t* a_smem = smem;                                        // [mtg][KB] tiles
+  uint8_t* b_smem = smem + (size_t)P.mtg * KB * TILE_BYTES;     // [NS] tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)NS * TILE_BYTES);
+  // bars: full[NS], empty[NS], a_full, acc_full[2], acc_empty[2]
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = smem_u32(bars + NS);
+  const uint32_t bar_a = smem_u32(bars + 2 * NS);
+  const uint32_t bar_accf = smem_u32(bars + 2 * NS + 1);
+  const uint32_t bar_acce = smem_u32(bars + 2 * NS + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, mt_count * 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0 && j1 > j0) {
+      mbar_expect_tx(bar_a, (uint32_t)(mt_count * KB * TILE_BYTES));
+      for (int mt = 0; mt < mt_count; ++mt)
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(smem_u32(a_smem + (size_t)(mt * KB + kb) * TILE_BYTES), &tmap_q, bar_a, kb * KBLK,
+                      (g * P.mtg + mt) * TILE_M);
+      uint32_t it = 0;
+      for (int j = j0; j < j1; ++j) {
+        const int tile = j * P.tile_step;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % NS, ph = (it / NS) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_full + 8 * s, TILE_BYTES);
+          tma_load_2d(smem_u32(b_smem + (size_t)s * TILE_BYTES), &tmap_idx, bar_full + 8 * s, kb * KBLK, tile * TILE_N);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0 && j1 > j0) {
+      const uint32_t idesc = make_idesc_bf16(TILE_M, TILE_N);
+      mbar_wait(bar_a, 0);
+      tc_fence_after();
+      uint32_t it = 0;
+      for (int j = j0; j < j1; ++j) {
+        const int jj = j - j0;
+        const int buf = jj & 1;
+        const uint32_t use = (uint32_t)(jj >> 1);
+        mbar_wait(bar_acce + 8 * buf, (use & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % NS, ph = (it / NS) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t bdesc = make_sw128_desc(smem_u32(b_smem + (size_t)s * TILE_BYTES));
+          for (int mt = 0; mt < mt_count; ++mt) {
+            const uint64_t adesc = make_sw128_desc(smem_u32(a_smem + (size_t)(mt * KB + kb) * TILE_BYTES));
+            const uint32_t d = tmem_base + (uint32_t)((buf * P.mtg + mt) * TILE_N);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)   // 4 x (K=16) per 64-wide k block: +32 bytes = +2 descriptor units
+              tc_mma_bf16(d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+          }
+          tc_commit(bar_empty + 8 * s);     // smem stage is free once these MMAs retire
+        }
+        tc_commit(bar_accf + 8 * buf);      // accumulators of this tile are complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread == query row =====
+    const int e = warp - 4;
+    const int mt = e >> 2, quarter = e & 3;
+    if (mt < mt_count) {
+      const int lrow = mt * TILE_M + quarter * 32 + lane;             // row within the group
+      const int grow = g * P.mtg * TILE_M + lrow;                     // padded global row
+      float thr = CUDART_INF_F;
+      int cnt = 0;
+      float* my_s = nullptr;
+      int32_t* my_i = nullptr;
+      if (MODE == MODE_FILTER) {
+        thr = P.tau[grow];
+        size_t base = ((size_t)item * (P.mtg * TILE_M) + lrow) * CAND_CAP;
+        my_s = P.cand_s + base;
+        my_i = P.cand_i + base;
+      }
+      for (int j = j0; j < j1; ++j) {
+        const int jj = j - j0;
+        const int buf = jj & 1;
+        const uint32_t use = (uint32_t)(jj >> 1);
+        const int tile = j * P.tile_step;
+        const int64_t col0 = (int64_t)tile * TILE_N;
+        const bool ragged = col0 + TILE_N > P.N;
+        mbar_wait(bar_accf + 8 * buf, use & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * P.mtg + mt) * TILE_N);
+        float tmax = -CUDART_INF_F;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t v[32];
+          TMEM_LD_32(taddr + ch * 32, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + ch * 32 + i >= P.N) v[i] = 0xff800000u;   // -inf
+          }
+          float m = __uint_as_float(v[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+          if (MODE == MODE_TILEMAX) {
+            tmax = fmaxf(tmax, m);
+          } else if (m > thr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float s = __uint_as_float(v[i]);
+              if (s > thr) {
+                if (cnt < CAND_CAP) {
+                  my_s[cnt] = s;
+                  my_i[cnt] = (int32_t)(P.global_offset + col0 + ch * 32 + i);
+                }
+                ++cnt;
+              }
+            }
+          }
+        }
+        if (MODE == MODE_TILEMAX) P.tilemax[(size_t)j * P.Qp + grow] = tmax;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+      }
+      if (MODE == MODE_FILTER) P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + lrow] = cnt;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// --------------------------------------------------------------- small kernels
+// q fp32 [Q,E] -> bf16 [Qp,E] (rows >= Q zero), qnorm[Qp]
+__global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, __nv_bfloat16* __restrict__ qb,
+                                    float* __restrict__ qnorm) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= Qp) return;
+  float ss = 0.f;
+  for (int j = lane; j < E; j += 32) {
+    float v = row < Q ? q[(size_t)row * E + j] : 0.f;
+    ss = fmaf(v, v, ss);
+    qb[(size_t)row * E + j] = __float2bfloat16_rn(v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) qnorm[row] = sqrtf(ss);
+}
+
+// max row norm of the index (one-time, at index_set): out[0] = max |t|
+__global__ void max_row_norm_kernel(const float* __restrict__ x, int64_t N, int E, float* __restrict__ out) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  float best = 0.f;
+  for (; row < N; row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    float ss = 0.f;
+    for (int j = lane; j < E; j += 32) { float v = x[(size_t)row * E + j]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    best = fmaxf(best, ss);
+  }
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best)));   // non-negative floats order as ints
+}
+
+// warp per row: tau[r] = (k-th largest of tilemax[0..n_s)[r]) - 2*eps_r ; rows >= Q: +inf
+__global__ void select_tau_kernel(const float* __restrict__ tilemax, int n_s, int Qp, int Q, int k,
+                                  const float* __restrict__ qnorm, const float* __restrict__ tnorm_max,
+                                  float* __restrict__ tau, float* __restrict__ margin) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= Qp) return;
+  if (row >= Q) { if (lane == 0) { tau[row] = CUDART_INF_F; margin[row] = 0.f; } return; }
+  // lane owns elements lane, lane+32, ... (<= 32 of them since n_s <= 1024)
+  uint32_t taken = 0;
+  float kth = -CUDART_INF_F;
+  for (int r = 0; r < k; ++r) {
+    float bs = -CUDART_INF_F;
+    int bp = -1;
+    for (int t = 0, j = lane; j < n_s; j += 32, ++t) {
+      if (taken & (1u << t)) continue;
+      float v = tilemax[(size_t)j * Qp + row];
+      if (bp < 0 || v > bs) { bs = v; bp = j; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      int op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (op >= 0 && (bp < 0 || os > bs || (os == bs && op < bp))) { bs = os; bp = op; }
+    }
+    if (bp < 0) { kth = -CUDART_INF_F; break; }
+    kth = bs;
+    if ((bp & 31) == lane) taken |= 1u << (bp >> 5);
+  }
+  if (lane == 0) {
+    float mg = 2.f * EPS_REL * qnorm[row] * tnorm_max[0];
+    margin[row] = mg;
+    tau[row] = kth - mg;
+  }
+}
+
+struct FinParams {
+  int n_groups, mtg;
+  int group_first_item[MAX_GROUPS];
+  int group_items[MAX_GROUPS];
+  const float* cand_s;
+  const int32_t* cand_i;
+  const int32_t* cand_cnt;
+  const float* margin;
+  const float* q;          // fp32 [Q,E]
+  const float* index;      // fp32 [N,E] local shard
+  int64_t global_offset;
+  int64_t N;
+  int Q, E, k;
+  float* out_s;
+  int32_t* out_i;
+  int32_t* overflow;       // [Q]
+};
+
+// bitonic sort of n (power of two) pairs in smem, order (score desc, idx asc)
+__device__ __forceinline__ bool pair_before(float sa, int32_t ia, float sb, int32_t ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+__device__ void bitonic_sort_pairs(float* s, int32_t* id, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        int lo = 2 * t - (t & (stride - 1));
+        int hi = lo + stride;
+        bool up = ((lo & size) == 0);     // first-half blocks sorted "best first"
+        float sa = s[lo], sb = s[hi];
+        int32_t ia = id[lo], ib = id[hi];
+        bool swap = up ? pair_before(sb, ib, sa, ia) : pair_before(sa, ia, sb, ib);
+        if (swap) { s[lo] = sb; s[hi] = sa; id[lo] = ib; id[hi] = ia; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ FinParams P) {
+  __shared__ float cs[FIN_MAXC];
+  __shared__ int32_t ci[FIN_MAXC];
+  __shared__ int s_total, s_over, s_m;
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int rows_per_group = P.mtg * TILE_M;
+  const int g = row / rows_per_group, lrow = row % rows_per_group;
+  const int first = P.group_first_item[g], R = P.group_items[g];
+  if (tid == 0) { s_total = 0; s_over = 0; }
+  __syncthreads();
+  // gather candidates (one item at a time per thread; counts are small)
+  for (int it = tid; it < R; it += blockDim.x) {
+    size_t slot = (size_t)(first + it) * rows_per_group + lrow;
+    int c = P.cand_cnt[slot];
+    if (c > CAND_CAP) { atomicExch(&s_over, 1); c = CAND_CAP; }
+    int at = atomicAdd(&s_total, c);
+    if (at + c > FIN_MAXC) { atomicExch(&s_over, 1); continue; }
+    for (int x = 0; x < c; ++x) { cs[at + x] = P.cand_s[slot * CAND_CAP + x]; ci[at + x] = P.cand_i[slot * CAND_CAP + x]; }
+  }
+  __syncthreads();
+  int total = min(s_total, FIN_MAXC);
+  if (s_over) {
+    if (tid == 0) P.overflow[row] = 1;
+    return;
+  }
+  if (tid == 0) P.overflow[row] = 0;
+  int n2 = 1;
+  while (n2 < total) n2 <<= 1;
+  for (int x = total + tid; x < n2; x += blockDim.x) { cs[x] = -CUDART_INF_F; ci[x] = 0x7fffffff; }
+  bitonic_sort_pairs(cs, ci, n2);
+  // survivors: approx >= A_k - margin
+  const int k = P.k;
+  if (tid == 0) {
+    int m = total;
+    if (total >= k) {
+      float cut = cs[k - 1] - P.margin[row];
+      int lo = k, hi = total;          // first index with cs < cut (sorted descending)
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (cs[mid] >= cut) lo = mid + 1; else hi = mid; }
+      m = lo;
+    }
+    s_m = m;
+  }
+  __syncthreads();
+  int m = s_m;
+  if (m > FIN_MAXR) {
+    if (tid == 0) P.overflow[row] = 1;
+    return;
+  }
+  // exact fp32 re-score of the m survivors: warp per candidate
+  const int warp = tid >> 5, lane = tid & 31;
+  const float* qr = P.q + (size_t)row * P.E;
+  for (int c = warp; c < m; c += 4) {
+    const float* tr = P.index + (size_t)(ci[c] - P.global_offset) * P.E;
+    float acc = 0.f;
+    for (int j = lane * 4; j < P.E; j += 128) {
+      float4 a = *reinterpret_cast<const float4*>(qr + j);
+      float4 b = *reinterpret_cast<const float4*>(tr + j);
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) cs[c] = acc;
+  }
+  __syncthreads();
+  int m2 = 1;
+  while (m2 < m) m2 <<= 1;
+  for (int x = m + tid; x < m2; x += blockDim.x) { cs[x] = -CUDART_INF_F; ci[x] = 0x7fffffff; }
+  bitonic_sort_pairs(cs, ci, m2);
+  for (int x = tid; x < k; x += blockDim.x) {
+    bool ok = x < m;
+    P.out_s[(size_t)row * k + x] = ok ? cs[x] : -CUDART_INF_F;
+    P.out_i[(size_t)row * k + x] = ok ? ci[x] : -1;
+  }
+}
+
+// rows flagged by finalize: brute-force exact fp32 top-k (rare: pathological ties / clustered index)
+__global__ void __launch_bounds__(256) fallback_kernel(const __grid_constant__ FinParams P) {
+  extern __shared__ float dyn[];   // per warp k scores + k idx
+  const int row = blockIdx.x;
+  if (!P.overflow[row]) return;
+  const int k = P.k, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float* ls = dyn + (size_t)warp * k * 2;
+  int32_t* li = reinterpret_cast<int32_t*>(ls + k);
+  for (int x = lane; x < k; x += 32) { ls[x] = -CUDART_INF_F; li[x] = -1; }
+  __syncwarp();
+  const float* qr = P.q + (size_t)row * P.E;
+  for (int64_t n = warp; n < P.N; n += nw) {      // ascending n per warp keeps ties at the lower index
+    const float* tr = P.index + (size_t)n * P.E;
+    float acc = 0.f;
+    for (int j = lane * 4; j < P.E; j += 128) {
+      float4 a = *reinterpret_cast<const float4*>(qr + j);
+      float4 b = *reinterpret_cast<const float4*>(tr + j);
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && acc > ls[k - 1]) {
+      int p = k - 1;
+      while (p > 0 && ls[p - 1] < acc) { ls[p] = ls[p - 1]; li[p] = li[p - 1]; --p; }
+      ls[p] = acc;
+      li[p] = (int32_t)(P.global_offset + n);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // merge the nw lists: thread 0, k rounds (tiny)
+  if (threadIdx.x == 0) {
+    int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int x = 0; x < k; ++x) {
+      int bw = -1;
+      for (int w = 0; w < nw; ++w) {
+        if (head[w] >= k) continue;
+        float s = dyn[(size_t)w * k * 2 + head[w]];
+        int32_t i = reinterpret_cast<int32_t*>(dyn + (size_t)w * k * 2 + k)[head[w]];
+        if (i < 0) continue;
+        if (bw < 0) { bw = w; continue; }
+        float bs = dyn[(size_t)bw * k * 2 + head[bw]];
+        int32_t bi = reinterpret_cast<int32_t*>(dyn + (size_t)bw * k * 2 + k)[head[bw]];
+        if (pair_before(s, i, bs, bi)) bw = w;
+      }
+      if (bw < 0) { P.out_s[(size_t)row * k + x] = -CUDART_INF_F; P.out_i[(size_t)row * k + x] = -1; continue; }
+      P.out_s[(size_t)row * k + x] = dyn[(size_t)bw * k * 2 + head[bw]];
+      P.out_i[(size_t)row * k + x] = reinterpret_cast<int32_t*>(dyn + (size_t)bw * k * 2 + k)[head[bw]];
+      ++head[bw];
+    }
+  }
+}
+
+// ------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 [rows, E] row-major, box = 64 cols x 128 rows, 128-byte swizzle
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int E) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return SSE_ECUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)E, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)E * 2};
+  cuuint32_t box[2] = {KBLK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld E=%d", (int)r, (long long)rows, E); return SSE_ECUDA; }
+  return SSE_OK;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+bool search_tc_supported(int E, int64_t N, int k) {
+  return E % 64 == 0 && E >= 64 && E <= 512 && k >= 1 && k <= 32 && N >= 64 * TILE_N && N < ((int64_t)1 << 31) - 256;
+}
+
+int search_tc_prepare(TcIndex& ti, const float* index_f32, int64_t N, int E, cudaStream_t st, int64_t* launches) {
+  search_tc_release(ti);
+  ti.N = N; ti.E = E;
+  size_t bytes = (size_t)N * E * 2 + 64;
+  cudaError_t e = cudaMalloc(&ti.bf16, bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(bf16 index, %zu) failed: %s", bytes, cudaGetErrorString(e)); return SSE_ENOMEM; }
+  SSE_TRY(f32_to_bf16(index_f32, ti.bf16, N * E, st, launches));
+  // slot for max |t| lives behind the matrix
+  float* tn = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.bf16) + align_up((size_t)N * E * 2, 16));
+  SSE_CUDA_OK(cudaMemsetAsync(tn, 0, 4, st));
+  max_row_norm_kernel<<<148 * 4, 256, 0, st>>>(index_f32, N, E, tn);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap), ti.bf16, N, E));
+  ti.tmap_ok = true;
+  return SSE_OK;
+}
+
+void search_tc_release(TcIndex& ti) {
+  if (ti.bf16) cudaFree(ti.bf16);
+  ti.bf16 = nullptr; ti.N = 0; ti.E = 0; ti.tmap_ok = false;
+}
+
+int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
+              float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches) {
+  if (Q <= 0) return SSE_OK;
+  if (!ti.tmap_ok || ti.E != E) { set_error("search_tc: index not prepared"); return SSE_ESTATE; }
+  const int64_t N = ti.N;
+  const int KB = E / KBLK;
+  const int m_tiles = cdiv(Q, TILE_M);
+  int mtg = (m_tiles >= 2 && KB <= 4) ? 2 : 1;
+  const int n_groups = cdiv(m_tiles, mtg);
+  if (n_groups > MAX_GROUPS) { set_error("search_tc: Q=%d too large for one call (max %d rows)", Q, MAX_GROUPS * 2 * TILE_M); return SSE_EINVAL; }
+  const int Qp = n_groups * mtg * TILE_M;
+  const int n_tiles = (int)cdiv64(N, TILE_N);
+  int n_s = n_tiles / 16;
+  if (n_s < 64) n_s = 64;
+  if (n_s > 1024) n_s = 1024;
+  if (n_s > n_tiles) n_s = n_tiles;
+  const int s_step = n_tiles / n_s;
+
+  // smem budget
+  const size_t a_bytes = (size_t)mtg * KB * TILE_BYTES;
+  int NS = (int)((232448 - 1024 - 256 - a_bytes) / TILE_BYTES);
+  if (NS > 8) NS = 8;
+  if (NS < 2) { set_error("search_tc: E=%d does not fit shared memory", E); return SSE_EINVAL; }
+  const size_t smem = 1024 + a_bytes + (size_t)NS * TILE_BYTES + 256;
+
+  // items: split ~num_sms CTAs over groups in proportion to their m-tile count
+  ScanParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.n_groups = n_groups; sp.mtg = mtg; sp.kb = KB; sp.n_stages = NS;
+  sp.N = N; sp.Qp = Qp; sp.global_offset = global_offset;
+  int items = 0;
+  {
+    int budget = max(num_sms, n_groups);
+    int assigned_mt = 0, assigned_items = 0;
+    for (int g = 0; g < n_groups; ++g) {
+      int mtc = min(mtg, m_tiles - g * mtg);
+      assigned_mt += mtc;
+      int upto = (int)((int64_t)budget * assigned_mt / m_tiles);
+      int cnt = max(1, upto - assigned_items);
+      sp.group_first_item[g] = assigned_items;
+      sp.group_items[g] = cnt;
+      sp.group_mt[g] = mtc;
+      assigned_items += cnt;
+    }
+    items = assigned_items;
+  }
+  // a group never needs more items than tiles
+  // (tiny N is excluded by search_tc_supported: n_tiles >= 64)
+
+  // workspace carve
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  size_t o_qb = carve((size_t)Qp * E * 2);
+  size_t o_qn = carve((size_t)Qp * 4);
+  size_t o_tau = carve((size_t)Qp * 4);
+  size_t o_mg = carve((size_t)Qp * 4);
+  size_t o_tm = carve((size_t)n_s * Qp * 4);
+  size_t o_cs = carve((size_t)items * mtg * TILE_M * CAND_CAP * 4);
+  size_t o_ci = carve((size_t)items * mtg * TILE_M * CAND_CAP * 4);
+  size_t o_cc = carve((size_t)items * mtg * TILE_M * 4);
+  size_t o_ov = carve((size_t)Qp * 4);
+  SSE_TRY(ws.ensure(off));
+  uint8_t* w = ws.as<uint8_t>();
+  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(w + o_qb);
+  float* qn = reinterpret_cast<float*>(w + o_qn);
+  float* tau = reinterpret_cast<float*>(w + o_tau);
+  float* mg = reinterpret_cast<float*>(w + o_mg);
+  float* tm = reinterpret_cast<float*>(w + o_tm);
+  float* tn = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.bf16) + align_up((size_t)N * E * 2, 16));
+
+  prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E, qb, qn);
+  if (launches) ++*launches;
+
+  CUtensorMap tmq;
+  SSE_TRY(make_tmap(&tmq, qb, Qp, E));
+  const CUtensorMap& tmi = *reinterpret_cast<const CUtensorMap*>(ti.tmap);
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    SSE_CUDA_OK(cudaFuncSetAttribute(scan_kernel<MODE_TILEMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SSE_CUDA_OK(cudaFuncSetAttribute(scan_kernel<MODE_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_done = true;
+  }
+
+  // pass A: tile maxima over the strided sample
+  sp.n_j = n_s; sp.tile_step = s_step; sp.tilemax = tm; sp.tau = nullptr;
+  scan_kernel<MODE_TILEMAX><<<items, SCAN_THREADS, smem, st>>>(tmq, tmi, sp);
+  if (launches) ++*launches;
+  select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, qn, tn, tau, mg);
+  if (launches) ++*launches;
+
+  // pass B: filter over all tiles
+  sp.n_j = n_tiles; sp.tile_step = 1; sp.tilemax = nullptr; sp.tau = tau;
+  sp.cand_s = reinterpret_cast<float*>(w + o_cs);
+  sp.cand_i = reinterpret_cast<int32_t*>(w + o_ci);
+  sp.cand_cnt = reinterpret_cast<int32_t*>(w + o_cc);
+  scan_kernel<MODE_FILTER><<<items, SCAN_THREADS, smem, st>>>(tmq, tmi, sp);
+  if (launches) ++*launches;
+
+  FinParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.n_groups = n_groups; fp.mtg = mtg;
+  for (int g = 0; g < n_groups; ++g) { fp.group_first_item[g] = sp.group_first_item[g]; fp.group_items[g] = sp.group_items[g]; }
+  fp.cand_s = sp.cand_s; fp.cand_i = sp.cand_i; fp.cand_cnt = sp.cand_cnt; fp.margin = mg;
+  fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E; fp.k = k;
+  fp.out_s = out_scores; fp.out_i = out_idx; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov);
+  finalize_kernel<<<Q, 128, 0, st>>>(fp);
+  if (launches) ++*launches;
+  fallback_kernel<<<Q, 256, (size_t)8 * k * 8, st>>>(fp);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
+}  // namespace sse

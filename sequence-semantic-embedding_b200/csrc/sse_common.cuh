@@ -1,0 +1,117 @@
+// Shared declarations of libsse_b200.so (internal; the public ABI is include/sse_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <algorithm>
+
+#include "../../include/sse_b200.h"
+
+namespace sse {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SSE_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::sse::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return SSE_ECUDA;                                                                \
+    }                                                                                  \
+  } while (0)
+
+#define SSE_TRY(expr)              \
+  do {                             \
+    int _r = (expr);               \
+    if (_r != SSE_OK) return _r;   \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  float* dev = nullptr;
+  int64_t numel = 0;
+  bool trainable = true;
+  int64_t grad_off = -1;   // offset (floats) of the dense gradient in the arena, -1 = none (sparse / non-trainable)
+};
+
+// One LSTM tower (TF layouts, device pointers into Params).
+struct LstmTower {
+  const float* K = nullptr;   // [We+H, 4H], column blocks i,j,f,o
+  const float* b = nullptr;   // [4H]
+  const float* M = nullptr;   // [H, E]
+  int H = 0;
+  int kparam = -1, bparam = -1, mparam = -1;   // indices into params
+};
+
+struct CnnTower {
+  int nf = 0;
+  int ksize[SSE_MAX_CNN_FILTERS];
+  int nfilt[SSE_MAX_CNN_FILTERS];
+  const float* W[SSE_MAX_CNN_FILTERS];   // [k, We, 1, F]
+  const float* b[SSE_MAX_CNN_FILTERS];   // [F]
+  int wparam[SSE_MAX_CNN_FILTERS], bparam[SSE_MAX_CNN_FILTERS];
+  const float* M = nullptr;              // [sumF, E]
+  int mparam = -1;
+  int sumF = 0;
+};
+
+// growable device scratch buffer
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// ---- kernels (implemented in the .cu files) --------------------------------
+// lstm_simt.cu
+int lstm_forward_simt(const int32_t* tokens, int B, int T, int t_start, const float* emb, int We,
+                      const LstmTower& tw, float* h0, float* h1, float* c,      // [B,H] each
+                      const float* init_h, const float* init_c,                // optional [H] broadcast initial state (pad-prefix table row)
+                      float* save_h, float* save_c, float* save_g,             // optional training stash: [T,B,H],[T,B,H],[T,B,5H]
+                      float** h_final, cudaStream_t st, int64_t* launches);
+int sgemm(bool ta, bool tb, int M, int N, int Kd, float alpha, const float* A, int lda, const float* Bm, int ldb,
+          float beta, float* C, int ldc, cudaStream_t st, int64_t* launches);
+int l2norm_rows(float* x, int rows, int cols, cudaStream_t st, int64_t* launches);
+int l2norm_rows_out(const float* x, float* y, int rows, int cols, cudaStream_t st, int64_t* launches);
+
+// cnn.cu
+int cnn_forward_ws(const int32_t* tokens, int B, int T, const float* emb, int We, const CnnTower& tw, float* xg,
+                   float* conv, float* pool /*[B,sumF]*/, int32_t* argmax /*optional [B,sumF]*/, cudaStream_t st,
+                   int64_t* launches);
+
+// search_simt.cu
+int search_simt(const float* q, int Q, int E, const float* index, int64_t N, int64_t global_offset, int k,
+                float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches);
+int merge_topk(const float* cand_s, const int32_t* cand_i, int Q, int C, int k, float* out_s, int32_t* out_i,
+               cudaStream_t st, int64_t* launches);
+
+// search_tc.cu (tcgen05 bf16 scan + exact fp32 re-rank)
+struct TcIndex {
+  __nv_bfloat16* bf16 = nullptr;   // [N, E] row-major
+  int64_t N = 0;
+  int E = 0;
+  alignas(64) unsigned char tmap[128];   // CUtensorMap of the bf16 index
+  bool tmap_ok = false;
+};
+bool search_tc_supported(int E, int64_t N, int k);
+int search_tc_prepare(TcIndex& ti, const float* index_f32, int64_t N, int E, cudaStream_t st, int64_t* launches);
+void search_tc_release(TcIndex& ti);
+int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
+              float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches);
+
+// small utilities (util.cu)
+int fill_f32(float* p, int64_t n, float v, cudaStream_t st, int64_t* launches);
+int f32_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st, int64_t* launches);
+
+}  // namespace sse

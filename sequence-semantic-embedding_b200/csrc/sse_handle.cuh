@@ -1,0 +1,51 @@
+// The opaque handle behind the C ABI (internal).
+#pragma once
+#include "sse_common.cuh"
+
+namespace sse {
+struct PadTable {
+  Scratch buf;
+  const float* h = nullptr;   // [T][H]: state after t+1 leading PADs
+  const float* c = nullptr;
+  bool valid = false;
+};
+}  // namespace sse
+
+struct sse_handle {
+  sse_config cfg;
+  int num_sms = 148;
+  int cc_major = 0;
+  std::vector<sse::Param> params;   // variables first (n_vars), then their "/Adagrad" slots in the same order
+  int n_vars = 0;
+  int emb_param = -1;
+  int tgt_table_param = -1;
+  sse::LstmTower lstm[2];           // [SSE_SIDE_SRC], [SSE_SIDE_TGT]
+  sse::CnnTower cnn[2];
+  sse::PadTable pad[2];
+  float learning_rate = 0.f;
+  int64_t global_step = 0;
+
+  // resident target index (this rank's shard)
+  float* index_f32 = nullptr;
+  bool index_owned = false;
+  int64_t index_n = 0, index_off = 0;
+  sse::TcIndex tc;
+
+  // workspaces
+  sse::Scratch enc_ws, search_ws, io_ws, train_ws;
+  float* grad_arena = nullptr;      // dense gradients, laid out by Param::grad_off, then the dense embedding gradient
+  int64_t grad_floats = 0;          // dense (non-embedding) part
+  int64_t arena_floats = 0;
+
+  int opt_search = 0, opt_encoder = 0;
+  bool opt_pad_skip = false;
+  int64_t launches = 0;
+};
+
+namespace sse {
+int find_param(sse_handle* h, const char* name);
+void refresh_pointers(sse_handle* h);
+bool side_is_cnn(const sse_handle* h, int side);
+int encode_device(sse_handle* h, int side, const int32_t* tokens, int B, float* out, int normalize, int t_start,
+                  cudaStream_t st);
+}  // namespace sse

@@ -1,0 +1,338 @@
+"""ctypes binding of libsse_b200.so (the C ABI declared in include/sse_b200.h).
+
+This is the only place Python touches the native library.  There is no CPU
+fallback: if the shared library is missing or no GPU is visible, the calls
+raise.  Device memory is passed as raw pointers (``tensor.data_ptr()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsse_b200.so")
+
+SSE_OK = 0
+MODE_IDS = {
+    "dual-encoder": 0,
+    "shared-encoder": 1,
+    "source-encoder-only": 2,
+    "source_only_cnn": 3,
+    "dual-cnn": 4,
+}
+PRECISION_FP32, PRECISION_TC = 0, 1
+SIDE_SRC, SIDE_TGT = 0, 1
+MAX_CNN = 8
+
+
+class SseConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("network_mode", C.c_int32),
+        ("vocab_size", C.c_int32),
+        ("embedding_size", C.c_int32),
+        ("encoding_size", C.c_int32),
+        ("src_cell_size", C.c_int32),
+        ("tgt_cell_size", C.c_int32),
+        ("max_seq_length", C.c_int32),
+        ("predict_nbest", C.c_int32),
+        ("forward_only", C.c_int32),
+        ("target_space_size", C.c_int64),
+        ("learning_rate", C.c_float),
+        ("learning_rate_decay_factor", C.c_float),
+        ("device", C.c_int32),
+        ("precision", C.c_int32),
+        ("n_cnn_filters", C.c_int32),
+        ("cnn_filter_sizes", C.c_int32 * MAX_CNN),
+        ("cnn_num_filters", C.c_int32 * MAX_CNN),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+class SseError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)   -- must list every symbol include/sse_b200.h declares
+    "sse_create": (C.c_int, [C.POINTER(SseConfig), C.POINTER(_P)]),
+    "sse_destroy": (C.c_int, [_P]),
+    "sse_last_error": (C.c_char_p, []),
+    "sse_version": (C.c_char_p, []),
+    "sse_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "sse_get_param": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "sse_param_count": (C.c_int, [_P]),
+    "sse_param_info": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "sse_encode": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
+    "sse_encode_host": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int]),
+    "sse_index_set": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
+    "sse_index_build": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int]),
+    "sse_index_get": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
+    "sse_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "sse_merge_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "sse_query_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "sse_l2_normalize_rows": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "sse_pair_score": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
+    "sse_train_step": (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float), _P]),
+    "sse_train_grads": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
+    "sse_grad_arena": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "sse_train_apply": (C.c_int, [_P, C.POINTER(C.c_float), _P]),
+    "sse_lr_decay": (C.c_int, [_P]),
+    "sse_get_scalars": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "sse_set_scalars": (C.c_int, [_P, C.c_float, C.c_int64]),
+    "sse_launch_count": (C.c_int64, [_P]),
+    "sse_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """Load libsse_b200.so and attach signatures.  Raises if it is missing:
+    the product path has no fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise SseError(
+            "libsse_b200.so not found at %s -- build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU fallback for the SSE hot path." % p)
+    lib = C.CDLL(p)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(x) -> int:
+    """Raw address of a numpy array / torch tensor / int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+def _stream_ptr(stream) -> Optional[int]:
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return stream or None
+    return stream.cuda_stream or None
+
+
+class Handle:
+    """One sse_handle (weights + optimizer state + resident index on one GPU)."""
+
+    def __init__(self, mode: str, vocab_size: int, embedding_size: int, encoding_size: int, src_cell_size: int,
+                 tgt_cell_size: int, max_seq_length: int, predict_nbest: int = 10, target_space_size: int = 0,
+                 learning_rate: float = 0.9, learning_rate_decay_factor: float = 0.99, device: int = 0,
+                 precision: int = PRECISION_TC, cnn_filter_sizes: Sequence[int] = (), cnn_num_filters: Sequence[int] = ()):
+        self.lib = load_library()
+        if mode not in MODE_IDS:
+            raise SseError("Unsupported network mode: %s" % mode)
+        cfg = SseConfig()
+        cfg.struct_size = C.sizeof(SseConfig)
+        cfg.network_mode = MODE_IDS[mode]
+        cfg.vocab_size = vocab_size
+        cfg.embedding_size = embedding_size
+        cfg.encoding_size = encoding_size
+        cfg.src_cell_size = src_cell_size
+        cfg.tgt_cell_size = tgt_cell_size
+        cfg.max_seq_length = max_seq_length
+        cfg.predict_nbest = predict_nbest
+        cfg.target_space_size = target_space_size
+        cfg.learning_rate = learning_rate
+        cfg.learning_rate_decay_factor = learning_rate_decay_factor
+        cfg.device = device
+        cfg.precision = precision
+        cfg.n_cnn_filters = len(cnn_filter_sizes)
+        for i, (k, f) in enumerate(zip(cnn_filter_sizes, cnn_num_filters)):
+            cfg.cnn_filter_sizes[i] = k
+            cfg.cnn_num_filters[i] = f
+        self.cfg = cfg
+        self.mode = mode
+        self.T = max_seq_length
+        self.E = encoding_size
+        self._h = _P()
+        self._check(self.lib.sse_create(C.byref(cfg), C.byref(self._h)))
+
+    # -- plumbing
+    def _check(self, rc: int):
+        if rc != SSE_OK:
+            msg = self.lib.sse_last_error()
+            raise SseError("libsse_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+    def close(self):
+        if self._h:
+            self.lib.sse_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- variables
+    def param_names(self) -> List[Tuple[str, Tuple[int, ...]]]:
+        out = []
+        n = self.lib.sse_param_count(self._h)
+        buf = C.create_string_buffer(128)
+        shape = (C.c_int64 * 4)()
+        nd = C.c_int()
+        for i in range(n):
+            self._check(self.lib.sse_param_info(self._h, i, buf, 128, shape, C.byref(nd)))
+            out.append((buf.value.decode(), tuple(int(shape[d]) for d in range(nd.value))))
+        return out
+
+    def set_param(self, name: str, value):
+        """value: numpy fp32 array or a torch tensor (host or device)."""
+        if isinstance(value, np.ndarray):
+            value = np.ascontiguousarray(value, dtype=np.float32)
+            shape = value.shape
+        else:
+            value = value.contiguous().float()
+            shape = tuple(value.shape)
+        sh = (C.c_int64 * len(shape))(*shape)
+        self._check(self.lib.sse_set_param(self._h, name.encode(), _ptr(value), sh, len(shape)))
+
+    def get_param(self, name: str) -> np.ndarray:
+        shapes = dict(self.param_names())
+        if name not in shapes:
+            raise SseError("unknown variable %s" % name)
+        out = np.empty(shapes[name], dtype=np.float32)
+        self._check(self.lib.sse_get_param(self._h, name.encode(), out.ctypes.data, out.nbytes))
+        return out
+
+    def set_params(self, params: Dict[str, np.ndarray]):
+        for k, v in params.items():
+            self.set_param(k, v)
+
+    # -- encoders
+    def encode(self, side: int, tokens_dev, B: int, out_dev, normalize: bool = True, stream=None):
+        self._check(self.lib.sse_encode(self._h, side, _ptr(tokens_dev), B, _ptr(out_dev), int(normalize),
+                                        _stream_ptr(stream)))
+
+    def encode_host(self, side: int, tokens: np.ndarray, normalize: bool = True) -> np.ndarray:
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        B = tokens.shape[0]
+        if tokens.ndim != 2 or tokens.shape[1] != self.T:
+            raise SseError("tokens must be [B, %d]" % self.T)
+        out = np.empty((B, self.E), dtype=np.float32)
+        self._check(self.lib.sse_encode_host(self._h, side, tokens.ctypes.data, B, out.ctypes.data, int(normalize)))
+        return out
+
+    # -- index / retrieval
+    def index_set(self, tgt, n_local: Optional[int] = None, global_offset: int = 0):
+        if isinstance(tgt, np.ndarray):
+            tgt = np.ascontiguousarray(tgt, dtype=np.float32)
+        n = int(tgt.shape[0]) if n_local is None else n_local
+        self._check(self.lib.sse_index_set(self._h, _ptr(tgt), n, global_offset))
+
+    def index_build(self, tgt_tokens, global_offset: int = 0, batch: int = 10000):
+        if isinstance(tgt_tokens, np.ndarray):
+            tgt_tokens = np.ascontiguousarray(tgt_tokens, dtype=np.int32)
+        n = int(tgt_tokens.shape[0])
+        self._check(self.lib.sse_index_build(self._h, _ptr(tgt_tokens), n, global_offset, batch))
+
+    def index_get(self, row0: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.E), dtype=np.float32)
+        self._check(self.lib.sse_index_get(self._h, row0, n, out.ctypes.data))
+        return out
+
+    def search(self, q_dev, Q: int, k: int, scores_dev, idx_dev, stream=None):
+        self._check(self.lib.sse_search(self._h, _ptr(q_dev), Q, k, _ptr(scores_dev), _ptr(idx_dev), _stream_ptr(stream)))
+
+    def merge_topk(self, cand_s_dev, cand_i_dev, Q: int, Cn: int, k: int, scores_dev, idx_dev, stream=None):
+        self._check(self.lib.sse_merge_topk(self._h, _ptr(cand_s_dev), _ptr(cand_i_dev), Q, Cn, k, _ptr(scores_dev),
+                                            _ptr(idx_dev), _stream_ptr(stream)))
+
+    def query_host(self, tokens, k: int, normalize: bool = True, scores_out=None, idx_out=None):
+        """tokens: int32 [Q,T] numpy array or pinned torch tensor; returns (scores [Q,k], idx [Q,k]) numpy."""
+        if isinstance(tokens, np.ndarray):
+            tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        Q = int(tokens.shape[0])
+        if scores_out is None:
+            scores_out = np.empty((Q, k), dtype=np.float32)
+        if idx_out is None:
+            idx_out = np.empty((Q, k), dtype=np.int32)
+        self._check(self.lib.sse_query_host(self._h, _ptr(tokens), Q, k, int(normalize), _ptr(scores_out), _ptr(idx_out)))
+        return scores_out, idx_out
+
+    def l2_normalize_rows(self, x_dev, rows: int, cols: int, stream=None):
+        self._check(self.lib.sse_l2_normalize_rows(self._h, _ptr(x_dev), rows, cols, _stream_ptr(stream)))
+
+    # -- training
+    def pair_score(self, src_dev, tgt_dev, B: int, cos_dev, stream=None):
+        self._check(self.lib.sse_pair_score(self._h, _ptr(src_dev), _ptr(tgt_dev), B, _ptr(cos_dev), _stream_ptr(stream)))
+
+    def train_step(self, src, tgt, labels, stream=None, want_scalars: bool = True):
+        if isinstance(src, np.ndarray):
+            src = np.ascontiguousarray(src, dtype=np.int32)
+            tgt = np.ascontiguousarray(tgt, dtype=np.int32)
+            labels = np.ascontiguousarray(labels, dtype=np.float32)
+        B = int(src.shape[0])
+        loss, acc, gn = C.c_float(), C.c_float(), C.c_float()
+        if want_scalars:
+            self._check(self.lib.sse_train_step(self._h, _ptr(src), _ptr(tgt), _ptr(labels), B, C.byref(loss),
+                                                C.byref(acc), C.byref(gn), _stream_ptr(stream)))
+            return loss.value, acc.value, gn.value
+        self._check(self.lib.sse_train_step(self._h, _ptr(src), _ptr(tgt), _ptr(labels), B, None, None, None,
+                                            _stream_ptr(stream)))
+        return None
+
+    def train_grads(self, src, tgt, labels, B_global: int, stream=None):
+        if isinstance(src, np.ndarray):
+            src = np.ascontiguousarray(src, dtype=np.int32)
+            tgt = np.ascontiguousarray(tgt, dtype=np.int32)
+            labels = np.ascontiguousarray(labels, dtype=np.float32)
+        B = int(src.shape[0])
+        loss, acc = C.c_float(), C.c_float()
+        self._check(self.lib.sse_train_grads(self._h, _ptr(src), _ptr(tgt), _ptr(labels), B, B_global, C.byref(loss),
+                                             C.byref(acc), _stream_ptr(stream)))
+        return loss.value, acc.value
+
+    def grad_arena(self) -> Tuple[int, int]:
+        p = _P()
+        n = C.c_int64()
+        self._check(self.lib.sse_grad_arena(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def train_apply(self, stream=None) -> float:
+        gn = C.c_float()
+        self._check(self.lib.sse_train_apply(self._h, C.byref(gn), _stream_ptr(stream)))
+        return gn.value
+
+    def lr_decay(self):
+        self._check(self.lib.sse_lr_decay(self._h))
+
+    def scalars(self) -> Tuple[float, int]:
+        lr = C.c_float()
+        gs = C.c_int64()
+        self._check(self.lib.sse_get_scalars(self._h, C.byref(lr), C.byref(gs)))
+        return lr.value, int(gs.value)
+
+    def set_scalars(self, lr: float, global_step: int):
+        self._check(self.lib.sse_set_scalars(self._h, lr, global_step))
+
+    def launch_count(self) -> int:
+        return int(self.lib.sse_launch_count(self._h))
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.sse_set_option(self._h, key.encode(), int(value)))

@@ -1,0 +1,124 @@
+"""GPU parity: the CUDA encoders (called through the C ABI) against the CPU oracle on the
+same seeded inputs.  Tolerances: encoder outputs within 1e-3 of the fp32 reference
+(north_star); the fp32 SIMT path is expected at ~1e-6 and is held to 2e-5."""
+import numpy as np
+import pytest
+
+import sse_ffi
+import sse_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 2e-5
+
+
+def make(mode, V, We, E, Hs, Ht, T, seed=1234, precision=sse_ffi.PRECISION_FP32, **kw):
+    p = O.init_params(mode, V, We, E, Hs, Ht, seed=seed, **{k: v for k, v in kw.items() if k.startswith("cnn") or k == "target_space_size"})
+    rng = np.random.default_rng(seed + 1)
+    for k in p:     # non-zero biases so the bias path is exercised
+        if k.endswith("/bias"):
+            p[k] = (rng.normal(size=p[k].shape) * 0.1).astype(np.float32)
+    h = sse_ffi.Handle(mode, V, We, E, Hs, Ht, T, precision=precision,
+                       target_space_size=kw.get("target_space_size", 0),
+                       cnn_filter_sizes=kw.get("cnn_filter_sizes", ()), cnn_num_filters=kw.get("cnn_num_filters", ()))
+    h.set_params(p)
+    return h, p
+
+
+# the real reference recipes (makefile:5,17,30,42) and the BASELINE shape
+SHAPES = [
+    ("dual-encoder", 3000, 50, 64, 96, 96, 80, 37),      # classification
+    ("shared-encoder", 2500, 40, 50, 96, 96, 50, 70),    # crosslingual
+    ("dual-encoder", 3000, 30, 64, 96, 96, 60, 130),     # ranking
+    ("dual-encoder", 4000, 256, 256, 256, 256, 50, 150), # BASE
+    ("dual-encoder", 500, 7, 5, 3, 9, 6, 1),             # odd everything, B = 1, Hs != Ht
+]
+
+
+@pytest.mark.parametrize("mode,V,We,E,Hs,Ht,T,B", SHAPES)
+def test_lstm_encode_matches_oracle(mode, V, We, E, Hs, Ht, T, B):
+    h, p = make(mode, V, We, E, Hs, Ht, T)
+    rng = np.random.default_rng(42)
+    for side, name in ((sse_ffi.SIDE_SRC, "src"), (sse_ffi.SIDE_TGT, "tgt")):
+        tok = np.concatenate([O.synth_tokens(rng, B - B // 2, T, V, "full"), O.synth_tokens(rng, B // 2, T, V, "real", 4.0)])
+        for normalize in (True, False):
+            got = h.encode_host(side, tok, normalize)
+            want = O.encode(p, mode, name, tok, normalize)
+            scale = 1.0 if normalize else max(1.0, np.abs(want).max())
+            assert np.abs(got - want).max() / scale < TOL_FP32, (side, normalize)
+    h.close()
+
+
+def test_edge_rows_all_pad_and_truncated():
+    mode, V, We, E, H, T = "dual-encoder", 300, 16, 16, 32, 10
+    h, p = make(mode, V, We, E, H, H, T)
+    rows = [O.pad_tokens([], T), O.pad_tokens(list(range(2, 40)), T), O.pad_tokens([7], T)]
+    tok = np.array(rows, np.int32)
+    got = h.encode_host(sse_ffi.SIDE_SRC, tok, True)
+    assert np.abs(got - O.encode(p, mode, "src", tok, True)).max() < TOL_FP32
+    h.close()
+
+
+def test_pad_prefix_skip_is_bit_identical():
+    mode, V, We, E, H, T = "dual-encoder", 2000, 64, 64, 128, 50
+    h, p = make(mode, V, We, E, H, H, T)
+    rng = np.random.default_rng(5)
+    tok = O.synth_tokens(rng, 90, T, V, "real", 3.0)          # queries: ~3 real tokens of 50
+    full = h.encode_host(sse_ffi.SIDE_SRC, tok, True)
+    h.set_option("pad_skip", 1)
+    skipped = h.encode_host(sse_ffi.SIDE_SRC, tok, True)
+    assert np.array_equal(full, skipped)
+    # weights change -> table must be invalidated
+    p2 = {k: (v * 1.01).astype(np.float32) for k, v in p.items()}
+    h.set_params(p2)
+    s2 = h.encode_host(sse_ffi.SIDE_SRC, tok, True)
+    assert np.abs(s2 - O.encode(p2, mode, "src", tok, True)).max() < TOL_FP32
+    h.close()
+
+
+def test_device_pointer_entry_point_matches_host_entry_point():
+    import torch
+    mode, V, We, E, H, T, B = "shared-encoder", 1000, 32, 48, 64, 20, 33
+    h, p = make(mode, V, We, E, H, H, T)
+    tok = O.synth_tokens(np.random.default_rng(2), B, T, V, "real", 6.0)
+    dtok = torch.from_numpy(tok).cuda()
+    out = torch.empty(B, E, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        h.encode(sse_ffi.SIDE_TGT, dtok, B, out, True, stream=st)
+    st.synchronize()
+    assert np.array_equal(out.cpu().numpy(), h.encode_host(sse_ffi.SIDE_TGT, tok, True))
+    h.close()
+
+
+@pytest.mark.parametrize("mode", ["dual-cnn", "source_only_cnn"])
+def test_cnn_encode_matches_oracle(mode):
+    V, We, E, T, B = 2000, 64, 48, 30, 41
+    kw = dict(cnn_filter_sizes=(3, 4, 5), cnn_num_filters=(64, 32, 48)) if mode == "dual-cnn" else dict(target_space_size=11)
+    h, p = make(mode, V, We, E, 0, 0, T, **kw)
+    rng = np.random.default_rng(8)
+    tok = O.synth_tokens(rng, B, T, V, "real", 9.0)
+    sides = [("src", 0)] + ([("tgt", 1)] if mode == "dual-cnn" else [])
+    for name, side in sides:
+        got = h.encode_host(side, tok, True)
+        assert np.abs(got - O.encode(p, mode, name, tok, True)).max() < TOL_FP32
+    if mode == "source_only_cnn":
+        with pytest.raises(sse_ffi.SseError):
+            h.encode_host(1, tok, True)
+    h.close()
+
+
+def test_param_round_trip_and_errors():
+    h, p = make("dual-encoder", 100, 8, 8, 16, 16, 12)
+    names = dict(h.param_names())
+    for k, v in p.items():
+        assert names[k] == v.shape
+        assert np.array_equal(h.get_param(k), v)
+        assert np.allclose(h.get_param(k + "/Adagrad"), 0.1)
+    with pytest.raises(sse_ffi.SseError):
+        h.set_param("nope", np.zeros(3, np.float32))
+    with pytest.raises(sse_ffi.SseError):
+        h.set_param("word_embedding", np.zeros((3, 3), np.float32))
+    with pytest.raises(sse_ffi.SseError):
+        h.encode_host(0, np.zeros((2, 5), np.int32))
+    h.close()
