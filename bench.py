@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Headline benchmark of the SSE hot path: queries/sec for encode + cosine top-k.
+
+Workload (BASELINE.json metric / north_star): cross-lingual style dual LSTM encoder
+(V=32000, We=H=E=256, T=50), an index of N target SSE vectors resident in HBM, query
+batches of Q token rows; one "step" = one query batch through the source encoder and the
+cosine top-k (k=10) of the whole index.  Tokens are synthetic in the FULL-length regime
+(one leading PAD, T-2 real tokens), i.e. every one of the T LSTM steps does real work.
+
+    python bench.py --gpus N --steps K --warmup W            (B200 arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+        the reference's own CPU path (numpy restatement of the TF1 encoder + the
+        reference's np.dot / full-argsort ranking) on the host cores, bounded sample.
+
+N > 1: launched under torchrun, one rank per GPU; the index is sharded by rows
+(N/G per rank, weak scaling = fixed N_local per GPU), every rank encodes the same Q
+queries, searches its shard, and ONE NCCL all-gather of the packed per-shard top-k
+([Q,k] scores + ids) is followed by the merge kernel.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for p in (REPO, os.path.join(REPO, "sequence-semantic-embedding_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+V, WE, H, E, T, K_TOP = 32000, 256, 256, 256, 50, 10
+F_LSTM = 2 * T * (WE + H) * 4 * H + 2 * H * E          # flops / sequence: 52 559 872
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--targets", type=int, default=1_000_000, help="index rows PER GPU (weak scaling)")
+    ap.add_argument("--queries", type=int, default=600, help="query rows per step (sse_evaluator.py:104 batch)")
+    ap.add_argument("--search", type=int, default=0, help="0 auto (tcgen05), 1 fp32 SIMT, 2 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-targets", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-queries", type=int, default=64)
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return pk.get("hbm_gbs", 6650.0), pk.get("bf16_tflops", 1590.0), "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_tokens(rng, B):
+    """FULL regime rows: [PAD] + (T-2 ids ~ Zipf-like over [2,V)) + [EOS]  (SURVEY 8d)."""
+    u = rng.random((B, T - 2))
+    ids = np.minimum(2 + np.floor((V - 2) * u ** 3), V - 1).astype(np.int32)
+    out = np.zeros((B, T), np.int32)
+    out[:, 1:T - 1] = ids
+    out[:, T - 1] = 1
+    return out
+
+
+def init_weights(seed=1234):
+    """Reference initialisers (sse_model.py:160, 227; BasicLSTMCell Glorot kernel / zero bias)."""
+    rng = np.random.default_rng(seed)
+    p = {"word_embedding": rng.uniform(-0.25, 0.25, (V, WE)).astype(np.float32)}
+    for scope, m in (("source_encoder", "src_M"), ("target_encoder", "tgt_M")):
+        lim = np.sqrt(6.0 / (WE + H + 4 * H))
+        p[scope + "/rnn/basic_lstm_cell/kernel"] = rng.uniform(-lim, lim, (WE + H, 4 * H)).astype(np.float32)
+        p[scope + "/rnn/basic_lstm_cell/bias"] = np.zeros(4 * H, np.float32)
+        p["%s/%s" % (scope, m)] = np.clip(rng.standard_normal((H, E)), -2, 2).astype(np.float32)
+    return p
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import sse_ffi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    Q, k = args.queries, K_TOP
+    n_local = args.targets
+    h = sse_ffi.Handle("dual-encoder", V, WE, E, H, H, T, predict_nbest=k, device=local, precision=sse_ffi.PRECISION_TC)
+    h.set_params(init_weights())
+    h.set_option("search", args.search)
+
+    # index shard: synthetic normalised target SSE vectors (seed 7 + rank), resident in HBM
+    g = torch.Generator(device="cuda").manual_seed(7 + rank)
+    idx = torch.randn(n_local, E, device="cuda", generator=g)
+    idx = idx / idx.norm(dim=1, keepdim=True)
+    h.index_set(idx, n_local, global_offset=rank * n_local)
+    del idx
+    rng = np.random.default_rng(42)             # same queries on every rank
+    n_batches = 4                                # rotate batches; the index (>= 256 MB bf16) exceeds nothing smaller than L2 at 100k+
+    tok_host = [torch.from_numpy(synth_tokens(rng, Q)).pin_memory() for _ in range(n_batches)]
+    tok_dev = [t.cuda() for t in tok_host]
+    enc = torch.empty(Q, E, device="cuda")
+    sc = torch.empty(Q, k, device="cuda")
+    ix = torch.empty(Q, k, device="cuda", dtype=torch.int32)
+    packed = torch.empty(Q, 2 * k, device="cuda")
+    gathered = torch.empty(world, Q, 2 * k, device="cuda") if world > 1 else None
+    fs = torch.empty(Q, k, device="cuda")
+    fi = torch.empty(Q, k, device="cuda", dtype=torch.int32)
+    out_s_host = torch.empty(Q, k).pin_memory()
+    out_i_host = torch.empty(Q, k, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def step_device(b):
+        h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Q, enc, True, stream)
+        h.search(enc, Q, k, sc, ix, stream)
+        if world > 1:
+            packed[:, :k] = sc
+            packed[:, k:] = ix.view(torch.float32)
+            dist.all_gather_into_tensor(gathered, packed)
+            cs = gathered[:, :, :k].permute(1, 0, 2).reshape(Q, world * k).contiguous()
+            ci = gathered[:, :, k:].permute(1, 0, 2).reshape(Q, world * k).contiguous().view(torch.int32)
+            h.merge_topk(cs, ci, Q, world * k, k, fs, fi, stream)
+
+    def step_e2e(b):
+        tok_dev[b].copy_(tok_host[b], non_blocking=True)               # H2D of the step's inputs
+        step_device(b)
+        src_s, src_i = (fs, fi) if world > 1 else (sc, ix)
+        out_s_host.copy_(src_s, non_blocking=True)                     # D2H of the step's result
+        out_i_host.copy_(src_i, non_blocking=True)
+        stream.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for w in range(warmup):
+            fn(w % n_batches)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s % n_batches)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = h.launch_count()
+    ms_dev = timed(step_device, args.steps, max(args.warmup, 3))
+    launches = h.launch_count() - l0
+    launches_per_step = launches / float(args.steps + max(args.warmup, 3))
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+
+    # dominant kernel (the index scan) timed alone, CUDA events on the launching stream, for the roofline
+    h.encode(sse_ffi.SIDE_SRC, tok_dev[0], Q, enc, True, stream)
+    for _ in range(3):
+        h.search(enc, Q, k, sc, ix, stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(5, args.steps)
+    e0.record()
+    for _ in range(reps):
+        h.search(enc, Q, k, sc, ix, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_search = e0.elapsed_time(e1) / reps
+    e0.record()
+    for _ in range(reps):
+        h.encode(sse_ffi.SIDE_SRC, tok_dev[0], Q, enc, True, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_enc = e0.elapsed_time(e1) / reps
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm_gbs, bf16_tf, src = load_peaks()
+    use_tc = args.search != 1
+    flops = 2.0 * Q * n_local * E
+    bytes_alg = n_local * E * (2 if use_tc else 4) + Q * E * 4 + Q * k * 8
+    t_s = ms_search * 1e-3
+    tensor_bound_s = flops / (bf16_tf * 1e12)
+    hbm_bound_s = bytes_alg / (hbm_gbs * 1e9)
+    if use_tc and tensor_bound_s >= hbm_bound_s:
+        roof = {"bound": "tensor", "achieved": flops / t_s / 1e12, "peak": bf16_tf, "unit": "TFLOP/s"}
+    else:
+        roof = {"bound": "hbm", "achieved": bytes_alg / t_s / 1e9, "peak": hbm_gbs, "unit": "GB/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["peak_source"] = src
+    roof["kernel"] = "search (prep+sample scan+select_tau+filter scan+finalize)" if use_tc else "search_simt_kernel+merge"
+    roof["ms_per_launch"] = ms_search
+    roof["algorithmic"] = {"flops": flops, "bytes": bytes_alg}
+    roof["encoder"] = {"ms": ms_enc, "flops": Q * F_LSTM, "achieved_tflops": Q * F_LSTM / (ms_enc * 1e-3) / 1e12,
+                       "kernel": "lstm_step_kernel x T (fp32 SIMT) + sgemm + l2norm"}
+
+    total_q = Q * args.steps
+    out = {
+        "metric": "queries/sec encode+cosine-top-k", "value": total_q / (ms_dev * 1e-3), "unit": "queries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 scan + fp32 re-rank; fp32 encoder" if use_tc else "f32",
+        "data": "synthetic",
+        "config": {"workload": "dual LSTM encoder V=32000 We=H=E=256 T=50 (FULL-length rows), Q=%d queries/step, "
+                               "cosine top-%d over N=%d targets per GPU (%d total)" % (Q, k, n_local, n_local * world),
+                   "targets_per_gpu": n_local, "targets_total": n_local * world, "queries_per_step": Q, "k": k,
+                   "parallelism": "index-shard x%d + 1 NCCL all-gather of [Q,k]" % world if world > 1 else "single GPU",
+                   "l2": "index shard (%.0f MB) is re-streamed every step and exceeds L2 (126 MB); query batches rotate" %
+                         (bytes_alg / 1e6)},
+        "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * T * 4,
+                "d2h_bytes_per_step": Q * k * 8, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(round(launches_per_step * args.steps)),
+        "clocks": clocks,
+        "roofline": roof,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_reference(args.cpu_sample_queries, args.cpu_sample_targets, runs=1)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference(Qs, Ns, runs=1):
+    """The reference's CPU path on a bounded sample: numpy restatement of the TF1 LSTM encoder
+    (oracle, BLAS threads = all cores) + the reference's float64 np.dot and full argsort
+    (sse_evaluator.py:110-111, data_utils.py:263-267).  queries/s = Q / (t_encode + t_dot + t_sort)."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import sse_oracle as O
+    cores = os.cpu_count() or 1
+    p = init_weights()
+    rng = np.random.default_rng(42)
+    tok = synth_tokens(rng, Qs)
+    r2 = np.random.default_rng(7)
+    tgt = r2.standard_normal((Ns, E)).astype(np.float32)
+    tgt /= np.linalg.norm(tgt, axis=1, keepdims=True)
+    tgt64 = tgt.astype(np.float64)                 # Evaluator parses the index into float64
+    best = None
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        enc = O.encode(p, "dual-encoder", "src", tok, True)
+        t1 = time.perf_counter()
+        d = np.dot(enc, tgt64.T)
+        t2 = time.perf_counter()
+        O.get_sorted_results(d)
+        t3 = time.perf_counter()
+        cur = (t3 - t0, t1 - t0, t2 - t1, t3 - t2)
+        best = cur if best is None or cur[0] < best[0] else best
+    return {"value": Qs / best[0], "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": "Q=%d queries x N=%d targets (same model shape; encode %.2fs + np.dot f64 %.2fs + full argsort %.2fs); "
+                      "fewer queries per batch than the B200 arm, same index size unless N was capped" %
+                      (Qs, Ns, best[1], best[2], best[3])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Qs, Ns = args.cpu_sample_queries, min(args.targets, args.cpu_sample_targets)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # keep the whole run within a few minutes: one warm-up + at most 3 timed steps of the bounded sample
+    steps = min(steps, 3)
+    warm = min(warm, 1)
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    for _ in range(warm):
+        cpu_reference(Qs, Ns)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(steps):
+        last = cpu_reference(Qs, Ns)
+    dt = time.perf_counter() - t0
+    val = Qs * steps / dt
+    out = {"impl": "reference", "metric": "queries/sec encode+cosine-top-k", "value": val, "unit": "queries/s",
+           "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32 encoder / f64 scoring", "data": "synthetic",
+           "config": {"workload": "dual LSTM encoder V=32000 We=H=E=256 T=50 (FULL-length rows), CPU bounded sample "
+                                  "Q=%d x N=%d (B200 arm: Q=%d x N=%d per GPU)" % (Qs, Ns, args.queries, args.targets)},
+           "cpu_baseline": dict(last, value=val),
+           "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

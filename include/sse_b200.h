@@ -170,7 +170,7 @@ int sse_train_step(sse_handle* h, const int32_t* src, const int32_t* tgt, const 
 int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const float* labels, int B,
                     int B_global, float* loss_host, float* acc_host, void* stream);
 int sse_grad_arena(sse_handle* h, float** dev_ptr_out, int64_t* n_floats_out);
-int sse_train_apply(sse_handle* h, float* gnorm_host, void* stream);
+int sse_train_apply(sse_handle* h, float* loss_host, float* acc_host, float* gnorm_host, void* stream);
 /* learning_rate_decay_op, sse_model.py:123-124 */
 int sse_lr_decay(sse_handle* h);
 int sse_get_scalars(sse_handle* h, float* learning_rate, int64_t* global_step);

@@ -186,7 +186,7 @@ def lstm_last_state(tokens: np.ndarray, emb: np.ndarray, K: np.ndarray, b: np.nd
     tokens = np.asarray(tokens)
     B, T = tokens.shape
     H = K.shape[1] // 4
-    emb = emb.astype(dtype); K = K.astype(dtype); b = b.astype(dtype)
+    emb = emb.astype(dtype, copy=False); K = K.astype(dtype, copy=False); b = b.astype(dtype, copy=False)
     c = np.zeros((B, H), dtype); h = np.zeros((B, H), dtype)
     one = dtype(1.0)
     hs, cs, gates = [], [], []

@@ -81,7 +81,7 @@ _SIGNATURES = {
                                  C.POINTER(C.c_float), _P]),
     "sse_train_grads": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
     "sse_grad_arena": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
-    "sse_train_apply": (C.c_int, [_P, C.POINTER(C.c_float), _P]),
+    "sse_train_apply": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
     "sse_lr_decay": (C.c_int, [_P]),
     "sse_get_scalars": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "sse_set_scalars": (C.c_int, [_P, C.c_float, C.c_int64]),
@@ -314,10 +314,13 @@ class Handle:
         self._check(self.lib.sse_grad_arena(self._h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
 
-    def train_apply(self, stream=None) -> float:
-        gn = C.c_float()
-        self._check(self.lib.sse_train_apply(self._h, C.byref(gn), _stream_ptr(stream)))
-        return gn.value
+    def train_apply(self, stream=None, want_scalars: bool = True):
+        loss, acc, gn = C.c_float(), C.c_float(), C.c_float()
+        if not want_scalars:
+            self._check(self.lib.sse_train_apply(self._h, None, None, None, _stream_ptr(stream)))
+            return None
+        self._check(self.lib.sse_train_apply(self._h, C.byref(loss), C.byref(acc), C.byref(gn), _stream_ptr(stream)))
+        return loss.value, acc.value, gn.value
 
     def lr_decay(self):
         self._check(self.lib.sse_lr_decay(self._h))
