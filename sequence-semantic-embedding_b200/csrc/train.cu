@@ -334,8 +334,8 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
     embed_scatter_kernel<<<148 * 4, 256, 0, st>>>(tok, B, T, dXH, ld, We, G, touched, scalars);
     ++h->launches;
   }
-  sumsq_kernel<<<148 * 2, 256, 0, st>>>(arena, h->grad_floats, scalars);
-  ++h->launches;
+  // NOTE: the dense part of the global norm is taken in sse_train_apply, AFTER any cross-rank
+  // all-reduce of the arena (|sum g|^2 != sum |g|^2); the un-merged embedding slices are additive.
   SSE_CUDA_OK(cudaGetLastError());
   if (loss_host || acc_host) {
     float sc[4];
@@ -366,6 +366,8 @@ int sse_train_apply(sse_handle* h, float* loss_host, float* acc_host, float* gno
   float* touched = G + (size_t)V * We;
   float* scalars = touched + V;
   const float lr = h->learning_rate, max_norm = 5.0f;   // self.max_gradient_norm, sse_model.py:117
+  sumsq_kernel<<<148 * 2, 256, 0, st>>>(arena, h->grad_floats, scalars);
+  ++h->launches;
   for (int i = 0; i < h->n_vars; ++i) {
     Param& p = h->params[i];
     if (p.grad_off < 0) continue;

@@ -1,0 +1,81 @@
+# coding=utf-8
+"""Interactive n-best demo (re-host of reference sse_demo.py:59-138).  The query is encoded with
+the UN-normalised source embedding (sse_demo.py:123) and scored against the normalised index;
+scoring + ranking is the fused GPU top-k instead of np.dot + full sort."""
+from __future__ import print_function
+
+import argparse
+import codecs
+import os
+import sys
+
+import numpy as np
+
+import data_utils
+import sse_model
+import text_encoder
+
+
+def load_index(path):
+    """id, text, encoding rows of targetEncodingIndex.tsv (sse_demo.py:79-90)."""
+    ids, names, encs = [], {}, []
+    for line in codecs.open(path, "rt", "utf-8").readlines():
+        info = line.strip().split("\t")
+        if len(info) != 3:
+            print("Error in targetIndexFile! %s" % line)
+            continue
+        ids.append(info[0])
+        names[info[0]] = info[1]
+        encs.append(np.array(info[2].strip().split(","), dtype=np.float32))
+    return ids, names, np.array(encs, dtype=np.float32)
+
+
+class DemoSession(object):
+    def __init__(self, model_dir, indexFile):
+        if not os.path.exists(os.path.join(model_dir, indexFile)):
+            raise IOError("Index file does not exist!!!")
+        self.encoder = data_utils.load_vocabulary(model_dir)
+        self.targetIDs, self.names, encs = load_index(os.path.join(model_dir, indexFile))
+        self.cfg = data_utils.load_model_configs(model_dir)
+        self.sess = sse_model.Session()
+        self.model = sse_model.SSEModel(self.cfg)
+        ckpt = sse_model.get_checkpoint_state(model_dir)
+        if not ckpt:
+            raise IOError("Error!!!Could not load any model from specified folder: %s" % model_dir)
+        print("Reading model parameters from %s" % ckpt.model_checkpoint_path)
+        self.model.saver.restore(self.sess, ckpt.model_checkpoint_path)
+        self.model.handle.index_set(encs, global_offset=0)
+        self.T = int(self.cfg["max_seq_length"])
+
+    def query(self, sentence, nbest, normalize=False):
+        ids = self.encoder.encode(sentence.lower())
+        if len(ids) > self.T - 2:
+            print("Input sentence too long, max allowed is %d. Try to increase limit!!!!" % self.T)
+        toks = np.array([text_encoder.pad_tokens(ids, self.T)], dtype=np.int32)
+        k = min(nbest, len(self.targetIDs), 128)
+        scores, idx = self.model.handle.query_host(toks, k, normalize=normalize)
+        return [(self.targetIDs[j], float(s), self.names[self.targetIDs[j]]) for s, j in zip(scores[0], idx[0])]
+
+
+def demo(nbest, model_dir, indexFile):
+    d = DemoSession(model_dir, indexFile)
+    sys.stdout.write("\n\nPlease type some keywords to get related task results.\nType 'exit' to quit demo.\n > ")
+    sys.stdout.flush()
+    sentence = sys.stdin.readline()
+    while sentence and sentence.strip().lower() != "exit":
+        res = d.query(sentence.strip(), nbest)
+        print("Top %s Prediction results are:\n" % nbest)
+        for i, (tid, conf, name) in enumerate(res):
+            print("top%d:  %s , %f ,  %s " % (i + 1, tid, conf, name))
+        print("> ", end="")
+        sys.stdout.flush()
+        sentence = sys.stdin.readline()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("nbest", type=int, nargs="?", default=10)
+    ap.add_argument("--model_dir", default="models-classification")
+    ap.add_argument("--indexFile", default="targetEncodingIndex.tsv")
+    a = ap.parse_args()
+    demo(a.nbest, a.model_dir, a.indexFile)

@@ -97,7 +97,47 @@ def padding_fixture():
     print("padding.npz written; PAD/EOS =", text_encoder.PAD_ID, text_encoder.EOS_ID)
 
 
+
+
+def subword_fixture():
+    """Build a small vocabulary with the REAL reference builder on the qna data set and freeze
+    (vocabulary file, sample lines, ids) so the repo's own encoder can be checked against it."""
+    import tarfile
+    import tempfile
+    import tokenizer
+    tmp = tempfile.mkdtemp()
+    with tarfile.open("/root/reference/rawdata-qna/DataSet.tar.gz") as t:
+        t.extractall(tmp)
+    root = tmp
+    for dp, dn, fn in os.walk(tmp):
+        if "targetIDs" in fn:
+            root = dp
+    lines = []
+    for name in ("TrainPairs", "targetIDs"):
+        for line in open(os.path.join(root, name), encoding="utf-8"):
+            lines.append(line.strip().split("\t")[0].lower())
+    corpus = os.path.join(tmp, "c.Corpus")
+    with open(corpus, "w", encoding="utf-8") as f:
+        f.write("\n".join(lines))
+    counts = tokenizer.corpus_token_counts(corpus, 2000000, split_on_newlines=True)
+    enc = text_encoder.SubwordTextEncoder.build_to_target_size(600, counts, 2, 1000)
+    vocab_path = os.path.join(HERE, "subword_vocab.txt")
+    enc.store_to_file(vocab_path)
+    sample = lines[:40] + ["Dude - that's so cool.", "snow_man \\ x_y 3.14 é中 zzzqqq", "", " ", "a  b"]
+    ids = [enc.encode(s) for s in sample]
+    width = max(len(i) for i in ids)
+    arr = np.full((len(ids), width), -1, np.int32)
+    for r, i in enumerate(ids):
+        arr[r, : len(i)] = i
+    import json
+    with open(os.path.join(HERE, "subword_samples.json"), "w", encoding="utf-8") as f:
+        json.dump(sample, f, ensure_ascii=False)
+    np.savez_compressed(os.path.join(HERE, "subword.npz"), ids=arr, vocab_size=enc.vocab_size)
+    print("subword fixture: vocab", enc.vocab_size, "samples", len(sample))
+
+
 if __name__ == "__main__":
     ranking_fixture()
     index_format_fixture()
     padding_fixture()
+    subword_fixture()
