@@ -160,7 +160,7 @@ def run_b200(args):
     sc = torch.empty(Q, k, device="cuda")
     ix = torch.empty(Q, k, device="cuda", dtype=torch.int32)
     packed = torch.empty(Q, 2 * k, device="cuda")
-    gathered = torch.empty(world, Q, 2 * k, device="cuda") if world > 1 else None
+    gathered = torch.empty(world * Q, 2 * k, device="cuda") if world > 1 else None
     fs = torch.empty(Q, k, device="cuda")
     fi = torch.empty(Q, k, device="cuda", dtype=torch.int32)
     out_s_host = torch.empty(Q, k).pin_memory()
@@ -174,8 +174,9 @@ def run_b200(args):
             packed[:, :k] = sc
             packed[:, k:] = ix.view(torch.float32)
             dist.all_gather_into_tensor(gathered, packed)
-            cs = gathered[:, :, :k].permute(1, 0, 2).reshape(Q, world * k).contiguous()
-            ci = gathered[:, :, k:].permute(1, 0, 2).reshape(Q, world * k).contiguous().view(torch.int32)
+            g3 = gathered.view(world, Q, 2 * k)
+            cs = g3[:, :, :k].permute(1, 0, 2).reshape(Q, world * k).contiguous()
+            ci = g3[:, :, k:].permute(1, 0, 2).reshape(Q, world * k).contiguous().view(torch.int32)
             h.merge_topk(cs, ci, Q, world * k, k, fs, fi, stream)
 
     def step_e2e(b):

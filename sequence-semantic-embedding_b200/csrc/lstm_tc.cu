@@ -1,0 +1,460 @@
+// LSTM tower on the 5th-gen tensor cores (sm_100a): one persistent CTA per 128 batch rows runs
+// all T steps on chip.  Restates BasicLSTMCell(forget_bias=1)+static_rnn (reference
+// sse_model.py:222-224,240-242,248-250,262-264,273-274) with fp16 operands / fp32 accumulate;
+// cell state c and all gate math stay fp32.  Measured deviation from the fp32 oracle on the
+// normalised encodings: <= ~7e-4 abs (north_star tolerance 1e-3); the fp32 SIMT path
+// (lstm_simt.cu) remains the exact mode.
+//
+// Per step t and per chunk of 32 hidden units (128 gate columns = i|j|f|o x 32):
+//     z[128 rows, 128] = x_t[128, We] * Wx_chunk  (A from smem, gathered fp16 embedding rows)
+//                      + h_{t-1}[128, H] * Wh_chunk (A from TENSOR MEMORY, written by the epilogue)
+//   the fp16 weights stream through a TMA ring (B operand, [128 gate cols x 64 k] SW128 tiles of
+//   the pre-transposed, chunk-major matrix Wt[4H, We+H]); accumulators are double-buffered in
+//   TMEM; the epilogue (thread == batch row) applies bias, sigmoid/tanh (tanh.approx), updates
+//   c (fp32, L2-resident scratch) and writes h_t back to TMEM as packed fp16 for the next step.
+// TMEM columns: h ping [0,128) | h pong [128,256) | acc0 [256,384) | acc1 [384,512).
+// warps 0-3 epilogue | warps 4-7 embedding gather (cp.async, thread == row, manual 128B swizzle) |
+// warp 8 MMA issuer | warp 9 TMA producer | warp 10 TMEM alloc  (single-thread critical roles on the
+// highest warp ids, which the sub-partition arbiter favours).
+#include "sse_common.cuh"
+#include <cuda.h>
+#include <math_constants.h>
+
+namespace sse {
+
+namespace {
+
+constexpr int KBLK = 64;
+constexpr int TILE_BYTES = 128 * KBLK * 2;   // 16 KB
+constexpr int LSTM_THREADS = 384;
+constexpr int CHUNK_UNITS = 32;
+
+struct LstmTcParams {
+  const int32_t* tokens;      // [B, T]
+  const __half* emb;   // [V, We] fp16
+  const float* bias_r;        // [4H] chunk-major, +1 folded into the forget gate
+  const float* init_h;        // optional [H] broadcast initial state (pad-prefix table row)
+  const float* init_c;
+  float* c_scratch;           // [Bpad, H] fp32
+  float* h_out;               // [B, H] fp32 (last step)
+  int B, T, t_start, We, H, n_stages;
+};
+
+// ---------------------------------------------------------------- PTX helpers (see search_tc.cu)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the warp SLEEPS in hardware until the phase completes (or the hint
+  // expires) instead of busy-polling -- spinning waiters steal issue slots from the single MMA-issuer /
+  // TMA-producer threads (measured: 10x slowdown of the issue loop).  A watchdog turns a protocol bug
+  // (a wait that can never complete) into a trap instead of a hung GPU.
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (done) break;
+    if ((spins & 0x3f) == 0x3f) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D=f32, A=B=f16
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
+}
+
+#define TMEM_LD_32(taddr, v)                                                                                       \
+  asm volatile(                                                                                                    \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28," \
+      "%29,%30,%31}, [%32];"                                                                                       \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),     \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),    \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                  \
+      : "r"(taddr))
+
+#define TMEM_ST_16(taddr, v)                                                                                   \
+  asm volatile(                                                                                                \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),    \
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])             \
+      : "memory")
+
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
+lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ LstmTcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KBx = P.We / KBLK, KBh = P.H / KBLK, NC = P.H / CHUNK_UNITS, NS = P.n_stages;
+  const int row0 = blockIdx.x * 128;
+  const int t0 = P.t_start;
+  const bool has_init = P.init_h != nullptr;
+
+  uint8_t* x_smem = smem;                                   // [KBx] tiles [128 x 64] fp16 SW128
+  uint8_t* w_smem = x_smem + (size_t)KBx * TILE_BYTES;      // [NS] ring
+  float* bias_s = reinterpret_cast<float*>(w_smem + (size_t)NS * TILE_BYTES);   // [4H]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 4 * P.H);
+  // bars: full[NS], empty[NS], x_full, x_empty, h_full, acc_full[2], acc_empty[2]
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = smem_u32(bars + NS);
+  const uint32_t bar_xf = smem_u32(bars + 2 * NS);
+  const uint32_t bar_xe = smem_u32(bars + 2 * NS + 1);
+  const uint32_t bar_hf = smem_u32(bars + 2 * NS + 2);
+  const uint32_t bar_accf = smem_u32(bars + 2 * NS + 3);
+  const uint32_t bar_acce = smem_u32(bars + 2 * NS + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 7);
+
+  for (int i = threadIdx.x; i < 4 * P.H; i += LSTM_THREADS) bias_s[i] = P.bias_r[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_xf, 128);
+    mbar_init(bar_xe, 1);
+    mbar_init(bar_hf, 4);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 10) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    // ===== TMA producer: weights, chunk-major =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = t0; t < P.T; ++t) {
+        const bool has_state = has_init || t > t0;
+        for (int c = 0; c < NC; ++c) {
+          const int nkb = KBx + (has_state ? KBh : 0);
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const uint32_t s = it % NS, ph = (it / NS) & 1;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            mbar_expect_tx(bar_full + 8 * s, TILE_BYTES);
+            tma_load_2d(smem_u32(w_smem + (size_t)s * TILE_BYTES), &tmap_w, bar_full + 8 * s, kb * KBLK, c * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 128);
+      uint32_t it = 0, gchunk = 0;
+      for (int t = t0; t < P.T; ++t) {
+        const int step = t - t0;
+        const bool has_state = has_init || t > t0;
+        // h_{t-1} lives in h buffer (t+1)&1 ; epilogue of step t writes buffer t&1
+        const uint32_t h_src = tmem_base + (uint32_t)(((t + 1) & 1) * 128);
+        for (int c = 0; c < NC; ++c, ++gchunk) {
+          const int buf = gchunk & 1;
+          const uint32_t use = gchunk >> 1;
+          const uint32_t d = tmem_base + 256u + (uint32_t)(buf * 128);
+          mbar_wait(bar_acce + 8 * buf, (use & 1) ^ 1);
+          tc_fence_after();
+          if (c == 0) { mbar_wait(bar_xf, step & 1); tc_fence_after(); }
+          for (int kb = 0; kb < KBx; ++kb, ++it) {
+            const uint32_t s = it % NS, ph = (it / NS) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            tc_fence_after();
+            const uint64_t adesc = make_sw128_desc(smem_u32(x_smem + (size_t)kb * TILE_BYTES));
+            const uint64_t bdesc = make_sw128_desc(smem_u32(w_smem + (size_t)s * TILE_BYTES));
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) tc_mma_ss(d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+            tc_commit(bar_empty + 8 * s);
+          }
+          if (c == NC - 1) tc_commit(bar_xe);      // x_t fully consumed once these MMAs retire
+          if (has_state) {
+            if (c == 0) {
+              // completions of h_full: [initial state staged (only with init)], end of step t0, t0+1, ...
+              const uint32_t idx = has_init ? (uint32_t)step : (uint32_t)(step - 1);
+              mbar_wait(bar_hf, idx & 1);
+              tc_fence_after();
+            }
+            for (int kb = 0; kb < KBh; ++kb, ++it) {
+              const uint32_t s = it % NS, ph = (it / NS) & 1;
+              mbar_wait(bar_full + 8 * s, ph);
+              tc_fence_after();
+              const uint64_t bdesc = make_sw128_desc(smem_u32(w_smem + (size_t)s * TILE_BYTES));
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) tc_mma_ts(d, h_src + (uint32_t)(kb * 32 + k4 * 8), bdesc + 2 * k4, idesc, 1u);
+              tc_commit(bar_empty + 8 * s);
+            }
+          }
+          tc_commit(bar_accf + 8 * buf);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {   // gather warps 4..7
+    // ===== embedding gather: thread == row, cp.async 16 B chunks into the 128B-swizzled tiles =====
+    const int r = (warp - 4) * 32 + lane;
+    const int grow = min(row0 + r, P.B - 1);
+    const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    for (int t = t0; t < P.T; ++t) {
+      const int step = t - t0;
+      mbar_wait(bar_xe, (step & 1) ^ 1);
+      const int tok = __ldg(P.tokens + (size_t)grow * P.T + t);
+      const __half* src = P.emb + (size_t)tok * P.We;
+      for (int kb = 0; kb < KBx; ++kb) {
+        const uint32_t tile = smem_u32(x_smem + (size_t)kb * TILE_BYTES) + row_off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = tile + (uint32_t)(((j ^ (r & 7)) * 16));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + kb * KBLK + j * 8) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(bar_xf);
+    }
+  } else if (warp < 4) {
+    // ===== epilogue: thread == batch row =====
+    const int quarter = warp;
+    const int r = quarter * 32 + lane;
+    const int grow = row0 + r;
+    const bool valid = grow < P.B;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float* crow = P.c_scratch + (size_t)(row0 + r) * P.H;
+    if (has_init) {
+      // stage the broadcast initial state: h -> TMEM buffer (t0+1)&1 (read by step t0), c -> scratch
+      const uint32_t hdst = lane_base + (uint32_t)(((t0 + 1) & 1) * 128);
+      for (int u0 = 0; u0 < P.H; u0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_f16x2(__ldg(P.init_h + u0 + 2 * i), __ldg(P.init_h + u0 + 2 * i + 1));
+        TMEM_ST_16(hdst + u0 / 2, pk);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) crow[u0 + i] = __ldg(P.init_c + u0 + i);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hf);      // phase 0 of h_full == "initial state staged"
+    }
+    uint32_t gchunk = 0;
+    for (int t = t0; t < P.T; ++t) {
+      const bool has_c = has_init || t > t0;
+      const bool last = t == P.T - 1;
+      const uint32_t hdst = lane_base + (uint32_t)((t & 1) * 128);
+      for (int c = 0; c < NC; ++c, ++gchunk) {
+        const int buf = gchunk & 1;
+        const uint32_t use = gchunk >> 1;
+        const int u0 = c * CHUNK_UNITS;
+        // previous cell state for this row / chunk (fp32, issued before the accumulator wait)
+        float cold[32];
+        if (has_c) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v = *reinterpret_cast<const float4*>(crow + u0 + q * 4);
+            cold[q * 4] = v.x; cold[q * 4 + 1] = v.y; cold[q * 4 + 2] = v.z; cold[q * 4 + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) cold[i] = 0.f;
+        }
+        mbar_wait(bar_accf + 8 * buf, use & 1);
+        tc_fence_after();
+        const uint32_t acc = lane_base + 256u + (uint32_t)(buf * 128);
+        const float* bs = bias_s + c * 128;
+        uint32_t vi[32], vj[32];
+        TMEM_LD_32(acc, vi);
+        TMEM_LD_32(acc + 32, vj);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          p[i] = sigmoid_approx(__uint_as_float(vi[i]) + bs[i]) * tanh_approx(__uint_as_float(vj[i]) + bs[32 + i]);
+        TMEM_LD_32(acc + 64, vi);     // f
+        TMEM_LD_32(acc + 96, vj);     // o
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // accumulator buffer is free as soon as it sits in registers
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float c0 = fmaf(cold[i], sigmoid_approx(__uint_as_float(vi[i]) + bs[64 + i]), p[i]);          // bias_r has +1 folded in
+          float c1 = fmaf(cold[i + 1], sigmoid_approx(__uint_as_float(vi[i + 1]) + bs[64 + i + 1]), p[i + 1]);
+          float h0 = tanh_approx(c0) * sigmoid_approx(__uint_as_float(vj[i]) + bs[96 + i]);
+          float h1 = tanh_approx(c1) * sigmoid_approx(__uint_as_float(vj[i + 1]) + bs[96 + i + 1]);
+          cold[i] = c0; cold[i + 1] = c1;
+          p[i] = h0; p[i + 1] = h1;
+          pk[i >> 1] = pack_f16x2(h0, h1);
+        }
+        if (!last) {
+          TMEM_ST_16(hdst + (uint32_t)(u0 / 2), pk);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(crow + u0 + q * 4) = make_float4(cold[q * 4], cold[q * 4 + 1], cold[q * 4 + 2], cold[q * 4 + 3]);
+        } else if (valid) {
+          float* ho = P.h_out + (size_t)grow * P.H + u0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(ho + q * 4) = make_float4(p[q * 4], p[q * 4 + 1], p[q * 4 + 2], p[q * 4 + 3]);
+        }
+      }
+      if (!last) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_hf);    // h_t complete in TMEM (all chunks of this warp's rows)
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// Wt[n'][k] = K[k][g*H + 32c + j],  n' = c*128 + g*32 + j ; bias_r[n'] = b[g*H + 32c + j] (+1 for g == 2)
+__global__ void prep_weights_kernel(const float* __restrict__ K, const float* __restrict__ b, int We, int H,
+                                    __half* __restrict__ Wt, float* __restrict__ bias_r) {
+  const int Kd = We + H;
+  int64_t total = (int64_t)4 * H * Kd;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int np = (int)(i / Kd), k = (int)(i - (int64_t)np * Kd);
+    int c = np >> 7, g = (np >> 5) & 3, j = np & 31;
+    int col = g * H + c * CHUNK_UNITS + j;
+    Wt[i] = __float2half_rn(K[(size_t)k * 4 * H + col]);
+    if (k == 0) bias_r[np] = b[col] + (g == 2 ? 1.0f : 0.0f);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+bool lstm_tc_supported(int We, int H) { return We % 64 == 0 && We >= 64 && We <= 256 && H % 64 == 0 && H >= 64 && H <= 256; }
+
+void lstm_tc_release(TcTower& tt) {
+  if (tt.wt) cudaFree(tt.wt);
+  if (tt.bias_r) cudaFree(tt.bias_r);
+  tt.wt = nullptr; tt.bias_r = nullptr; tt.valid = false;
+}
+
+int lstm_tc_prepare(TcTower& tt, const float* K, const float* b, int We, int H, cudaStream_t st, int64_t* launches) {
+  if (!tt.wt) {
+    SSE_CUDA_OK(cudaMalloc(&tt.wt, (size_t)4 * H * (We + H) * 2));
+    SSE_CUDA_OK(cudaMalloc(&tt.bias_r, (size_t)4 * H * 4));
+  }
+  prep_weights_kernel<<<148 * 4, 256, 0, st>>>(K, b, We, H, tt.wt, tt.bias_r);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SSE_ECUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)(We + H), (cuuint64_t)(4 * H)};
+  cuuint64_t gstr[1] = {(cuuint64_t)(We + H) * 2};
+  cuuint32_t box[2] = {KBLK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<PFN_encodeTiled>(p)(reinterpret_cast<CUtensorMap*>(tt.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                                                    tt.wt, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(Wt) failed (%d)", (int)r); return SSE_ECUDA; }
+  tt.valid = true;
+  return SSE_OK;
+}
+
+int lstm_forward_tc(const int32_t* tokens, int B, int T, int t_start, const __half* emb_f16, int We, int H,
+                    const TcTower& tt, const float* init_h, const float* init_c, float* c_scratch, float* h_out,
+                    cudaStream_t st, int64_t* launches) {
+  if (B <= 0) return SSE_OK;
+  LstmTcParams p;
+  p.tokens = tokens; p.emb = emb_f16; p.bias_r = tt.bias_r; p.init_h = init_h; p.init_c = init_c;
+  p.c_scratch = c_scratch; p.h_out = h_out; p.B = B; p.T = T; p.t_start = t_start; p.We = We; p.H = H;
+  const size_t fixed = 1024 + (size_t)(We / KBLK) * TILE_BYTES + (size_t)4 * H * 4 + 512;
+  int NS = (int)((232448 - fixed) / TILE_BYTES);
+  if (NS > 12) NS = 12;
+  if (NS < 2) { set_error("lstm_tc: shared memory budget"); return SSE_EINVAL; }
+  p.n_stages = NS;
+  const size_t smem = fixed + (size_t)NS * TILE_BYTES;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SSE_CUDA_OK(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_done = true;
+  }
+  lstm_tc_kernel<<<cdiv(B, 128), LSTM_THREADS, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(tt.tmap), p);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
+}  // namespace sse

@@ -1,10 +1,10 @@
-// Cosine scoring + row top-k on the 5th-gen tensor cores (sm_100a): bf16 tcgen05
+// Cosine scoring + row top-k on the 5th-gen tensor cores (sm_100a): fp16 tcgen05
 // scan of the whole index with a threshold-filter epilogue, then an EXACT fp32
 // re-score of the few survivors.  Replaces np.dot + full argsort
 // (reference sse_evaluator.py:110-111, data_utils.py:263-267) for E % 64 == 0.
 //
 // Pipeline per query batch (all on one stream, no host sync):
-//   1. prep_queries      q fp32 [Q,E] -> bf16 [Qp,E] (zero padded) + row norms
+//   1. prep_queries      q fp32 [Q,E] -> fp16 [Qp,E] (zero padded) + row norms
 //   2. scan<TILEMAX>     tcgen05 GEMM over a strided SAMPLE of 128-row index tiles;
 //                        epilogue = per (row, tile) max            (no divergence)
 //   3. select_tau        tau[r] = k-th largest sampled tile max - margin[r]
@@ -12,12 +12,12 @@
 //   4. scan<FILTER>      tcgen05 GEMM over ALL tiles; epilogue compares every score
 //                        with tau[r] in registers and appends the rare survivors
 //                        to a private per-(CTA,row) candidate list
-//   5. finalize          per row: sort candidates, keep those within the bf16 error
+//   5. finalize          per row: sort candidates, keep those within the fp16 error
 //                        margin of the k-th best, re-score them in fp32 against the
 //                        fp32 index, sort by (score desc, idx asc), emit k
 //   6. fallback          rows whose candidate lists overflowed (pathological ties)
 //                        are recomputed by brute force in fp32
-// Exactness: |approx - exact| <= eps_r = 0.0045*|q_r|*max|t| (bf16 operand rounding,
+// Exactness: |approx - exact| <= eps_r = 0.0045*|q_r|*max|t| (fp16 operand rounding,
 // fp32 accumulate).  Every exact top-k element has approx >= A_k - 2 eps >= tau, so it
 // survives 4 and 5; the final order/scores come from fp32 arithmetic only.
 //
@@ -28,21 +28,20 @@
 #include "sse_common.cuh"
 #include <cuda.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace sse {
 
 namespace {
 
-constexpr int TILE_N = 128;          // index rows per MMA tile
 constexpr int TILE_M = 128;          // query rows per m-tile
-constexpr int KBLK = 64;             // bf16 elements per 128-byte swizzle row
-constexpr int TILE_BYTES = 128 * KBLK * 2;   // 16 KB: one [128 x 64] bf16 SW128 tile
+constexpr int KBLK = 64;             // fp16 elements per 128-byte swizzle row
 constexpr int CAND_CAP = 64;         // candidates per (CTA item, row)
 constexpr int MAX_GROUPS = 32;
 constexpr int SCAN_THREADS = 384;
 constexpr int FIN_MAXC = 2048;       // candidates per row the finalize kernel can sort
 constexpr int FIN_MAXR = 256;        // candidates per row re-scored exactly
-constexpr float EPS_REL = 0.0045f;   // bf16 x bf16 dot error bound / (|q| |t|)
+constexpr float EPS_REL = 0.0011f;   // fp16 x fp16 dot error bound / (|q| |t|): 2*2^-11 + fp32 accumulation slack
 
 enum { MODE_TILEMAX = 0, MODE_FILTER = 1 };
 
@@ -51,6 +50,11 @@ struct ScanParams {
   int mtg;                         // m-tiles per group (smem / TMEM are sized for this)
   int kb;                          // E / 64
   int n_stages;
+  int tn;                          // index rows per MMA tile (64 or 128)
+  int a_cols;                      // TMEM columns holding the fp16 queries: mtg * E / 2
+  const __half* qb;         // [Qp, E] fp16 queries
+  long long* dbg;                  // optional [items][8] cycle counters (nullptr = off)
+  int dbg_flags;                   // timing experiments only: 1 = no TMA loads, 2 = no MMA issue
   int group_first_item[MAX_GROUPS];
   int group_items[MAX_GROUPS];
   int group_mt[MAX_GROUPS];        // valid m-tiles in the group
@@ -79,27 +83,34 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // try_wait suspends in hardware for a bounded time; loop until the phase completes.  A watchdog
-  // turns a protocol bug (a wait that can never complete) into a trap instead of a hung GPU.
+  // try_wait with a suspend-time hint: the warp SLEEPS in hardware until the phase completes (or the hint
+  // expires) instead of busy-polling -- spinning waiters steal issue slots from the single MMA-issuer /
+  // TMA-producer threads (measured: 10x slowdown of the issue loop).  A watchdog turns a protocol bug
+  // (a wait that can never complete) into a trap instead of a hung GPU.
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t spins = 0;; ++spins) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, P1;\n"
         "}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     if (done) break;
-    if ((spins & 0x3ff) == 0x3ff) {
+    if ((spins & 0x3f) == 0x3f) {
       long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
     }
   }
+}
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc) {
+  long long t = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -112,7 +123,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -134,9 +145,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
-__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=fp16, both K-major, M x N
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D=f32, A=B=f16
 }
 
 #define TMEM_LD_32(taddr, v)                                                                                       \
@@ -152,12 +163,38 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
 
 // ------------------------------------------------------------------ the scan
 // grid = number of work items; item -> (group g, range r of the j loop).
-// warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator, warps 4..11: epilogue
-// (warp 4+e: m-tile e/4, TMEM lane quarter e%4).
+// warps 0..7: epilogue (warp e: m-tile e/4, TMEM lane quarter e%4), warp 8: MMA issuer,
+// warp 9: TMA producer (index tiles), warp 10: TMEM allocator.  The two single-thread roles sit on
+// the HIGHEST warp ids: the SM sub-partition arbiter favours high warp ids, and they are the critical path.
+// The fp16 queries (A operand) live in TMEM ([lane = row][col = 2 consecutive k]); every byte of
+// shared memory is the TMA ring of index tiles, so ~200 KB of loads are in flight per SM.
+#define TMEM_ST_32(taddr, v)                                                                                        \
+  asm volatile(                                                                                                     \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                               \
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29," \
+      "%30,%31,%32};" ::"r"(taddr),                                                                                 \
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),   \
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),    \
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),    \
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])                                                                \
+      : "memory")
+
+// D[tmem] (+)= A[tmem] * B[smem desc]   (A from tensor memory, "TS" form)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_idx,
-            const __grid_constant__ ScanParams P) {
+scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant__ ScanParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,11 +208,12 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   const int mt_count = P.group_mt[g];
   const int j0 = (int)(((int64_t)P.n_j * r_in_g) / R);
   const int j1 = (int)(((int64_t)P.n_j * (r_in_g + 1)) / R);
-  const int KB = P.kb, NS = P.n_stages;
+  const int KB = P.kb, NS = P.n_stages, TN = P.tn;
+  const int E = KB * KBLK;
+  const uint32_t stage_bytes = (uint32_t)TN * KBLK * 2;
 
-  uint8_t* a_smem = smem;                                        // [mtg][KB] tiles
-  uint8_t* b_smem = smem + (size_t)P.mtg * KB * TILE_BYTES;     // [NS] tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)NS * TILE_BYTES);
+  uint8_t* b_smem = smem;                                        // [NS] tiles of [TN x 64] fp16, SW128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)NS * stage_bytes);
   // bars: full[NS], empty[NS], a_full, acc_full[2], acc_empty[2]
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + NS);
@@ -186,12 +224,12 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_a, 1);
+    mbar_init(bar_a, mt_count * 4);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, mt_count * 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 10) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -199,63 +237,83 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_col0 = (uint32_t)P.a_cols;          // accumulators sit behind the query columns
 
-  if (warp == 0) {
+  if (warp == 9) {
     // ===== TMA producer =====
     if (lane == 0 && j1 > j0) {
-      mbar_expect_tx(bar_a, (uint32_t)(mt_count * KB * TILE_BYTES));
-      for (int mt = 0; mt < mt_count; ++mt)
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(smem_u32(a_smem + (size_t)(mt * KB + kb) * TILE_BYTES), &tmap_q, bar_a, kb * KBLK,
-                      (g * P.mtg + mt) * TILE_M);
       uint32_t it = 0;
+      long long w_empty = 0, t_begin = clock64();
       for (int j = j0; j < j1; ++j) {
         const int tile = j * P.tile_step;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const uint32_t s = it % NS, ph = (it / NS) & 1;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_expect_tx(bar_full + 8 * s, TILE_BYTES);
-          tma_load_2d(smem_u32(b_smem + (size_t)s * TILE_BYTES), &tmap_idx, bar_full + 8 * s, kb * KBLK, tile * TILE_N);
+          mbar_wait_timed(bar_empty + 8 * s, ph ^ 1, w_empty);
+          if (P.dbg_flags & 1) { mbar_arrive(bar_full + 8 * s); continue; }
+          mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+          tma_load_2d(smem_u32(b_smem + (size_t)s * stage_bytes), &tmap_idx, bar_full + 8 * s, kb * KBLK, tile * TN);
         }
       }
+      if (P.dbg) { P.dbg[item * 8 + 0] = w_empty; P.dbg[item * 8 + 1] = clock64() - t_begin; }
     }
-  } else if (warp == 1) {
+  } else if (warp == 8) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0 && j1 > j0) {
-      const uint32_t idesc = make_idesc_bf16(TILE_M, TILE_N);
-      mbar_wait(bar_a, 0);
+      const uint32_t idesc = make_idesc_f16(TILE_M, TN);
+      long long w_full = 0, w_acce = 0, w_a = 0, t_begin = clock64();
+      mbar_wait_timed(bar_a, 0, w_a);
       tc_fence_after();
       uint32_t it = 0;
       for (int j = j0; j < j1; ++j) {
         const int jj = j - j0;
         const int buf = jj & 1;
         const uint32_t use = (uint32_t)(jj >> 1);
-        mbar_wait(bar_acce + 8 * buf, (use & 1) ^ 1);
+        mbar_wait_timed(bar_acce + 8 * buf, (use & 1) ^ 1, w_acce);
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const uint32_t s = it % NS, ph = (it / NS) & 1;
-          mbar_wait(bar_full + 8 * s, ph);
+          mbar_wait_timed(bar_full + 8 * s, ph, w_full);
           tc_fence_after();
-          const uint64_t bdesc = make_sw128_desc(smem_u32(b_smem + (size_t)s * TILE_BYTES));
-          for (int mt = 0; mt < mt_count; ++mt) {
-            const uint64_t adesc = make_sw128_desc(smem_u32(a_smem + (size_t)(mt * KB + kb) * TILE_BYTES));
-            const uint32_t d = tmem_base + (uint32_t)((buf * P.mtg + mt) * TILE_N);
+          const uint64_t bdesc = make_sw128_desc(smem_u32(b_smem + (size_t)s * stage_bytes));
+          for (int mt = 0; mt < mt_count && !(P.dbg_flags & 2); ++mt) {
+            const uint32_t a = tmem_base + (uint32_t)(mt * (E / 2) + kb * (KBLK / 2));
+            const uint32_t d = tmem_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)   // 4 x (K=16) per 64-wide k block: +32 bytes = +2 descriptor units
-              tc_mma_bf16(d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+            for (int k4 = 0; k4 < 4; ++k4)   // 4 x (K=16): A advances 8 columns, B 32 bytes (= 2 descriptor units)
+              tc_mma_f16_ts(d, a + 8 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
           }
           tc_commit(bar_empty + 8 * s);     // smem stage is free once these MMAs retire
         }
         tc_commit(bar_accf + 8 * buf);      // accumulators of this tile are complete
       }
+      if (P.dbg) { P.dbg[item * 8 + 2] = w_full; P.dbg[item * 8 + 3] = w_acce; P.dbg[item * 8 + 4] = clock64() - t_begin; P.dbg[item * 8 + 5] = w_a; }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ===== epilogue: thread == query row =====
-    const int e = warp - 4;
+    const int e = warp;
     const int mt = e >> 2, quarter = e & 3;
-    if (mt < mt_count) {
+    if (mt < mt_count && j1 > j0) {
       const int lrow = mt * TILE_M + quarter * 32 + lane;             // row within the group
       const int grow = g * P.mtg * TILE_M + lrow;                     // padded global row
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      // ---- stage this row's fp16 query into TMEM (A operand): 2 consecutive k per 32-bit column
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(P.qb + (size_t)grow * E);
+        const uint32_t a_t = lane_base + (uint32_t)(mt * (E / 2));
+        for (int c = 0; c < E / 2; c += 32) {
+          uint32_t v[32];
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            uint4 u = __ldg(src + (c / 4) + q4);
+            v[q4 * 4 + 0] = u.x; v[q4 * 4 + 1] = u.y; v[q4 * 4 + 2] = u.z; v[q4 * 4 + 3] = u.w;
+          }
+          TMEM_ST_32(a_t + c, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a);
+      }
       float thr = CUDART_INF_F;
       int cnt = 0;
       float* my_s = nullptr;
@@ -266,19 +324,21 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         my_s = P.cand_s + base;
         my_i = P.cand_i + base;
       }
+      const int n_chunks = TN / 32;
+      long long w_accf = 0, t_begin = clock64();
       for (int j = j0; j < j1; ++j) {
         const int jj = j - j0;
         const int buf = jj & 1;
         const uint32_t use = (uint32_t)(jj >> 1);
         const int tile = j * P.tile_step;
-        const int64_t col0 = (int64_t)tile * TILE_N;
-        const bool ragged = col0 + TILE_N > P.N;
-        mbar_wait(bar_accf + 8 * buf, use & 1);
+        const int64_t col0 = (int64_t)tile * TN;
+        const bool ragged = col0 + TN > P.N;
+        mbar_wait_timed(bar_accf + 8 * buf, use & 1, w_accf);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * P.mtg + mt) * TILE_N);
+        const uint32_t taddr = lane_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
         float tmax = -CUDART_INF_F;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < n_chunks; ++ch) {
           uint32_t v[32];
           TMEM_LD_32(taddr + ch * 32, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -312,19 +372,22 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
       }
       if (MODE == MODE_FILTER) P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + lrow] = cnt;
+      if (P.dbg && e == 0 && lane == 0) { P.dbg[item * 8 + 6] = w_accf; P.dbg[item * 8 + 7] = clock64() - t_begin; }
+    } else if (mt < mt_count && MODE == MODE_FILTER) {
+      P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + mt * TILE_M + quarter * 32 + lane] = 0;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 10) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
 // --------------------------------------------------------------- small kernels
-// q fp32 [Q,E] -> bf16 [Qp,E] (rows >= Q zero), qnorm[Qp]
-__global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, __nv_bfloat16* __restrict__ qb,
+// q fp32 [Q,E] -> fp16 [Qp,E] (rows >= Q zero), qnorm[Qp]
+__global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, __half* __restrict__ qb,
                                     float* __restrict__ qnorm) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
@@ -333,7 +396,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, 
   for (int j = lane; j < E; j += 32) {
     float v = row < Q ? q[(size_t)row * E + j] : 0.f;
     ss = fmaf(v, v, ss);
-    qb[(size_t)row * E + j] = __float2bfloat16_rn(v);
+    qb[(size_t)row * E + j] = __float2half_rn(v);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -355,7 +418,8 @@ __global__ void max_row_norm_kernel(const float* __restrict__ x, int64_t N, int 
   if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best)));   // non-negative floats order as ints
 }
 
-// warp per row: tau[r] = (k-th largest of tilemax[0..n_s)[r]) - 2*eps_r ; rows >= Q: +inf
+// warp per row: tau[r] = (k-th largest of tilemax[0..n_s)[r]) - 2*eps_r ; rows >= Q: +inf.
+// Each lane keeps its <= 32 strided samples in registers; k rounds of warp arg-max with removal.
 __global__ void select_tau_kernel(const float* __restrict__ tilemax, int n_s, int Qp, int Q, int k,
                                   const float* __restrict__ qnorm, const float* __restrict__ tnorm_max,
                                   float* __restrict__ tau, float* __restrict__ margin) {
@@ -363,29 +427,33 @@ __global__ void select_tau_kernel(const float* __restrict__ tilemax, int n_s, in
   int lane = threadIdx.x & 31;
   if (row >= Qp) return;
   if (row >= Q) { if (lane == 0) { tau[row] = CUDART_INF_F; margin[row] = 0.f; } return; }
-  // lane owns elements lane, lane+32, ... (<= 32 of them since n_s <= 1024)
-  uint32_t taken = 0;
+  float v[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    int j = lane + 32 * t;
+    v[t] = j < n_s ? __ldg(tilemax + (size_t)j * Qp + row) : -CUDART_INF_F;
+  }
   float kth = -CUDART_INF_F;
   for (int r = 0; r < k; ++r) {
-    float bs = -CUDART_INF_F;
-    int bp = -1;
-    for (int t = 0, j = lane; j < n_s; j += 32, ++t) {
-      if (taken & (1u << t)) continue;
-      float v = tilemax[(size_t)j * Qp + row];
-      if (bp < 0 || v > bs) { bs = v; bp = j; }
-    }
+    float bs = v[0];
+    int bt = 0;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      float os = __shfl_xor_sync(0xffffffffu, bs, o);
-      int op = __shfl_xor_sync(0xffffffffu, bp, o);
-      if (op >= 0 && (bp < 0 || os > bs || (os == bs && op < bp))) { bs = os; bp = op; }
+    for (int t = 1; t < 32; ++t)
+      if (v[t] > bs) { bs = v[t]; bt = t; }
+    float ws = bs;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ws = fmaxf(ws, __shfl_xor_sync(0xffffffffu, ws, o));
+    kth = ws;
+    // exactly one lane (the lowest holding the max) retires its element
+    unsigned m = __ballot_sync(0xffffffffu, bs == ws);
+    if (lane == __ffs(m) - 1) {
+#pragma unroll
+      for (int t = 0; t < 32; ++t)
+        if (t == bt) v[t] = -CUDART_INF_F;
     }
-    if (bp < 0) { kth = -CUDART_INF_F; break; }
-    kth = bs;
-    if ((bp & 31) == lane) taken |= 1u << (bp >> 5);
   }
   if (lane == 0) {
-    float mg = 2.f * EPS_REL * qnorm[row] * tnorm_max[0];
+    float mg = fmaxf(2.f * EPS_REL * qnorm[row] * tnorm_max[0], 1e-20f);
     margin[row] = mg;
     tau[row] = kth - mg;
   }
@@ -577,15 +645,15 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// bf16 [rows, E] row-major, box = 64 cols x 128 rows, 128-byte swizzle
-int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int E) {
+// fp16 [rows, E] row-major, box = 64 cols x box_rows rows, 128-byte swizzle
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int E, int box_rows) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return SSE_ECUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)E, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)E * 2};
-  cuuint32_t box[2] = {KBLK, 128};
+  cuuint32_t box[2] = {KBLK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld E=%d", (int)r, (long long)rows, E); return SSE_ECUDA; }
@@ -597,30 +665,31 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace
 
 bool search_tc_supported(int E, int64_t N, int k) {
-  return E % 64 == 0 && E >= 64 && E <= 512 && k >= 1 && k <= 32 && N >= 64 * TILE_N && N < ((int64_t)1 << 31) - 256;
+  return E % 64 == 0 && E >= 64 && E <= 512 && k >= 1 && k <= 32 && N >= 8192 && N < ((int64_t)1 << 31) - 256;
 }
 
 int search_tc_prepare(TcIndex& ti, const float* index_f32, int64_t N, int E, cudaStream_t st, int64_t* launches) {
   search_tc_release(ti);
   ti.N = N; ti.E = E;
   size_t bytes = (size_t)N * E * 2 + 64;
-  cudaError_t e = cudaMalloc(&ti.bf16, bytes);
-  if (e != cudaSuccess) { set_error("cudaMalloc(bf16 index, %zu) failed: %s", bytes, cudaGetErrorString(e)); return SSE_ENOMEM; }
-  SSE_TRY(f32_to_bf16(index_f32, ti.bf16, N * E, st, launches));
+  cudaError_t e = cudaMalloc(&ti.h16, bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(fp16 index, %zu) failed: %s", bytes, cudaGetErrorString(e)); return SSE_ENOMEM; }
+  SSE_TRY(f32_to_f16(index_f32, ti.h16, N * E, st, launches));
   // slot for max |t| lives behind the matrix
-  float* tn = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.bf16) + align_up((size_t)N * E * 2, 16));
-  SSE_CUDA_OK(cudaMemsetAsync(tn, 0, 4, st));
-  max_row_norm_kernel<<<148 * 4, 256, 0, st>>>(index_f32, N, E, tn);
+  float* tnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.h16) + align_up((size_t)N * E * 2, 16));
+  SSE_CUDA_OK(cudaMemsetAsync(tnorm, 0, 4, st));
+  max_row_norm_kernel<<<148 * 4, 256, 0, st>>>(index_f32, N, E, tnorm);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
-  SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap), ti.bf16, N, E));
+  SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap), ti.h16, N, E, 128));
+  SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap64), ti.h16, N, E, 64));
   ti.tmap_ok = true;
   return SSE_OK;
 }
 
 void search_tc_release(TcIndex& ti) {
-  if (ti.bf16) cudaFree(ti.bf16);
-  ti.bf16 = nullptr; ti.N = 0; ti.E = 0; ti.tmap_ok = false;
+  if (ti.h16) cudaFree(ti.h16);
+  ti.h16 = nullptr; ti.N = 0; ti.E = 0; ti.tmap_ok = false;
 }
 
 int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
@@ -630,28 +699,30 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   const int64_t N = ti.N;
   const int KB = E / KBLK;
   const int m_tiles = cdiv(Q, TILE_M);
-  int mtg = (m_tiles >= 2 && KB <= 4) ? 2 : 1;
+  // TMEM budget (512 columns): queries mtg*E/2  +  accumulators mtg * 2 buffers * tn
+  int mtg = (m_tiles >= 2 && E <= 256) ? 2 : 1;
+  const int a_cols = mtg * E / 2;
+  const int tn = (a_cols + mtg * 2 * 128 <= 512) ? 128 : 64;
   const int n_groups = cdiv(m_tiles, mtg);
   if (n_groups > MAX_GROUPS) { set_error("search_tc: Q=%d too large for one call (max %d rows)", Q, MAX_GROUPS * 2 * TILE_M); return SSE_EINVAL; }
   const int Qp = n_groups * mtg * TILE_M;
-  const int n_tiles = (int)cdiv64(N, TILE_N);
-  int n_s = n_tiles / 16;
+  const int n_tiles = (int)cdiv64(N, tn);
+  int n_s = (int)(N / 16 / tn);
   if (n_s < 64) n_s = 64;
   if (n_s > 1024) n_s = 1024;
   if (n_s > n_tiles) n_s = n_tiles;
   const int s_step = n_tiles / n_s;
 
-  // smem budget
-  const size_t a_bytes = (size_t)mtg * KB * TILE_BYTES;
-  int NS = (int)((232448 - 1024 - 256 - a_bytes) / TILE_BYTES);
-  if (NS > 8) NS = 8;
-  if (NS < 2) { set_error("search_tc: E=%d does not fit shared memory", E); return SSE_EINVAL; }
-  const size_t smem = 1024 + a_bytes + (size_t)NS * TILE_BYTES + 256;
+  // shared memory = the TMA ring only
+  const size_t stage_bytes = (size_t)tn * KBLK * 2;
+  int NS = (int)((232448 - 1024 - 512) / stage_bytes);
+  if (NS > 24) NS = 24;
+  const size_t smem = 1024 + (size_t)NS * stage_bytes + 512;
 
   // items: split ~num_sms CTAs over groups in proportion to their m-tile count
   ScanParams sp;
   memset(&sp, 0, sizeof(sp));
-  sp.n_groups = n_groups; sp.mtg = mtg; sp.kb = KB; sp.n_stages = NS;
+  sp.n_groups = n_groups; sp.mtg = mtg; sp.kb = KB; sp.n_stages = NS; sp.tn = tn; sp.a_cols = a_cols;
   sp.N = N; sp.Qp = Qp; sp.global_offset = global_offset;
   int items = 0;
   {
@@ -669,8 +740,6 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
     }
     items = assigned_items;
   }
-  // a group never needs more items than tiles
-  // (tiny N is excluded by search_tc_supported: n_tiles >= 64)
 
   // workspace carve
   size_t off = 0;
@@ -684,21 +753,22 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   size_t o_ci = carve((size_t)items * mtg * TILE_M * CAND_CAP * 4);
   size_t o_cc = carve((size_t)items * mtg * TILE_M * 4);
   size_t o_ov = carve((size_t)Qp * 4);
+  const bool want_dbg = getenv("SSE_SCAN_DEBUG") != nullptr;
+  size_t o_dbg = carve(want_dbg ? (size_t)items * 8 * 8 : 8);
   SSE_TRY(ws.ensure(off));
   uint8_t* w = ws.as<uint8_t>();
-  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(w + o_qb);
+  __half* qb = reinterpret_cast<__half*>(w + o_qb);
   float* qn = reinterpret_cast<float*>(w + o_qn);
   float* tau = reinterpret_cast<float*>(w + o_tau);
   float* mg = reinterpret_cast<float*>(w + o_mg);
   float* tm = reinterpret_cast<float*>(w + o_tm);
-  float* tn = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.bf16) + align_up((size_t)N * E * 2, 16));
+  float* tnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.h16) + align_up((size_t)N * E * 2, 16));
 
   prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E, qb, qn);
   if (launches) ++*launches;
 
-  CUtensorMap tmq;
-  SSE_TRY(make_tmap(&tmq, qb, Qp, E));
-  const CUtensorMap& tmi = *reinterpret_cast<const CUtensorMap*>(ti.tmap);
+  const CUtensorMap& tmi = *reinterpret_cast<const CUtensorMap*>(tn == 128 ? ti.tmap : ti.tmap64);
+  sp.qb = qb;
 
   static bool attr_done = false;
   if (!attr_done) {
@@ -709,17 +779,19 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
 
   // pass A: tile maxima over the strided sample
   sp.n_j = n_s; sp.tile_step = s_step; sp.tilemax = tm; sp.tau = nullptr;
-  scan_kernel<MODE_TILEMAX><<<items, SCAN_THREADS, smem, st>>>(tmq, tmi, sp);
+  scan_kernel<MODE_TILEMAX><<<items, SCAN_THREADS, smem, st>>>(tmi, sp);
   if (launches) ++*launches;
-  select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, qn, tn, tau, mg);
+  select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, qn, tnorm, tau, mg);
   if (launches) ++*launches;
 
   // pass B: filter over all tiles
   sp.n_j = n_tiles; sp.tile_step = 1; sp.tilemax = nullptr; sp.tau = tau;
+  sp.dbg = want_dbg ? reinterpret_cast<long long*>(w + o_dbg) : nullptr;
+  sp.dbg_flags = (want_dbg && getenv("SSE_SCAN_FLAGS")) ? atoi(getenv("SSE_SCAN_FLAGS")) : 0;
   sp.cand_s = reinterpret_cast<float*>(w + o_cs);
   sp.cand_i = reinterpret_cast<int32_t*>(w + o_ci);
   sp.cand_cnt = reinterpret_cast<int32_t*>(w + o_cc);
-  scan_kernel<MODE_FILTER><<<items, SCAN_THREADS, smem, st>>>(tmq, tmi, sp);
+  scan_kernel<MODE_FILTER><<<items, SCAN_THREADS, smem, st>>>(tmi, sp);
   if (launches) ++*launches;
 
   FinParams fp;
@@ -729,6 +801,17 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   fp.cand_s = sp.cand_s; fp.cand_i = sp.cand_i; fp.cand_cnt = sp.cand_cnt; fp.margin = mg;
   fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E; fp.k = k;
   fp.out_s = out_scores; fp.out_i = out_idx; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov);
+  if (want_dbg) {
+    std::vector<long long> hd((size_t)items * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hd.data(), w + o_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
+    const char* nm[8] = {"prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_acce", "mma_total", "mma_wait_a", "epi_wait_accf", "epi_total"};
+    for (int c = 0; c < 8; ++c) {
+      long long mn = 1LL << 62, mx = 0, sm = 0;
+      for (int i = 0; i < items; ++i) { long long v = hd[(size_t)i * 8 + c]; mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
+      fprintf(stderr, "[scan dbg] %-16s min %10lld avg %10lld max %10lld  (items %d, tiles/item ~%d, tn %d, NS %d)\n", nm[c], mn, sm / items, mx, items, n_tiles / items * n_groups, tn, NS);
+    }
+  }
   finalize_kernel<<<Q, 128, 0, st>>>(fp);
   if (launches) ++*launches;
   fallback_kernel<<<Q, 256, (size_t)8 * k * 8, st>>>(fp);

@@ -67,6 +67,12 @@ void refresh_pointers(sse_handle* h) {
   fix_l(h->lstm[0]); fix_l(h->lstm[1]); fix_c(h->cnn[0]); fix_c(h->cnn[1]);
 }
 
+void invalidate_derived(sse_handle* h) {
+  h->pad[0].valid = h->pad[1].valid = false;
+  h->tct[0].valid = h->tct[1].valid = false;
+  h->emb_f16_valid = false;
+}
+
 bool side_is_cnn(const sse_handle* h, int side) {
   (void)side;
   return h->cfg.network_mode == SSE_MODE_SOURCE_ONLY_CNN || h->cfg.network_mode == SSE_MODE_DUAL_CNN;
@@ -137,6 +143,27 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens, int B, float* 
     SSE_TRY(ensure_pad_table(h, side, st));
     ih = h->pad[side].h + (size_t)(t_start - 1) * H;
     ic = h->pad[side].c + (size_t)(t_start - 1) * H;
+  }
+  const bool want_tc = h->opt_encoder == 2 || (h->opt_encoder == 0 && c.precision == SSE_PRECISION_TC);
+  if (want_tc && lstm_tc_supported(We, H)) {
+    if (!h->emb_f16_valid) {
+      if (!h->emb_f16) SSE_CUDA_OK(cudaMalloc(&h->emb_f16, (size_t)c.vocab_size * We * 2));
+      SSE_TRY(f32_to_f16(emb, h->emb_f16, (int64_t)c.vocab_size * We, st, &h->launches));
+      h->emb_f16_valid = true;
+    }
+    TcTower& tt = h->tct[side];
+    if (!tt.valid) SSE_TRY(lstm_tc_prepare(tt, tw.K, tw.b, We, H, st, &h->launches));
+    const size_t Bpad = (size_t)cdiv(B, 128) * 128;
+    SSE_TRY(h->enc_ws.ensure((Bpad * H + (size_t)B * H) * 4));
+    float* cs = h->enc_ws.as<float>();
+    float* hout = cs + Bpad * H;
+    SSE_TRY(lstm_forward_tc(tokens, B, T, t_start, h->emb_f16, We, H, tt, ih, ic, cs, hout, st, &h->launches));
+    SSE_TRY(sgemm(false, false, B, E, H, 1.f, hout, H, tw.M, E, 0.f, out, E, st, &h->launches));
+    if (normalize) SSE_TRY(l2norm_rows(out, B, E, st, &h->launches));
+    return SSE_OK;
+  } else if (h->opt_encoder == 2) {
+    set_error("tcgen05 encoder needs We%%64==0, H%%64==0, We,H<=256 (We=%d H=%d)", We, H);
+    return SSE_EINVAL;
   }
   SSE_TRY(h->enc_ws.ensure((size_t)B * H * 3 * 4));
   float* h0 = h->enc_ws.as<float>();
@@ -292,6 +319,8 @@ int sse_destroy(sse_handle* h) {
   if (h->index_f32 && h->index_owned) cudaFree(h->index_f32);
   if (h->grad_arena) cudaFree(h->grad_arena);
   search_tc_release(h->tc);
+  lstm_tc_release(h->tct[0]); lstm_tc_release(h->tct[1]);
+  if (h->emb_f16) cudaFree(h->emb_f16);
   delete h;
   return SSE_OK;
 }
@@ -319,7 +348,7 @@ int sse_set_param(sse_handle* h, const char* name, const void* ptr, const int64_
   }
   SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
   SSE_CUDA_OK(cudaMemcpy(p.dev, ptr, (size_t)p.numel * 4, cudaMemcpyDefault));
-  h->pad[0].valid = h->pad[1].valid = false;   // weights changed: pad-prefix tables are stale
+  invalidate_derived(h);   // weights changed: pad-prefix tables / fp16 copies are stale
   return SSE_OK;
 }
 

@@ -1,7 +1,7 @@
 // Shared declarations of libsse_b200.so (internal; the public ABI is include/sse_b200.h).
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -96,12 +96,13 @@ int search_simt(const float* q, int Q, int E, const float* index, int64_t N, int
 int merge_topk(const float* cand_s, const int32_t* cand_i, int Q, int C, int k, float* out_s, int32_t* out_i,
                cudaStream_t st, int64_t* launches);
 
-// search_tc.cu (tcgen05 bf16 scan + exact fp32 re-rank)
+// search_tc.cu (tcgen05 fp16 scan + exact fp32 re-rank)
 struct TcIndex {
-  __nv_bfloat16* bf16 = nullptr;   // [N, E] row-major
+  __half* h16 = nullptr;    // [N, E] row-major fp16
   int64_t N = 0;
   int E = 0;
-  alignas(64) unsigned char tmap[128];   // CUtensorMap of the bf16 index
+  alignas(64) unsigned char tmap[128];     // CUtensorMap of the fp16 index, box 64 x 128 rows
+  alignas(64) unsigned char tmap64[128];   // same, box 64 x 64 rows
   bool tmap_ok = false;
 };
 bool search_tc_supported(int E, int64_t N, int k);
@@ -110,8 +111,22 @@ void search_tc_release(TcIndex& ti);
 int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
               float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches);
 
+// lstm_tc.cu (tcgen05 LSTM tower, fp16 operands / fp32 accumulate and state)
+struct TcTower {
+  __half* wt = nullptr;     // [4H, We+H] chunk-major transposed weights
+  float* bias_r = nullptr;         // [4H] chunk-major bias (+1 folded into the forget gate)
+  alignas(64) unsigned char tmap[128];
+  bool valid = false;
+};
+bool lstm_tc_supported(int We, int H);
+int lstm_tc_prepare(TcTower& tt, const float* K, const float* b, int We, int H, cudaStream_t st, int64_t* launches);
+void lstm_tc_release(TcTower& tt);
+int lstm_forward_tc(const int32_t* tokens, int B, int T, int t_start, const __half* emb_f16, int We, int H,
+                    const TcTower& tt, const float* init_h, const float* init_c, float* c_scratch, float* h_out,
+                    cudaStream_t st, int64_t* launches);
+
 // small utilities (util.cu)
 int fill_f32(float* p, int64_t n, float v, cudaStream_t st, int64_t* launches);
-int f32_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st, int64_t* launches);
+int f32_to_f16(const float* src, __half* dst, int64_t n, cudaStream_t st, int64_t* launches);
 
 }  // namespace sse

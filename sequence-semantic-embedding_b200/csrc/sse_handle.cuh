@@ -22,6 +22,9 @@ struct sse_handle {
   sse::LstmTower lstm[2];           // [SSE_SIDE_SRC], [SSE_SIDE_TGT]
   sse::CnnTower cnn[2];
   sse::PadTable pad[2];
+  sse::TcTower tct[2];              // tensor-core copies of the LSTM weights (lazy, invalidated with the weights)
+  __half* emb_f16 = nullptr;
+  bool emb_f16_valid = false;
   float learning_rate = 0.f;
   int64_t global_step = 0;
 
@@ -46,6 +49,7 @@ namespace sse {
 int find_param(sse_handle* h, const char* name);
 void refresh_pointers(sse_handle* h);
 bool side_is_cnn(const sse_handle* h, int side);
+void invalidate_derived(sse_handle* h);
 int encode_device(sse_handle* h, int side, const int32_t* tokens, int B, float* out, int normalize, int t_start,
                   cudaStream_t st);
 }  // namespace sse

@@ -384,7 +384,7 @@ int sse_train_apply(sse_handle* h, float* loss_host, float* acc_host, float* gno
   }
   SSE_CUDA_OK(cudaGetLastError());
   h->global_step += 1;
-  h->pad[0].valid = h->pad[1].valid = false;
+  invalidate_derived(h);
   if (loss_host || acc_host || gnorm_host) {
     float sc[4];
     SSE_CUDA_OK(cudaMemcpyAsync(sc, scalars, 16, cudaMemcpyDeviceToHost, st));

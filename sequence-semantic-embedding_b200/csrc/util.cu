@@ -29,20 +29,20 @@ namespace {
 __global__ void fill_kernel(float* p, int64_t n, float v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
-__global__ void f32_to_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, int64_t n4) {
+__global__ void f32_to_f16_kernel(const float* __restrict__ s, __half* __restrict__ d, int64_t n4) {
   // n4 = number of float4 groups
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(s)[i];
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
     uint2 o;
     o.x = *reinterpret_cast<uint32_t*>(&a);
     o.y = *reinterpret_cast<uint32_t*>(&b);
     reinterpret_cast<uint2*>(d)[i] = o;
   }
 }
-__global__ void f32_to_bf16_tail(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, int64_t from, int64_t n) {
+__global__ void f32_to_f16_tail(const float* __restrict__ s, __half* __restrict__ d, int64_t from, int64_t n) {
   int64_t i = from + threadIdx.x;
-  if (i < n) d[i] = __float2bfloat16_rn(s[i]);
+  if (i < n) d[i] = __float2half_rn(s[i]);
 }
 }  // namespace
 
@@ -55,16 +55,16 @@ int fill_f32(float* p, int64_t n, float v, cudaStream_t st, int64_t* launches) {
   return SSE_OK;
 }
 
-int f32_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st, int64_t* launches) {
+int f32_to_f16(const float* src, __half* dst, int64_t n, cudaStream_t st, int64_t* launches) {
   if (n <= 0) return SSE_OK;
   int64_t n4 = n / 4;
   if (n4 > 0) {
     int blocks = (int)std::min<int64_t>(cdiv64(n4, 256), 148 * 16);
-    f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(src, dst, n4);
+    f32_to_f16_kernel<<<blocks, 256, 0, st>>>(src, dst, n4);
     if (launches) ++*launches;
   }
   if (n4 * 4 < n) {
-    f32_to_bf16_tail<<<1, 4, 0, st>>>(src, dst, n4 * 4, n);
+    f32_to_f16_tail<<<1, 4, 0, st>>>(src, dst, n4 * 4, n);
     if (launches) ++*launches;
   }
   SSE_CUDA_OK(cudaGetLastError());

@@ -122,3 +122,50 @@ def test_param_round_trip_and_errors():
     with pytest.raises(sse_ffi.SseError):
         h.encode_host(0, np.zeros((2, 5), np.int32))
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, bf16 operands / fp32 accumulate + state) LSTM tower: north_star tolerance
+TOL_TC = 1e-3
+
+
+@pytest.mark.parametrize("We,H,E,T,B", [(256, 256, 256, 50, 300), (64, 64, 32, 12, 128), (128, 192, 64, 20, 77),
+                                        (256, 128, 256, 50, 1), (192, 256, 128, 30, 513)])
+def test_tc_lstm_encode_within_tolerance(We, H, E, T, B):
+    mode, V = "dual-encoder", 5000
+    h, p = make(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
+    h.set_option("encoder", 2)          # force the tcgen05 path (raise if unsupported)
+    rng = np.random.default_rng(We + H + B)
+    for side, name in ((sse_ffi.SIDE_SRC, "src"), (sse_ffi.SIDE_TGT, "tgt")):
+        tok = np.concatenate([O.synth_tokens(rng, B - B // 2, T, V, "full"), O.synth_tokens(rng, B // 2, T, V, "real", 4.0)]) \
+            if B > 1 else O.synth_tokens(rng, 1, T, V, "full")
+        got = h.encode_host(side, tok, True)
+        want = O.encode(p, mode, name, tok, True)
+        err = np.abs(got - want).max()
+        assert err < TOL_TC, (name, err)
+        assert err > 0          # it really is the bf16 path, not the fp32 one
+        raw = h.encode_host(side, tok, False)
+        wraw = O.encode(p, mode, name, tok, False)
+        assert np.abs(raw - wraw).max() < 2e-2 * np.abs(wraw).max()
+    h.close()
+
+
+def test_tc_lstm_pad_skip_and_exact_mode_switch():
+    mode, V, We, H, E, T, B = "shared-encoder", 3000, 128, 128, 64, 40, 200
+    h, p = make(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
+    rng = np.random.default_rng(12)
+    tok = O.synth_tokens(rng, B, T, V, "real", 3.0)
+    want = O.encode(p, mode, "src", tok, True)
+    h.set_option("encoder", 2)
+    a = h.encode_host(0, tok, True)
+    h.set_option("pad_skip", 1)
+    b = h.encode_host(0, tok, True)           # starts every row from the pad-prefix state table
+    assert np.abs(a - want).max() < TOL_TC and np.abs(b - want).max() < TOL_TC
+    h.set_option("encoder", 1)                # exact fp32 SIMT mode on the same handle
+    c = h.encode_host(0, tok, True)
+    assert np.abs(c - want).max() < TOL_FP32
+    with pytest.raises(sse_ffi.SseError):
+        h2, _ = make(mode, 100, 50, 64, 96, 96, 20, precision=sse_ffi.PRECISION_TC)
+        h2.set_option("encoder", 2)
+        h2.encode_host(0, np.zeros((2, 20), np.int32), True)
+    h.close()
