@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--queries", type=int, default=600, help="query rows per step (sse_evaluator.py:104 batch)")
     ap.add_argument("--search", type=int, default=0, help="0 auto (tcgen05), 1 fp32 SIMT, 2 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=5, help="timed train steps for the secondary train-step/s figure (0 = skip)")
+    ap.add_argument("--train-rows", type=int, default=1024, help="pair rows per GPU per train step (512 pos + 512 neg, data.py:95-115 layout)")
     ap.add_argument("--cpu-sample-targets", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=64)
     return ap.parse_args()
@@ -239,6 +241,41 @@ def run_b200(args):
     ms_enc = e0.elapsed_time(e1) / reps
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- secondary metric: train-step/s (fp32 pair-loss step: fwd both towers, BPTT, clip, Adagrad)
+    train = None
+    if args.train_steps > 0:
+        import sse_dist
+        Bt = args.train_rows
+        rng_t = np.random.default_rng(100 + rank)
+        src_t = torch.from_numpy(np.repeat(synth_tokens(rng_t, Bt // 2), 2, axis=0)).cuda()
+        tgt_t = torch.from_numpy(synth_tokens(rng_t, Bt)).cuda()
+        lab_t = torch.tensor([1.0, 0.0] * (Bt // 2), device="cuda")
+
+        def tstep():
+            if world > 1:
+                sse_dist.allreduce_train_step(h, src_t, tgt_t, lab_t, Bt * world)
+            else:
+                h.train_step(src_t, tgt_t, lab_t, stream=stream, want_scalars=False)
+        for _ in range(2):
+            tstep()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.train_steps):
+            tstep()
+        e1.record()
+        barrier()
+        ms_t = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms_t], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_t = float(tt.item())
+        train = {"metric": "train-step/s", "value": args.train_steps / (ms_t * 1e-3), "ms_per_step": ms_t / args.train_steps,
+                 "pair_rows_per_gpu": Bt, "pair_rows_global": Bt * world, "dtype": "f32",
+                 "flops_per_step": 3.0 * Bt * world * 2 * F_LSTM,
+                 "achieved_tflops": 3.0 * Bt * world * 2 * F_LSTM / (ms_t / args.train_steps * 1e-3) / 1e12,
+                 "parallelism": "data-parallel x%d, all-reduce of the gradient arena" % world if world > 1 else "single GPU"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -280,6 +317,7 @@ def run_b200(args):
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "clocks": clocks,
         "roofline": roof,
+        "train": train,
     }
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_reference(args.cpu_sample_queries, args.cpu_sample_targets, runs=1)

@@ -208,22 +208,23 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   const int mt_count = P.group_mt[g];
   const int j0 = (int)(((int64_t)P.n_j * r_in_g) / R);
   const int j1 = (int)(((int64_t)P.n_j * (r_in_g + 1)) / R);
-  const int KB = P.kb, NS = P.n_stages, TN = P.tn;
+  const int KB = P.kb, NG = P.n_stages, TN = P.tn;      // n_stages = number of TILE slots in the ring
   const int E = KB * KBLK;
-  const uint32_t stage_bytes = (uint32_t)TN * KBLK * 2;
+  const uint32_t kb_bytes = (uint32_t)TN * KBLK * 2;     // one [TN x 64] fp16 SW128 sub-tile
+  const uint32_t slot_bytes = kb_bytes * KB;             // one whole index tile [TN x E]
 
-  uint8_t* b_smem = smem;                                        // [NS] tiles of [TN x 64] fp16, SW128
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)NS * stage_bytes);
-  // bars: full[NS], empty[NS], a_full, acc_full[2], acc_empty[2]
+  uint8_t* b_smem = smem;                                // [NG] slots x [KB] sub-tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)NG * slot_bytes);
+  // bars: full[NG], empty[NG], a_full, acc_full[2], acc_empty[2]
   const uint32_t bar_full = smem_u32(bars);
-  const uint32_t bar_empty = smem_u32(bars + NS);
-  const uint32_t bar_a = smem_u32(bars + 2 * NS);
-  const uint32_t bar_accf = smem_u32(bars + 2 * NS + 1);
-  const uint32_t bar_acce = smem_u32(bars + 2 * NS + 3);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5);
+  const uint32_t bar_empty = smem_u32(bars + NG);
+  const uint32_t bar_a = smem_u32(bars + 2 * NG);
+  const uint32_t bar_accf = smem_u32(bars + 2 * NG + 1);
+  const uint32_t bar_acce = smem_u32(bars + 2 * NG + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NG + 5);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < NG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_a, mt_count * 4);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, mt_count * 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -240,51 +241,52 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   const uint32_t acc_col0 = (uint32_t)P.a_cols;          // accumulators sit behind the query columns
 
   if (warp == 9) {
-    // ===== TMA producer =====
+    // ===== TMA producer: one whole index tile (KB sub-tiles) per ring slot, one barrier per slot =====
     if (lane == 0 && j1 > j0) {
-      uint32_t it = 0;
       long long w_empty = 0, t_begin = clock64();
       for (int j = j0; j < j1; ++j) {
+        const int jj = j - j0;
+        const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
         const int tile = j * P.tile_step;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const uint32_t s = it % NS, ph = (it / NS) & 1;
-          mbar_wait_timed(bar_empty + 8 * s, ph ^ 1, w_empty);
-          if (P.dbg_flags & 1) { mbar_arrive(bar_full + 8 * s); continue; }
-          mbar_expect_tx(bar_full + 8 * s, stage_bytes);
-          tma_load_2d(smem_u32(b_smem + (size_t)s * stage_bytes), &tmap_idx, bar_full + 8 * s, kb * KBLK, tile * TN);
-        }
+        mbar_wait_timed(bar_empty + 8 * s, ph ^ 1, w_empty);
+        if (P.dbg_flags & 1) { mbar_arrive(bar_full + 8 * s); continue; }
+        mbar_expect_tx(bar_full + 8 * s, slot_bytes);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(smem_u32(b_smem + (size_t)s * slot_bytes + (size_t)kb * kb_bytes), &tmap_idx, bar_full + 8 * s,
+                      kb * KBLK, tile * TN);
       }
       if (P.dbg) { P.dbg[item * 8 + 0] = w_empty; P.dbg[item * 8 + 1] = clock64() - t_begin; }
     }
   } else if (warp == 8) {
-    // ===== MMA issuer (one thread) =====
+    // ===== MMA issuer (one thread): all MMAs of a tile back to back, ONE tcgen05.commit per tile =====
     if (lane == 0 && j1 > j0) {
       const uint32_t idesc = make_idesc_f16(TILE_M, TN);
       long long w_full = 0, w_acce = 0, w_a = 0, t_begin = clock64();
       mbar_wait_timed(bar_a, 0, w_a);
       tc_fence_after();
-      uint32_t it = 0;
       for (int j = j0; j < j1; ++j) {
         const int jj = j - j0;
         const int buf = jj & 1;
         const uint32_t use = (uint32_t)(jj >> 1);
+        const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
         mbar_wait_timed(bar_acce + 8 * buf, (use & 1) ^ 1, w_acce);
+        mbar_wait_timed(bar_full + 8 * s, ph, w_full);
         tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const uint32_t s = it % NS, ph = (it / NS) & 1;
-          mbar_wait_timed(bar_full + 8 * s, ph, w_full);
-          tc_fence_after();
-          const uint64_t bdesc = make_sw128_desc(smem_u32(b_smem + (size_t)s * stage_bytes));
-          for (int mt = 0; mt < mt_count && !(P.dbg_flags & 2); ++mt) {
-            const uint32_t a = tmem_base + (uint32_t)(mt * (E / 2) + kb * (KBLK / 2));
+        if (!(P.dbg_flags & 2)) {
+          const uint32_t slot = smem_u32(b_smem + (size_t)s * slot_bytes);
+          for (int mt = 0; mt < mt_count; ++mt) {
             const uint32_t d = tmem_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
+            const uint32_t a0 = tmem_base + (uint32_t)(mt * (E / 2));
+            for (int kb = 0; kb < KB; ++kb) {
+              const uint64_t bdesc = make_sw128_desc(slot + (uint32_t)kb * kb_bytes);
+              const uint32_t a = a0 + (uint32_t)(kb * (KBLK / 2));
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)   // 4 x (K=16): A advances 8 columns, B 32 bytes (= 2 descriptor units)
-              tc_mma_f16_ts(d, a + 8 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+              for (int k4 = 0; k4 < 4; ++k4)   // 4 x (K=16): A advances 8 columns, B 32 bytes (= 2 descriptor units)
+                tc_mma_f16_ts(d, a + 8 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+            }
           }
-          tc_commit(bar_empty + 8 * s);     // smem stage is free once these MMAs retire
         }
-        tc_commit(bar_accf + 8 * buf);      // accumulators of this tile are complete
+        tc_commit(bar_accf + 8 * buf);      // accumulators complete == this ring slot fully read
       }
       if (P.dbg) { P.dbg[item * 8 + 2] = w_full; P.dbg[item * 8 + 3] = w_acce; P.dbg[item * 8 + 4] = clock64() - t_begin; P.dbg[item * 8 + 5] = w_a; }
     }
@@ -335,6 +337,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         const bool ragged = col0 + TN > P.N;
         mbar_wait_timed(bar_accf + 8 * buf, use & 1, w_accf);
         tc_fence_after();
+        // the MMAs of this tile have retired: hand its ring slot back to the TMA producer
+        if (e == 0 && lane == 0) mbar_arrive(bar_empty + 8 * ((uint32_t)jj % NG));
         const uint32_t taddr = lane_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
         float tmax = -CUDART_INF_F;
 #pragma unroll 1
@@ -702,7 +706,8 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   // TMEM budget (512 columns): queries mtg*E/2  +  accumulators mtg * 2 buffers * tn
   int mtg = (m_tiles >= 2 && E <= 256) ? 2 : 1;
   const int a_cols = mtg * E / 2;
-  const int tn = (a_cols + mtg * 2 * 128 <= 512) ? 128 : 64;
+  // tile width: 128 index rows when TMEM (512 columns) and a >=3-deep ring allow it, else 64
+  const int tn = (a_cols + mtg * 2 * 128 <= 512 && 3 * 128 * E * 2 <= 232448 - 2048) ? 128 : 64;
   const int n_groups = cdiv(m_tiles, mtg);
   if (n_groups > MAX_GROUPS) { set_error("search_tc: Q=%d too large for one call (max %d rows)", Q, MAX_GROUPS * 2 * TILE_M); return SSE_EINVAL; }
   const int Qp = n_groups * mtg * TILE_M;
@@ -713,10 +718,11 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   if (n_s > n_tiles) n_s = n_tiles;
   const int s_step = n_tiles / n_s;
 
-  // shared memory = the TMA ring only
-  const size_t stage_bytes = (size_t)tn * KBLK * 2;
+  // shared memory = the TMA ring only: NS slots of one whole [tn x E] fp16 index tile each
+  const size_t stage_bytes = (size_t)tn * E * 2;
   int NS = (int)((232448 - 1024 - 512) / stage_bytes);
-  if (NS > 24) NS = 24;
+  if (NS > 16) NS = 16;
+  if (NS < 2) { set_error("search_tc: E=%d does not fit the shared-memory ring", E); return SSE_EINVAL; }
   const size_t smem = 1024 + (size_t)NS * stage_bytes + 512;
 
   // items: split ~num_sms CTAs over groups in proportion to their m-tile count
