@@ -24,6 +24,11 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint3
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %1;\n@%%px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred;
+}
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
@@ -51,7 +56,7 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int n_mma, int 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem = tslot;
-  if (threadIdx.x == 64) {   // warp 2 lane 0
+  if (threadIdx.x >= 64 && threadIdx.x < 96) {   // warp 2, converged; one elected lane issues (warp-uniform operands)
     uint64_t a = make_desc(smem_u32(smem)), b = make_desc(smem_u32(smem + 32768));
     uint32_t idesc = make_idesc(128, N);
     uint32_t ncommit = 0;
@@ -61,13 +66,17 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int n_mma, int 
       long long c0 = clock64();
       for (int i = 0; i < n_mma; ++i) {
         uint32_t d = tmem + 256 + (uint32_t)((i % n_acc) * 64 % 256);
-        if (mode == 0) mma_ss(d, a + 2 * (i & 3), b + 2 * (i & 3), idesc, 1);
-        else mma_ts(d, tmem + 8 * (i & 3), b + 2 * (i & 3), idesc, 1);
+        if (elect_one_sync()) {
+          if (mode == 0) mma_ss(d, a + 2 * (i & 3), b + 2 * (i & 3), idesc, 1);
+          else mma_ts(d, tmem + 8 * (i & 3), b + 2 * (i & 3), idesc, 1);
+        }
+        __syncwarp();
       }
       long long c1 = clock64();
       t_issue += c1 - c0;
       if (commit_every_rep || r == reps - 1) {
-        tc_commit(smem_u32(&bar)); ++ncommit;
+        if (elect_one_sync()) tc_commit(smem_u32(&bar));
+        __syncwarp(); ++ncommit;
         long long c2 = clock64();
         t_commit += c2 - c1;
         if (commit_every_rep == 2 || r == reps - 1) {   // 2 = also wait for completion every rep
@@ -77,7 +86,7 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int n_mma, int 
       }
     }
     long long t1 = clock64();
-    if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t_issue; out[2] = t_commit; out[3] = t_wait; }
+    if (blockIdx.x == 0 && threadIdx.x == 64) { out[0] = t1 - t0; out[1] = t_issue; out[2] = t_commit; out[3] = t_wait; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -88,10 +97,10 @@ int main() {
   long long* d; cudaMalloc(&d, 64);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int Ns[3] = {64, 128, 256};
-  for (int grid : {1, 148})
+  for (int grid : {148})
     for (int mode = 0; mode < 2; ++mode)
       for (int ni = 0; ni < 3; ++ni)
-        for (int n_acc : {1, 2})
+        for (int n_acc : {1})
           for (int cfg = 0; cfg < 4; ++cfg) {
             int N = Ns[ni];
             if (N == 256 && n_acc == 2) continue;

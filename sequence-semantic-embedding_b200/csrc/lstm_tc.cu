@@ -82,6 +82,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// One elected lane of a CONVERGED warp (cutlass elect_one_sync).  The single-thread roles must run their
+// loops warp-converged with warp-uniform operands and wrap only the issue in this predicate: under a plain
+// `if (lane == 0)` branch nvcc cannot keep descriptors in uniform registers and emits an ELECT/R2UR retry loop
+// around every UTCHMMA / UTMALDG -- measured ~208 cycles per tcgen05.mma issue instead of the tensor-pipe floor.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %1;\n@%%px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -188,7 +197,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
   if (warp == 9) {
     // ===== TMA producer: weights, chunk-major =====
-    if (lane == 0) {
+    {   // whole warp, converged; one elected lane issues
       uint32_t it = 0;
       for (int t = t0; t < P.T; ++t) {
         const bool has_state = has_init || t > t0;
@@ -197,15 +206,18 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const uint32_t s = it % NS, ph = (it / NS) & 1;
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * s, TILE_BYTES);
-            tma_load_2d(smem_u32(w_smem + (size_t)s * TILE_BYTES), &tmap_w, bar_full + 8 * s, kb * KBLK, c * 128);
+            if (elect_one_sync()) {
+              mbar_expect_tx(bar_full + 8 * s, TILE_BYTES);
+              tma_load_2d(smem_u32(w_smem + (size_t)s * TILE_BYTES), &tmap_w, bar_full + 8 * s, kb * KBLK, c * 128);
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 8) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: whole warp converged, one elected lane issues (warp-uniform operands) =====
+    {
       const uint32_t idesc = make_idesc_f16(128, 128);
       uint32_t it = 0, gchunk = 0;
       for (int t = t0; t < P.T; ++t) {
@@ -224,13 +236,16 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const uint32_t s = it % NS, ph = (it / NS) & 1;
             mbar_wait(bar_full + 8 * s, ph);
             tc_fence_after();
-            const uint64_t adesc = make_sw128_desc(smem_u32(x_smem + (size_t)kb * TILE_BYTES));
-            const uint64_t bdesc = make_sw128_desc(smem_u32(w_smem + (size_t)s * TILE_BYTES));
+            if (elect_one_sync()) {
+              const uint64_t adesc = make_sw128_desc(smem_u32(x_smem + (size_t)kb * TILE_BYTES));
+              const uint64_t bdesc = make_sw128_desc(smem_u32(w_smem + (size_t)s * TILE_BYTES));
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) tc_mma_ss(d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
-            tc_commit(bar_empty + 8 * s);
+              for (int k4 = 0; k4 < 4; ++k4) tc_mma_ss(d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+              tc_commit(bar_empty + 8 * s);
+              if (c == NC - 1 && kb == KBx - 1) tc_commit(bar_xe);      // x_t fully consumed once these MMAs retire
+            }
+            __syncwarp();
           }
-          if (c == NC - 1) tc_commit(bar_xe);      // x_t fully consumed once these MMAs retire
           if (has_state) {
             if (c == 0) {
               // completions of h_full: [initial state staged (only with init)], end of step t0, t0+1, ...
@@ -242,13 +257,17 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
               const uint32_t s = it % NS, ph = (it / NS) & 1;
               mbar_wait(bar_full + 8 * s, ph);
               tc_fence_after();
-              const uint64_t bdesc = make_sw128_desc(smem_u32(w_smem + (size_t)s * TILE_BYTES));
+              if (elect_one_sync()) {
+                const uint64_t bdesc = make_sw128_desc(smem_u32(w_smem + (size_t)s * TILE_BYTES));
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) tc_mma_ts(d, h_src + (uint32_t)(kb * 32 + k4 * 8), bdesc + 2 * k4, idesc, 1u);
-              tc_commit(bar_empty + 8 * s);
+                for (int k4 = 0; k4 < 4; ++k4) tc_mma_ts(d, h_src + (uint32_t)(kb * 32 + k4 * 8), bdesc + 2 * k4, idesc, 1u);
+                tc_commit(bar_empty + 8 * s);
+              }
+              __syncwarp();
             }
           }
-          tc_commit(bar_accf + 8 * buf);
+          if (elect_one_sync()) tc_commit(bar_accf + 8 * buf);
+          __syncwarp();
         }
       }
     }

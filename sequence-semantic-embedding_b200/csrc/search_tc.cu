@@ -118,6 +118,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// One elected lane of a CONVERGED warp (cutlass elect_one_sync).  The single-thread roles must run their
+// loops warp-converged with warp-uniform operands and wrap only the issue in this predicate: under a plain
+// `if (lane == 0)` branch nvcc cannot keep descriptors in uniform registers and emits an ELECT/R2UR retry loop
+// around every UTCHMMA / UTMALDG -- measured ~208 cycles per tcgen05.mma issue instead of the tensor-pipe floor.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %1;\n@%%px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -242,24 +251,30 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
 
   if (warp == 9) {
     // ===== TMA producer: one whole index tile (KB sub-tiles) per ring slot, one barrier per slot =====
-    if (lane == 0 && j1 > j0) {
+    if (j1 > j0) {     // whole warp, converged; one elected lane issues
       long long w_empty = 0, t_begin = clock64();
       for (int j = j0; j < j1; ++j) {
         const int jj = j - j0;
         const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
         const int tile = j * P.tile_step;
         mbar_wait_timed(bar_empty + 8 * s, ph ^ 1, w_empty);
-        if (P.dbg_flags & 1) { mbar_arrive(bar_full + 8 * s); continue; }
-        mbar_expect_tx(bar_full + 8 * s, slot_bytes);
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(smem_u32(b_smem + (size_t)s * slot_bytes + (size_t)kb * kb_bytes), &tmap_idx, bar_full + 8 * s,
-                      kb * KBLK, tile * TN);
+        if (elect_one_sync()) {
+          if (P.dbg_flags & 1) {
+            mbar_arrive(bar_full + 8 * s);
+          } else {
+            mbar_expect_tx(bar_full + 8 * s, slot_bytes);
+            for (int kb = 0; kb < KB; ++kb)
+              tma_load_2d(smem_u32(b_smem + (size_t)s * slot_bytes + (size_t)kb * kb_bytes), &tmap_idx, bar_full + 8 * s,
+                          kb * KBLK, tile * TN);
+          }
+        }
+        __syncwarp();
       }
-      if (P.dbg) { P.dbg[item * 8 + 0] = w_empty; P.dbg[item * 8 + 1] = clock64() - t_begin; }
+      if (P.dbg && lane == 0) { P.dbg[item * 8 + 0] = w_empty; P.dbg[item * 8 + 1] = clock64() - t_begin; }
     }
   } else if (warp == 8) {
     // ===== MMA issuer (one thread): all MMAs of a tile back to back, ONE tcgen05.commit per tile =====
-    if (lane == 0 && j1 > j0) {
+    if (j1 > j0) {     // whole warp, converged; one elected lane issues
       const uint32_t idesc = make_idesc_f16(TILE_M, TN);
       long long w_full = 0, w_acce = 0, w_a = 0, t_begin = clock64();
       mbar_wait_timed(bar_a, 0, w_a);
@@ -272,7 +287,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         mbar_wait_timed(bar_acce + 8 * buf, (use & 1) ^ 1, w_acce);
         mbar_wait_timed(bar_full + 8 * s, ph, w_full);
         tc_fence_after();
-        if (!(P.dbg_flags & 2)) {
+        if (elect_one_sync()) {
+         if (!(P.dbg_flags & 2)) {
           const uint32_t slot = smem_u32(b_smem + (size_t)s * slot_bytes);
           for (int mt = 0; mt < mt_count; ++mt) {
             const uint32_t d = tmem_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
@@ -285,10 +301,12 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
                 tc_mma_f16_ts(d, a + 8 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
             }
           }
+         }
+         tc_commit(bar_accf + 8 * buf);      // accumulators complete == this ring slot fully read
         }
-        tc_commit(bar_accf + 8 * buf);      // accumulators complete == this ring slot fully read
+        __syncwarp();
       }
-      if (P.dbg) { P.dbg[item * 8 + 2] = w_full; P.dbg[item * 8 + 3] = w_acce; P.dbg[item * 8 + 4] = clock64() - t_begin; P.dbg[item * 8 + 5] = w_a; }
+      if (P.dbg && lane == 0) { P.dbg[item * 8 + 2] = w_full; P.dbg[item * 8 + 3] = w_acce; P.dbg[item * 8 + 4] = clock64() - t_begin; P.dbg[item * 8 + 5] = w_a; }
     }
   } else if (warp < 8) {
     // ===== epilogue: thread == query row =====
