@@ -40,13 +40,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
 }
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
-// mode: 0 = SS, 1 = TS.  n_mma MMAs per commit, reps commits.  D alternates over n_acc accumulators.
-__global__ void __launch_bounds__(128, 1) bench(int mode, int N, int n_mma, int reps, int n_acc, int commit_every_rep, long long* out) {
+// MODE 0 = SS, 1 = TS.  reps x (8 MMAs unrolled with constant operands) then ONE commit + wait.
+// All operands are warp-uniform / loop-invariant so the issue loop is nothing but UTCHMMA.
+template <int MODE, int N, int NACC>
+__global__ void __launch_bounds__(128, 1) bench(int reps, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
   __shared__ uint32_t tslot;
-  for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512));
@@ -55,67 +57,49 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int n_mma, int 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  uint32_t tmem = tslot;
-  if (threadIdx.x >= 64 && threadIdx.x < 96) {   // warp 2, converged; one elected lane issues (warp-uniform operands)
-    uint64_t a = make_desc(smem_u32(smem)), b = make_desc(smem_u32(smem + 32768));
-    uint32_t idesc = make_idesc(128, N);
-    uint32_t ncommit = 0;
-    long long t_issue = 0, t_commit = 0, t_wait = 0;
+  const uint32_t tmem = tslot;
+  if (threadIdx.x >= 64 && threadIdx.x < 96) {
+    const uint64_t a = make_desc(smem_u32(smem)), b = make_desc(smem_u32(smem + 32768));
+    const uint32_t idesc = make_idesc(128, N);
+    const uint32_t d0 = tmem + 256, d1 = tmem + 256 + (NACC > 1 ? 128 : 0);
     long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) {
-      long long c0 = clock64();
-      for (int i = 0; i < n_mma; ++i) {
-        uint32_t d = tmem + 256 + (uint32_t)((i % n_acc) * 64 % 256);
-        if (elect_one_sync()) {
-          if (mode == 0) mma_ss(d, a + 2 * (i & 3), b + 2 * (i & 3), idesc, 1);
+    if (elect_one_sync()) {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t d = (i & 1) ? d1 : d0;
+          if (MODE == 0) mma_ss(d, a + 2 * (i & 3), b + 2 * (i & 3), idesc, 1);
           else mma_ts(d, tmem + 8 * (i & 3), b + 2 * (i & 3), idesc, 1);
         }
-        __syncwarp();
       }
-      long long c1 = clock64();
-      t_issue += c1 - c0;
-      if (commit_every_rep || r == reps - 1) {
-        if (elect_one_sync()) tc_commit(smem_u32(&bar));
-        __syncwarp(); ++ncommit;
-        long long c2 = clock64();
-        t_commit += c2 - c1;
-        if (commit_every_rep == 2 || r == reps - 1) {   // 2 = also wait for completion every rep
-          mbar_wait(smem_u32(&bar), (ncommit - 1) & 1);   // phase k completes at the k-th commit (count 1)
-          t_wait += clock64() - c2;
-        }
-      }
+      tc_commit(smem_u32(&bar));
     }
+    __syncwarp();
     long long t1 = clock64();
-    if (blockIdx.x == 0 && threadIdx.x == 64) { out[0] = t1 - t0; out[1] = t_issue; out[2] = t_commit; out[3] = t_wait; }
+    mbar_wait(smem_u32(&bar), 0);
+    long long t2 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 64) { out[0] = t2 - t0; out[1] = t1 - t0; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (threadIdx.x < 32) { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512)); }
 }
 
+template <int MODE, int N, int NACC>
+void run(long long* d) {
+  cudaFuncSetAttribute(bench<MODE, N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const int reps = 128;
+  for (int w = 0; w < 2; ++w) bench<MODE, N, NACC><<<148, 128, 100 * 1024>>>(reps, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  printf("%s N=%3d acc=%d : %7.1f cyc/MMA to completion, %7.1f cyc/MMA issue (floor %d) %s\n", MODE ? "TS" : "SS", N, NACC,
+         (double)h[0] / (reps * 8), (double)h[1] / (reps * 8), N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  fflush(stdout);
+}
+
 int main() {
   long long* d; cudaMalloc(&d, 64);
-  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  const int Ns[3] = {64, 128, 256};
-  for (int grid : {148})
-    for (int mode = 0; mode < 2; ++mode)
-      for (int ni = 0; ni < 3; ++ni)
-        for (int n_acc : {1})
-          for (int cfg = 0; cfg < 4; ++cfg) {
-            int N = Ns[ni];
-            if (N == 256 && n_acc == 2) continue;
-            int n_mma = cfg == 0 ? 256 : (cfg == 1 ? 32 : (cfg == 2 ? 8 : 8));
-            int reps = cfg == 0 ? 4 : (cfg == 1 ? 32 : 128);
-            int ce = cfg == 0 ? 0 : (cfg == 3 ? 2 : 1);
-            for (int w = 0; w < 2; ++w) bench<<<grid, 128, 100 * 1024>>>(mode, N, n_mma, reps, n_acc, ce, d);
-            cudaError_t e = cudaDeviceSynchronize();
-            long long h[4]; cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
-            long long total_mma = (long long)n_mma * reps;
-            printf("grid %3d %s N=%3d n_acc=%d mma/commit=%3d commits=%3d wait_each=%d : total %8lld cyc  per-mma %6.1f (floor %d)  issue/mma %6.1f  commit %6.1f  wait %7.1f  %s\n",
-                   grid, mode ? "TS" : "SS", N, n_acc, n_mma, ce ? reps : 1, ce == 2, h[0], (double)h[0] / total_mma, N / 2,
-                   (double)h[1] / total_mma, (double)h[2] / (ce ? reps : 1), (double)h[3] / (ce == 2 ? reps : 1), e == cudaSuccess ? "" : cudaGetErrorString(e));
-            fflush(stdout);
-            if (e != cudaSuccess) return 1;
-          }
+  run<0, 64, 1>(d); run<0, 128, 1>(d); run<0, 256, 1>(d); run<0, 64, 2>(d); run<0, 128, 2>(d);
+  run<1, 64, 1>(d); run<1, 128, 1>(d); run<1, 256, 1>(d); run<1, 64, 2>(d); run<1, 128, 2>(d);
   return 0;
 }

@@ -13,12 +13,13 @@
 //   TMEM; the epilogue (thread == batch row) applies bias, sigmoid/tanh (tanh.approx), updates
 //   c (fp32, L2-resident scratch) and writes h_t back to TMEM as packed fp16 for the next step.
 // TMEM columns: h ping [0,128) | h pong [128,256) | acc0 [256,384) | acc1 [384,512).
-// warps 0-3 epilogue | warps 4-7 embedding gather (cp.async, thread == row, manual 128B swizzle) |
-// warp 8 MMA issuer | warp 9 TMA producer | warp 10 TMEM alloc  (single-thread critical roles on the
-// highest warp ids, which the sub-partition arbiter favours).
+// warps 0-7 epilogue (warp w: TMEM lane quarter w%4, unit half w/4 of each 32-unit chunk) | warp 8 MMA issuer |
+// warp 9 TMA producer | warp 10 TMEM alloc | warp 11 embedding gather (cp.async, 4 rows per lane, manual 128B
+// swizzle).  Single-thread roles run warp-converged and issue through elect_one_sync().
 #include "sse_common.cuh"
 #include <cuda.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace sse {
 
@@ -38,6 +39,8 @@ struct LstmTcParams {
   float* c_scratch;           // [Bpad, H] fp32
   float* h_out;               // [B, H] fp32 (last step)
   int B, T, t_start, We, H, n_stages;
+  long long* dbg;             // optional [grid][8] cycle counters
+  int use3d;                  // 1: one 3-D TMA per slot; 0: KB 2-D loads per slot (fallback if the 3-D map is rejected)
 };
 
 // ---------------------------------------------------------------- PTX helpers (see search_tc.cu)
@@ -52,29 +55,34 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // try_wait with a suspend-time hint: the warp SLEEPS in hardware until the phase completes (or the hint
-  // expires) instead of busy-polling -- spinning waiters steal issue slots from the single MMA-issuer /
-  // TMA-producer threads (measured: 10x slowdown of the issue loop).  A watchdog turns a protocol bug
-  // (a wait that can never complete) into a trap instead of a hung GPU.
+  // Plain try_wait loop (the default suspend window is short, so the wake-up is prompt; a suspend-time HINT
+  // was measured to add a ~730-cycle wake-up quantum to every blocking wait).  The waiters that spin are the
+  // low warp ids; the single-thread critical roles sit on the highest warp ids, which the arbiter favours.
+  // A watchdog turns a protocol bug (a wait that can never complete) into a trap instead of a hung GPU.
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t spins = 0;; ++spins) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
         "selp.u32 %0, 1, 0, P1;\n"
         "}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if ((spins & 0x3f) == 0x3f) {
+    if ((spins & 0xfff) == 0xfff) {
       long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
     }
   }
+}
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc) {
+  long long t = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -90,6 +98,12 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
   uint32_t pred = 0;
   asm volatile("{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %1;\n@%%px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xFFFFFFFFu));
   return pred;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -145,6 +159,17 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                  \
       : "r"(taddr))
 
+#define TMEM_LD_16(taddr, v)                                                                                    \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),      \
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])  \
+               : "r"(taddr))
+
+#define TMEM_ST_8(taddr, v)                                                                                  \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), \
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])                     \
+               : "memory")
+
 #define TMEM_ST_16(taddr, v)                                                                                   \
   asm volatile(                                                                                                \
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
@@ -152,19 +177,42 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
       "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])             \
       : "memory")
 
+// descriptor given as (lo, hi) words: only the low word (address field) varies per MMA
+__device__ __forceinline__ void tc_mma_ss2(uint32_t d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 ad, {%1, %3};\nmov.b64 bd, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, p;\n}\n" ::"r"(d),
+      "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts2(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 bd, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n}\n" ::"r"(d),
+      "r"(a_tmem), "r"(blo), "r"(hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// KXT / KHT: compile-time We/64 and H/64 (0 = run-time)
+template <int KXT, int KHT>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ LstmTcParams P) {
+lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_wx, const __grid_constant__ CUtensorMap tmap_wh,
+               const __grid_constant__ CUtensorMap tmap_w2d, const __grid_constant__ LstmTcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KBx = P.We / KBLK, KBh = P.H / KBLK, NC = P.H / CHUNK_UNITS, NS = P.n_stages;
+  const int KBx = KXT ? KXT : P.We / KBLK, KBh = KHT ? KHT : P.H / KBLK, NC = P.H / CHUNK_UNITS, NS = P.n_stages;
   const int row0 = blockIdx.x * 128;
   const int t0 = P.t_start;
   const bool has_init = P.init_h != nullptr;
 
   uint8_t* x_smem = smem;                                   // [KBx] tiles [128 x 64] fp16 SW128
-  uint8_t* w_smem = x_smem + (size_t)KBx * TILE_BYTES;      // [NS] ring
-  float* bias_s = reinterpret_cast<float*>(w_smem + (size_t)NS * TILE_BYTES);   // [4H]
+  // weight ring: NS slots, each holds the x-part OR the h-part of one chunk ([128 gate cols x (KBx|KBh) k-blocks],
+  // ONE 3-D TMA instruction per slot: a single issuing thread sustains only ~1 bulk load per ~700 cycles)
+  const int KBmax = KBx > KBh ? KBx : KBh;
+  const uint32_t slot_bytes = (uint32_t)KBmax * TILE_BYTES;
+  uint8_t* w_smem = x_smem + (size_t)KBx * TILE_BYTES;      // [NS] slots
+  float* bias_s = reinterpret_cast<float*>(w_smem + (size_t)NS * slot_bytes);   // [4H]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 4 * P.H);
   // bars: full[NS], empty[NS], x_full, x_empty, h_full, acc_full[2], acc_empty[2]
   const uint32_t bar_full = smem_u32(bars);
@@ -179,10 +227,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   for (int i = threadIdx.x; i < 4 * P.H; i += LSTM_THREADS) bias_s[i] = P.bias_r[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_xf, 128);
+    mbar_init(bar_xf, 32);
     mbar_init(bar_xe, 1);
-    mbar_init(bar_hf, 4);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, 4); }
+    mbar_init(bar_hf, 8);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -202,13 +250,20 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       for (int t = t0; t < P.T; ++t) {
         const bool has_state = has_init || t > t0;
         for (int c = 0; c < NC; ++c) {
-          const int nkb = KBx + (has_state ? KBh : 0);
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int nparts = has_state ? 2 : 1;
+          for (int part = 0; part < nparts; ++part, ++it) {
             const uint32_t s = it % NS, ph = (it / NS) & 1;
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
             if (elect_one_sync()) {
-              mbar_expect_tx(bar_full + 8 * s, TILE_BYTES);
-              tma_load_2d(smem_u32(w_smem + (size_t)s * TILE_BYTES), &tmap_w, bar_full + 8 * s, kb * KBLK, c * 128);
+              const uint32_t dst = smem_u32(w_smem + (size_t)s * slot_bytes);
+              const int nkb = part == 0 ? KBx : KBh, kb0 = part == 0 ? 0 : KBx;
+              mbar_expect_tx(bar_full + 8 * s, (uint32_t)nkb * TILE_BYTES);
+              if (P.use3d) {
+                tma_load_3d(dst, part == 0 ? &tmap_wx : &tmap_wh, bar_full + 8 * s, 0, c * 128, kb0);
+              } else {
+                for (int kb = 0; kb < nkb; ++kb)
+                  tma_load_2d(dst + (uint32_t)kb * TILE_BYTES, &tmap_w2d, bar_full + 8 * s, (kb0 + kb) * KBLK, c * 128);
+              }
             }
             __syncwarp();
           }
@@ -220,6 +275,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     {
       const uint32_t idesc = make_idesc_f16(128, 128);
       uint32_t it = 0, gchunk = 0;
+      long long w_acce = 0, w_xf = 0, w_full = 0, w_hf = 0, t_begin = clock64();
       for (int t = t0; t < P.T; ++t) {
         const int step = t - t0;
         const bool has_state = has_init || t > t0;
@@ -229,20 +285,34 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           const int buf = gchunk & 1;
           const uint32_t use = gchunk >> 1;
           const uint32_t d = tmem_base + 256u + (uint32_t)(buf * 128);
-          mbar_wait(bar_acce + 8 * buf, (use & 1) ^ 1);
+          mbar_wait_timed(bar_acce + 8 * buf, (use & 1) ^ 1, w_acce);
           tc_fence_after();
-          if (c == 0) { mbar_wait(bar_xf, step & 1); tc_fence_after(); }
-          for (int kb = 0; kb < KBx; ++kb, ++it) {
+          if (c == 0) { mbar_wait_timed(bar_xf, step & 1, w_xf); tc_fence_after(); }
+          {   // x part: one slot
             const uint32_t s = it % NS, ph = (it / NS) & 1;
-            mbar_wait(bar_full + 8 * s, ph);
+            ++it;
+            mbar_wait_timed(bar_full + 8 * s, ph, w_full);
             tc_fence_after();
             if (elect_one_sync()) {
-              const uint64_t adesc = make_sw128_desc(smem_u32(x_smem + (size_t)kb * TILE_BYTES));
-              const uint64_t bdesc = make_sw128_desc(smem_u32(w_smem + (size_t)s * TILE_BYTES));
+              const uint64_t b0 = make_sw128_desc(smem_u32(w_smem + (size_t)s * slot_bytes));
+              const uint64_t a0 = make_sw128_desc(smem_u32(x_smem));
+              const uint32_t blo = (uint32_t)b0, alo = (uint32_t)a0, hi = (uint32_t)(b0 >> 32);
+              if (KXT > 0) {
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) tc_mma_ss(d, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+                for (int kb = 0; kb < (KXT > 0 ? KXT : 1); ++kb)
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    tc_mma_ss2(d, alo + (uint32_t)(kb * (TILE_BYTES >> 4) + 2 * k4), blo + (uint32_t)(kb * (TILE_BYTES >> 4) + 2 * k4), hi, idesc,
+                               (kb | k4) ? 1u : 0u);
+              } else {
+                for (int kb = 0; kb < KBx; ++kb)
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    tc_mma_ss2(d, alo + (uint32_t)(kb * (TILE_BYTES >> 4) + 2 * k4), blo + (uint32_t)(kb * (TILE_BYTES >> 4) + 2 * k4), hi, idesc,
+                               (kb | k4) ? 1u : 0u);
+              }
               tc_commit(bar_empty + 8 * s);
-              if (c == NC - 1 && kb == KBx - 1) tc_commit(bar_xe);      // x_t fully consumed once these MMAs retire
+              if (c == NC - 1) tc_commit(bar_xe);      // x_t fully consumed once these MMAs retire
             }
             __syncwarp();
           }
@@ -250,53 +320,81 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             if (c == 0) {
               // completions of h_full: [initial state staged (only with init)], end of step t0, t0+1, ...
               const uint32_t idx = has_init ? (uint32_t)step : (uint32_t)(step - 1);
-              mbar_wait(bar_hf, idx & 1);
+              mbar_wait_timed(bar_hf, idx & 1, w_hf);
               tc_fence_after();
             }
-            for (int kb = 0; kb < KBh; ++kb, ++it) {
-              const uint32_t s = it % NS, ph = (it / NS) & 1;
-              mbar_wait(bar_full + 8 * s, ph);
-              tc_fence_after();
-              if (elect_one_sync()) {
-                const uint64_t bdesc = make_sw128_desc(smem_u32(w_smem + (size_t)s * TILE_BYTES));
+            const uint32_t s = it % NS, ph = (it / NS) & 1;
+            ++it;
+            mbar_wait_timed(bar_full + 8 * s, ph, w_full);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              const uint64_t b0 = make_sw128_desc(smem_u32(w_smem + (size_t)s * slot_bytes));
+              const uint32_t blo = (uint32_t)b0, hi = (uint32_t)(b0 >> 32);
+              if (KHT > 0) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) tc_mma_ts(d, h_src + (uint32_t)(kb * 32 + k4 * 8), bdesc + 2 * k4, idesc, 1u);
-                tc_commit(bar_empty + 8 * s);
+                for (int kb = 0; kb < (KHT > 0 ? KHT : 1); ++kb)
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    tc_mma_ts2(d, h_src + (uint32_t)(kb * 32 + k4 * 8), blo + (uint32_t)(kb * (TILE_BYTES >> 4) + 2 * k4), hi, idesc, 1u);
+              } else {
+                for (int kb = 0; kb < KBh; ++kb)
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    tc_mma_ts2(d, h_src + (uint32_t)(kb * 32 + k4 * 8), blo + (uint32_t)(kb * (TILE_BYTES >> 4) + 2 * k4), hi, idesc, 1u);
               }
-              __syncwarp();
+              tc_commit(bar_empty + 8 * s);
             }
+            __syncwarp();
           }
           if (elect_one_sync()) tc_commit(bar_accf + 8 * buf);
           __syncwarp();
         }
       }
+      if (P.dbg && lane == 0) {
+        long long* o = P.dbg + blockIdx.x * 8;
+        o[0] = w_acce; o[1] = w_xf; o[2] = w_full; o[3] = w_hf; o[4] = clock64() - t_begin;
+      }
     }
-  } else if (warp >= 4 && warp < 8) {   // gather warps 4..7
-    // ===== embedding gather: thread == row, cp.async 16 B chunks into the 128B-swizzled tiles =====
-    const int r = (warp - 4) * 32 + lane;
-    const int grow = min(row0 + r, P.B - 1);
-    const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+  } else if (warp == 11) {
+    // ===== embedding gather (one warp, 4 rows per lane): cp.async 16 B chunks into the 128B-swizzled x tiles =====
+    int grow[4];
+    uint32_t row_off[4];
+    int tok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = q * 32 + lane;
+      grow[q] = min(row0 + r, P.B - 1);
+      row_off[q] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+      tok[q] = __ldg(P.tokens + (size_t)grow[q] * P.T + t0);
+    }
     for (int t = t0; t < P.T; ++t) {
       const int step = t - t0;
       mbar_wait(bar_xe, (step & 1) ^ 1);
-      const int tok = __ldg(P.tokens + (size_t)grow * P.T + t);
-      const __half* src = P.emb + (size_t)tok * P.We;
-      for (int kb = 0; kb < KBx; ++kb) {
-        const uint32_t tile = smem_u32(x_smem + (size_t)kb * TILE_BYTES) + row_off;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t dst = tile + (uint32_t)(((j ^ (r & 7)) * 16));
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + kb * KBLK + j * 8) : "memory");
+      for (int q = 0; q < 4; ++q) {
+        const __half* src = P.emb + (size_t)tok[q] * P.We;
+        const uint32_t sw = (uint32_t)((q * 32 + lane) & 7);
+        for (int kb = 0; kb < KBx; ++kb) {
+          const uint32_t tile = smem_u32(x_smem + (size_t)kb * TILE_BYTES) + row_off[q];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t dst = tile + (uint32_t)(((j ^ sw) * 16));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + kb * KBLK + j * 8) : "memory");
+          }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      if (t + 1 < P.T) {          // next step's token ids while the rows are in flight
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tok[q] = __ldg(P.tokens + (size_t)grow[q] * P.T + t + 1);
+      }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       mbar_arrive(bar_xf);
     }
-  } else if (warp < 4) {
-    // ===== epilogue: thread == batch row =====
-    const int quarter = warp;
+  } else if (warp < 8) {
+    // ===== epilogue: 8 warps; thread == (batch row, half of the chunk's 32 hidden units) =====
+    const int quarter = warp & 3, half = warp >> 2;
     const int r = quarter * 32 + lane;
     const int grow = row0 + r;
     const bool valid = grow < P.B;
@@ -305,13 +403,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     if (has_init) {
       // stage the broadcast initial state: h -> TMEM buffer (t0+1)&1 (read by step t0), c -> scratch
       const uint32_t hdst = lane_base + (uint32_t)(((t0 + 1) & 1) * 128);
-      for (int u0 = 0; u0 < P.H; u0 += 32) {
-        uint32_t pk[16];
+      for (int u0 = half * 16; u0 < P.H; u0 += 32) {
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_f16x2(__ldg(P.init_h + u0 + 2 * i), __ldg(P.init_h + u0 + 2 * i + 1));
-        TMEM_ST_16(hdst + u0 / 2, pk);
+        for (int i = 0; i < 8; ++i) pk[i] = pack_f16x2(__ldg(P.init_h + u0 + 2 * i), __ldg(P.init_h + u0 + 2 * i + 1));
+        TMEM_ST_8(hdst + u0 / 2, pk);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) crow[u0 + i] = __ldg(P.init_c + u0 + i);
+        for (int i = 0; i < 16; ++i) crow[u0 + i] = __ldg(P.init_c + u0 + i);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -319,6 +417,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       if (lane == 0) mbar_arrive(bar_hf);      // phase 0 of h_full == "initial state staged"
     }
     uint32_t gchunk = 0;
+    long long w_accf = 0, t_begin_e = clock64();
     for (int t = t0; t < P.T; ++t) {
       const bool has_c = has_init || t > t0;
       const bool last = t == P.T - 1;
@@ -326,68 +425,67 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       for (int c = 0; c < NC; ++c, ++gchunk) {
         const int buf = gchunk & 1;
         const uint32_t use = gchunk >> 1;
-        const int u0 = c * CHUNK_UNITS;
-        // previous cell state for this row / chunk (fp32, issued before the accumulator wait)
-        float cold[32];
+        const int u0 = c * CHUNK_UNITS + half * 16;       // first hidden unit of this thread's 16
+        // previous cell state for this row / half chunk (fp32, issued before the accumulator wait)
+        float cold[16];
         if (has_c) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             float4 v = *reinterpret_cast<const float4*>(crow + u0 + q * 4);
             cold[q * 4] = v.x; cold[q * 4 + 1] = v.y; cold[q * 4 + 2] = v.z; cold[q * 4 + 3] = v.w;
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) cold[i] = 0.f;
+          for (int i = 0; i < 16; ++i) cold[i] = 0.f;
         }
-        mbar_wait(bar_accf + 8 * buf, use & 1);
+        mbar_wait_timed(bar_accf + 8 * buf, use & 1, w_accf);
         tc_fence_after();
-        const uint32_t acc = lane_base + 256u + (uint32_t)(buf * 128);
-        const float* bs = bias_s + c * 128;
-        uint32_t vi[32], vj[32];
-        TMEM_LD_32(acc, vi);
-        TMEM_LD_32(acc + 32, vj);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          p[i] = sigmoid_approx(__uint_as_float(vi[i]) + bs[i]) * tanh_approx(__uint_as_float(vj[i]) + bs[32 + i]);
-        TMEM_LD_32(acc + 64, vi);     // f
-        TMEM_LD_32(acc + 96, vj);     // o
+        const uint32_t acc = lane_base + 256u + (uint32_t)(buf * 128 + half * 16);
+        const float* bs = bias_s + c * 128 + half * 16;
+        uint32_t vi[16], vj[16], vf[16], vo[16];
+        TMEM_LD_16(acc, vi);
+        TMEM_LD_16(acc + 32, vj);
+        TMEM_LD_16(acc + 64, vf);
+        TMEM_LD_16(acc + 96, vo);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         // accumulator buffer is free as soon as it sits in registers
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
-        uint32_t pk[16];
+        uint32_t pk[8];
+        float hv[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float c0 = fmaf(cold[i], sigmoid_approx(__uint_as_float(vi[i]) + bs[64 + i]), p[i]);          // bias_r has +1 folded in
-          float c1 = fmaf(cold[i + 1], sigmoid_approx(__uint_as_float(vi[i + 1]) + bs[64 + i + 1]), p[i + 1]);
-          float h0 = tanh_approx(c0) * sigmoid_approx(__uint_as_float(vj[i]) + bs[96 + i]);
-          float h1 = tanh_approx(c1) * sigmoid_approx(__uint_as_float(vj[i + 1]) + bs[96 + i + 1]);
+        for (int i = 0; i < 16; i += 2) {
+          float p0 = sigmoid_approx(__uint_as_float(vi[i]) + bs[i]) * tanh_approx(__uint_as_float(vj[i]) + bs[32 + i]);
+          float p1 = sigmoid_approx(__uint_as_float(vi[i + 1]) + bs[i + 1]) * tanh_approx(__uint_as_float(vj[i + 1]) + bs[32 + i + 1]);
+          float c0 = fmaf(cold[i], sigmoid_approx(__uint_as_float(vf[i]) + bs[64 + i]), p0);          // bias_r has +1 folded in
+          float c1 = fmaf(cold[i + 1], sigmoid_approx(__uint_as_float(vf[i + 1]) + bs[64 + i + 1]), p1);
+          float h0 = tanh_approx(c0) * sigmoid_approx(__uint_as_float(vo[i]) + bs[96 + i]);
+          float h1 = tanh_approx(c1) * sigmoid_approx(__uint_as_float(vo[i + 1]) + bs[96 + i + 1]);
           cold[i] = c0; cold[i + 1] = c1;
-          p[i] = h0; p[i + 1] = h1;
+          hv[i] = h0; hv[i + 1] = h1;
           pk[i >> 1] = pack_f16x2(h0, h1);
         }
         if (!last) {
-          TMEM_ST_16(hdst + (uint32_t)(u0 / 2), pk);
+          TMEM_ST_8(hdst + (uint32_t)(u0 / 2), pk);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
+          for (int q = 0; q < 4; ++q)
             *reinterpret_cast<float4*>(crow + u0 + q * 4) = make_float4(cold[q * 4], cold[q * 4 + 1], cold[q * 4 + 2], cold[q * 4 + 3]);
         } else if (valid) {
           float* ho = P.h_out + (size_t)grow * P.H + u0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(ho + q * 4) = make_float4(p[q * 4], p[q * 4 + 1], p[q * 4 + 2], p[q * 4 + 3]);
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(ho + q * 4) = make_float4(hv[q * 4], hv[q * 4 + 1], hv[q * 4 + 2], hv[q * 4 + 3]);
         }
       }
       if (!last) {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_hf);    // h_t complete in TMEM (all chunks of this warp's rows)
+        if (lane == 0) mbar_arrive(bar_hf);    // h_t complete in TMEM (this warp's rows / unit halves)
       }
     }
+    if (P.dbg && warp == 0 && lane == 0) { P.dbg[blockIdx.x * 8 + 5] = w_accf; P.dbg[blockIdx.x * 8 + 6] = clock64() - t_begin_e; }
   }
   tc_fence_before();
   __syncthreads();
@@ -439,15 +537,31 @@ int lstm_tc_prepare(TcTower& tt, const float* K, const float* b, int We, int H, 
     set_error("cuTensorMapEncodeTiled entry point not available");
     return SSE_ECUDA;
   }
-  cuuint64_t gdim[2] = {(cuuint64_t)(We + H), (cuuint64_t)(4 * H)};
-  cuuint64_t gstr[1] = {(cuuint64_t)(We + H) * 2};
-  cuuint32_t box[2] = {KBLK, 128};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = reinterpret_cast<PFN_encodeTiled>(p)(reinterpret_cast<CUtensorMap*>(tt.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                                                    tt.wt, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(Wt) failed (%d)", (int)r); return SSE_ECUDA; }
+  // 3-D view of Wt[4H, We+H] fp16: (k within a 64-wide block, gate row, k-block); one box = a half chunk
+  // [128 gate rows x KBx (or KBh) k-blocks], landing in smem as consecutive [128 x 64] SWIZZLE_128B tiles.
+  PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(p);
+  tt.use3d = getenv("SSE_LSTM_NO3D") == nullptr;
+  const int KBx = We / KBLK, KBh = H / KBLK;
+  cuuint64_t gdim[3] = {(cuuint64_t)KBLK, (cuuint64_t)(4 * H), (cuuint64_t)(KBx + KBh)};
+  cuuint64_t gstr[2] = {(cuuint64_t)(We + H) * 2, (cuuint64_t)KBLK * 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  for (int part = 0; part < 2; ++part) {
+    cuuint32_t box[3] = {KBLK, 128, (cuuint32_t)(part == 0 ? KBx : KBh)};
+    CUresult r = enc(reinterpret_cast<CUtensorMap*>(part == 0 ? tt.tmap : tt.tmap_h), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, tt.wt, gdim,
+                     gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) tt.use3d = false;
+  }
+  {
+    cuuint64_t gdim2[2] = {(cuuint64_t)(We + H), (cuuint64_t)(4 * H)};
+    cuuint64_t gstr2[1] = {(cuuint64_t)(We + H) * 2};
+    cuuint32_t box2[2] = {KBLK, 128};
+    cuuint32_t estr2[2] = {1, 1};
+    CUresult r = enc(reinterpret_cast<CUtensorMap*>(tt.tmap2d), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, tt.wt, gdim2, gstr2, box2, estr2,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(Wt) failed (%d)", (int)r); return SSE_ECUDA; }
+  }
   tt.valid = true;
   return SSE_OK;
 }
@@ -460,19 +574,39 @@ int lstm_forward_tc(const int32_t* tokens, int B, int T, int t_start, const __ha
   p.tokens = tokens; p.emb = emb_f16; p.bias_r = tt.bias_r; p.init_h = init_h; p.init_c = init_c;
   p.c_scratch = c_scratch; p.h_out = h_out; p.B = B; p.T = T; p.t_start = t_start; p.We = We; p.H = H;
   const size_t fixed = 1024 + (size_t)(We / KBLK) * TILE_BYTES + (size_t)4 * H * 4 + 512;
-  int NS = (int)((232448 - fixed) / TILE_BYTES);
-  if (NS > 12) NS = 12;
+  const size_t slot = (size_t)std::max(We, H) / KBLK * TILE_BYTES;
+  int NS = (int)((232448 - fixed) / slot);
+  if (NS > 6) NS = 6;
   if (NS < 2) { set_error("lstm_tc: shared memory budget"); return SSE_EINVAL; }
   p.n_stages = NS;
-  const size_t smem = fixed + (size_t)NS * TILE_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SSE_CUDA_OK(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_done = true;
-  }
-  lstm_tc_kernel<<<cdiv(B, 128), LSTM_THREADS, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(tt.tmap), p);
+  p.use3d = tt.use3d ? 1 : 0;
+  p.dbg = nullptr;
+  const bool want_dbg = getenv("SSE_LSTM_DEBUG") != nullptr;
+  long long* d_dbg = nullptr;
+  const int grid = cdiv(B, 128);
+  if (want_dbg) { cudaMalloc(&d_dbg, (size_t)grid * 64); cudaMemset(d_dbg, 0, (size_t)grid * 64); p.dbg = d_dbg; }
+  const size_t smem = fixed + (size_t)NS * slot;
+  typedef void (*lstm_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const LstmTcParams);
+  lstm_fn fn = (We == 256 && H == 256) ? lstm_tc_kernel<4, 4> : lstm_tc_kernel<0, 0>;
+  SSE_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  fn<<<cdiv(B, 128), LSTM_THREADS, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(tt.tmap),
+                                                            *reinterpret_cast<const CUtensorMap*>(tt.tmap_h),
+                                                            *reinterpret_cast<const CUtensorMap*>(tt.tmap2d), p);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
+  if (want_dbg) {
+    std::vector<long long> hd((size_t)grid * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_dbg);
+    const char* nm[7] = {"mma_wait_acce", "mma_wait_xfull", "mma_wait_wfull", "mma_wait_hfull", "mma_total", "epi_wait_accf", "epi_total"};
+    for (int c = 0; c < 7; ++c) {
+      long long sm = 0;
+      for (int i = 0; i < grid; ++i) sm += hd[(size_t)i * 8 + c];
+      fprintf(stderr, "[lstm dbg] %-15s avg %10lld cycles  (grid %d, steps %d, chunks/step %d, NS %d, use3d %d)\n", nm[c], sm / grid, grid,
+              T - t_start, H / CHUNK_UNITS, NS, p.use3d);
+    }
+  }
   return SSE_OK;
 }
 

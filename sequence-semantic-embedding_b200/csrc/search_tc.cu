@@ -55,6 +55,7 @@ struct ScanParams {
   const __half* qb;         // [Qp, E] fp16 queries
   long long* dbg;                  // optional [items][8] cycle counters (nullptr = off)
   int dbg_flags;                   // timing experiments only: 1 = no TMA loads, 2 = no MMA issue
+  int use3d;                       // one 3-D TMA instruction per index tile (else KB 2-D loads)
   int group_first_item[MAX_GROUPS];
   int group_items[MAX_GROUPS];
   int group_mt[MAX_GROUPS];        // valid m-tiles in the group
@@ -83,24 +84,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // try_wait with a suspend-time hint: the warp SLEEPS in hardware until the phase completes (or the hint
-  // expires) instead of busy-polling -- spinning waiters steal issue slots from the single MMA-issuer /
-  // TMA-producer threads (measured: 10x slowdown of the issue loop).  A watchdog turns a protocol bug
-  // (a wait that can never complete) into a trap instead of a hung GPU.
+  // Plain try_wait loop (the default suspend window is short, so the wake-up is prompt; a suspend-time HINT
+  // was measured to add a ~730-cycle wake-up quantum to every blocking wait).  The waiters that spin are the
+  // low warp ids; the single-thread critical roles sit on the highest warp ids, which the arbiter favours.
+  // A watchdog turns a protocol bug (a wait that can never complete) into a trap instead of a hung GPU.
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t spins = 0;; ++spins) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
         "selp.u32 %0, 1, 0, P1;\n"
         "}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if ((spins & 0x3f) == 0x3f) {
+    if ((spins & 0xfff) == 0xfff) {
       long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
@@ -126,6 +127,12 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
   uint32_t pred = 0;
   asm volatile("{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %1;\n@%%px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xFFFFFFFFu));
   return pred;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -201,7 +208,23 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
       : "memory");
 }
 
-template <int MODE>
+// D[tmem] (+)= A[tmem] * B[smem desc given as (lo, hi) words]: only the low word (address field) varies per MMA
+__device__ __forceinline__ void tc_mma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 bd;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 bd, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// KBT / TNT: compile-time E/64 and tile width (0 = take them from the params at run time)
+template <int MODE, int KBT, int TNT>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant__ ScanParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -217,7 +240,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   const int mt_count = P.group_mt[g];
   const int j0 = (int)(((int64_t)P.n_j * r_in_g) / R);
   const int j1 = (int)(((int64_t)P.n_j * (r_in_g + 1)) / R);
-  const int KB = P.kb, NG = P.n_stages, TN = P.tn;      // n_stages = number of TILE slots in the ring
+  const int KB = KBT ? KBT : P.kb, NG = P.n_stages, TN = TNT ? TNT : P.tn;   // n_stages = number of TILE slots in the ring
   const int E = KB * KBLK;
   const uint32_t kb_bytes = (uint32_t)TN * KBLK * 2;     // one [TN x 64] fp16 SW128 sub-tile
   const uint32_t slot_bytes = kb_bytes * KB;             // one whole index tile [TN x E]
@@ -263,9 +286,13 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
             mbar_arrive(bar_full + 8 * s);
           } else {
             mbar_expect_tx(bar_full + 8 * s, slot_bytes);
-            for (int kb = 0; kb < KB; ++kb)
-              tma_load_2d(smem_u32(b_smem + (size_t)s * slot_bytes + (size_t)kb * kb_bytes), &tmap_idx, bar_full + 8 * s,
-                          kb * KBLK, tile * TN);
+            if (P.use3d) {
+              tma_load_3d(smem_u32(b_smem + (size_t)s * slot_bytes), &tmap_idx, bar_full + 8 * s, 0, tile * TN, 0);
+            } else {
+              for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(smem_u32(b_smem + (size_t)s * slot_bytes + (size_t)kb * kb_bytes), &tmap_idx, bar_full + 8 * s,
+                            kb * KBLK, tile * TN);
+            }
           }
         }
         __syncwarp();
@@ -289,16 +316,28 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         tc_fence_after();
         if (elect_one_sync()) {
          if (!(P.dbg_flags & 2)) {
-          const uint32_t slot = smem_u32(b_smem + (size_t)s * slot_bytes);
-          for (int mt = 0; mt < mt_count; ++mt) {
-            const uint32_t d = tmem_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
-            const uint32_t a0 = tmem_base + (uint32_t)(mt * (E / 2));
-            for (int kb = 0; kb < KB; ++kb) {
-              const uint64_t bdesc = make_sw128_desc(slot + (uint32_t)kb * kb_bytes);
-              const uint32_t a = a0 + (uint32_t)(kb * (KBLK / 2));
+          const uint64_t bd0 = make_sw128_desc(smem_u32(b_smem + (size_t)s * slot_bytes));
+          const uint32_t bd_lo = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
+          const uint32_t kb_units = kb_bytes >> 4;           // descriptor address units (16 B) per k-block
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)   // 4 x (K=16): A advances 8 columns, B 32 bytes (= 2 descriptor units)
-                tc_mma_f16_ts(d, a + 8 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+          for (int mt = 0; mt < 2; ++mt) {
+            if (mt < mt_count) {
+              const uint32_t d = tmem_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
+              const uint32_t a0 = tmem_base + (uint32_t)(mt * (E / 2));
+              if (KBT > 0) {
+#pragma unroll
+                for (int kb = 0; kb < (KBT > 0 ? KBT : 1); ++kb)
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)   // 4 x (K=16): A advances 8 columns, B 32 bytes (= 2 descriptor units)
+                    tc_mma_f16_ts2(d, a0 + (uint32_t)(kb * (KBLK / 2) + 8 * k4), bd_lo + (uint32_t)kb * kb_units + 2 * k4, bd_hi, idesc,
+                                   (kb | k4) ? 1u : 0u);
+              } else {
+                for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    tc_mma_f16_ts2(d, a0 + (uint32_t)(kb * (KBLK / 2) + 8 * k4), bd_lo + (uint32_t)kb * kb_units + 2 * k4, bd_hi, idesc,
+                                   (kb | k4) ? 1u : 0u);
+              }
             }
           }
          }
@@ -682,6 +721,20 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int E, int box_ro
   return SSE_OK;
 }
 
+// 3-D view (k within a 64-wide block, index row, k-block), box = one whole [box_rows x E] tile
+int make_tmap3d(CUtensorMap* tm, const void* base, int64_t rows, int E, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return SSE_ECUDA;
+  cuuint64_t gdim[3] = {(cuuint64_t)KBLK, (cuuint64_t)rows, (cuuint64_t)(E / KBLK)};
+  cuuint64_t gstr[2] = {(cuuint64_t)E * 2, (cuuint64_t)KBLK * 2};
+  cuuint32_t box[3] = {KBLK, (cuuint32_t)box_rows, (cuuint32_t)(E / KBLK)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SSE_OK : SSE_ECUDA;
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -705,6 +758,9 @@ int search_tc_prepare(TcIndex& ti, const float* index_f32, int64_t N, int E, cud
   SSE_CUDA_OK(cudaGetLastError());
   SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap), ti.h16, N, E, 128));
   SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap64), ti.h16, N, E, 64));
+  ti.use3d = getenv("SSE_SCAN_NO3D") == nullptr &&
+             make_tmap3d(reinterpret_cast<CUtensorMap*>(ti.tmap3d), ti.h16, N, E, 128) == SSE_OK &&
+             make_tmap3d(reinterpret_cast<CUtensorMap*>(ti.tmap3d64), ti.h16, N, E, 64) == SSE_OK;
   ti.tmap_ok = true;
   return SSE_OK;
 }
@@ -791,19 +847,23 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E, qb, qn);
   if (launches) ++*launches;
 
-  const CUtensorMap& tmi = *reinterpret_cast<const CUtensorMap*>(tn == 128 ? ti.tmap : ti.tmap64);
+  const CUtensorMap& tmi = ti.use3d ? *reinterpret_cast<const CUtensorMap*>(tn == 128 ? ti.tmap3d : ti.tmap3d64)
+                                    : *reinterpret_cast<const CUtensorMap*>(tn == 128 ? ti.tmap : ti.tmap64);
   sp.qb = qb;
+  sp.use3d = ti.use3d ? 1 : 0;
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    SSE_CUDA_OK(cudaFuncSetAttribute(scan_kernel<MODE_TILEMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    SSE_CUDA_OK(cudaFuncSetAttribute(scan_kernel<MODE_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_done = true;
-  }
+  // specialised instances for the common E = 256 (fully unrolled MMA issue), generic otherwise
+  typedef void (*scan_fn)(const CUtensorMap, const ScanParams);
+  scan_fn fn_tilemax, fn_filter;
+  if (KB == 4 && tn == 64) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 64>; fn_filter = scan_kernel<MODE_FILTER, 4, 64>; }
+  else if (KB == 4 && tn == 128) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 128>; fn_filter = scan_kernel<MODE_FILTER, 4, 128>; }
+  else { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0>; fn_filter = scan_kernel<MODE_FILTER, 0, 0>; }
+  SSE_CUDA_OK(cudaFuncSetAttribute(fn_tilemax, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  SSE_CUDA_OK(cudaFuncSetAttribute(fn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
 
   // pass A: tile maxima over the strided sample
   sp.n_j = n_s; sp.tile_step = s_step; sp.tilemax = tm; sp.tau = nullptr;
-  scan_kernel<MODE_TILEMAX><<<items, SCAN_THREADS, smem, st>>>(tmi, sp);
+  fn_tilemax<<<items, SCAN_THREADS, smem, st>>>(tmi, sp);
   if (launches) ++*launches;
   select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, qn, tnorm, tau, mg);
   if (launches) ++*launches;
@@ -815,7 +875,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   sp.cand_s = reinterpret_cast<float*>(w + o_cs);
   sp.cand_i = reinterpret_cast<int32_t*>(w + o_ci);
   sp.cand_cnt = reinterpret_cast<int32_t*>(w + o_cc);
-  scan_kernel<MODE_FILTER><<<items, SCAN_THREADS, smem, st>>>(tmi, sp);
+  fn_filter<<<items, SCAN_THREADS, smem, st>>>(tmi, sp);
   if (launches) ++*launches;
 
   FinParams fp;

@@ -103,6 +103,9 @@ struct TcIndex {
   int E = 0;
   alignas(64) unsigned char tmap[128];     // CUtensorMap of the fp16 index, box 64 x 128 rows
   alignas(64) unsigned char tmap64[128];   // same, box 64 x 64 rows
+  alignas(64) unsigned char tmap3d[128];   // 3-D (k-in-block, row, k-block), box = whole [128 x E] tile
+  alignas(64) unsigned char tmap3d64[128]; // 3-D, box = whole [64 x E] tile
+  bool use3d = false;
   bool tmap_ok = false;
 };
 bool search_tc_supported(int E, int64_t N, int k);
@@ -115,7 +118,10 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
 struct TcTower {
   __half* wt = nullptr;     // [4H, We+H] chunk-major transposed weights
   float* bias_r = nullptr;         // [4H] chunk-major bias (+1 folded into the forget gate)
-  alignas(64) unsigned char tmap[128];
+  alignas(64) unsigned char tmap[128];     // 3-D map, box = x part of a chunk
+  alignas(64) unsigned char tmap_h[128];   // 3-D map, box = h part of a chunk
+  alignas(64) unsigned char tmap2d[128];   // 2-D map, box = one [128 x 64] sub-tile (fallback)
+  bool use3d = true;
   bool valid = false;
 };
 bool lstm_tc_supported(int We, int H);
