@@ -1,8 +1,8 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -12
-timeout 300 python scripts/lstm_debug.py 2>&1 | tail -16
-timeout 300 python scripts/scan_debug.py 2>&1 | grep -v "prod_total\|mma_wait_a\|epi_total" | grep -A5 "Q=600 N=1000000 flags=0" | head -8
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+timeout 300 python scripts/lstm_debug.py 2>&1 | grep "encode"
+for r in 64 128; do SSE_LSTM_ROWS=$r timeout 300 python scripts/lstm_debug.py 2>&1 | grep "encode" | head -1; done
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; python -c "
 import json
 d=json.load(open('gpurun_out/bench_n1.json'))

@@ -83,11 +83,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // Plain try_wait loop (the default suspend window is short, so the wake-up is prompt; a suspend-time HINT
-  // was measured to add a ~730-cycle wake-up quantum to every blocking wait).  The waiters that spin are the
-  // low warp ids; the single-thread critical roles sit on the highest warp ids, which the arbiter favours.
-  // A watchdog turns a protocol bug (a wait that can never complete) into a trap instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 32) {
+  // Poll with try_wait and SLEEP between polls (nanosleep): a busy-polling waiter steals issue slots from
+  // the warps that are doing the work on its SM sub-partition (the waiters include the high-priority
+  // single-thread roles, so a spinning producer starved the epilogue warps -- measured 2x slowdown), while
+  // the try_wait suspend-time hint showed a ~700-cycle wake-up quantum.  A watchdog turns a protocol bug
+  // (a wait that can never complete) into a trap instead of a hung GPU.
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t spins = 0;; ++spins) {
@@ -101,6 +102,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
+    if (backoff_ns) __nanosleep(backoff_ns);
     if ((spins & 0xfff) == 0xfff) {
       long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -108,9 +110,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc) {
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc, uint32_t backoff_ns = 32) {
   long long t = clock64();
-  mbar_wait(bar, parity);
+  mbar_wait(bar, parity, backoff_ns);
   acc += clock64() - t;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
@@ -280,7 +282,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         const int jj = j - j0;
         const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
         const int tile = j * P.tile_step;
-        mbar_wait_timed(bar_empty + 8 * s, ph ^ 1, w_empty);
+        mbar_wait_timed(bar_empty + 8 * s, ph ^ 1, w_empty, 64);
         if (elect_one_sync()) {
           if (P.dbg_flags & 1) {
             mbar_arrive(bar_full + 8 * s);
@@ -806,12 +808,17 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   sp.N = N; sp.Qp = Qp; sp.global_offset = global_offset;
   int items = 0;
   {
+    // split ~num_sms CTAs over the m-groups in proportion to their measured cost per index tile:
+    // ~1100 cycles of feed / fixed work + ~475 cycles per resident m-tile (MMA + TMEM read-out).
     int budget = max(num_sms, n_groups);
-    int assigned_mt = 0, assigned_items = 0;
+    double wsum = 0.0, w[MAX_GROUPS];
+    for (int g = 0; g < n_groups; ++g) { int mtc = min(mtg, m_tiles - g * mtg); w[g] = 1100.0 + 475.0 * mtc; wsum += w[g]; }
+    int assigned_items = 0;
+    double acc = 0.0;
     for (int g = 0; g < n_groups; ++g) {
       int mtc = min(mtg, m_tiles - g * mtg);
-      assigned_mt += mtc;
-      int upto = (int)((int64_t)budget * assigned_mt / m_tiles);
+      acc += w[g];
+      int upto = (g == n_groups - 1) ? budget : (int)(budget * acc / wsum + 0.5);
       int cnt = max(1, upto - assigned_items);
       sp.group_first_item[g] = assigned_items;
       sp.group_items[g] = cnt;

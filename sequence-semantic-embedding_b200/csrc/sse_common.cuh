@@ -118,8 +118,8 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
 struct TcTower {
   __half* wt = nullptr;     // [4H, We+H] chunk-major transposed weights
   float* bias_r = nullptr;         // [4H] chunk-major bias (+1 folded into the forget gate)
-  alignas(64) unsigned char tmap[128];     // 3-D map, box = x part of a chunk
-  alignas(64) unsigned char tmap_h[128];   // 3-D map, box = h part of a chunk
+  alignas(64) unsigned char tmap[128];     // 3-D map (k-in-block, gate row, k-block), box = [128 rows x slot_kb k-blocks]
+  int slot_kb = 2;
   alignas(64) unsigned char tmap2d[128];   // 2-D map, box = one [128 x 64] sub-tile (fallback)
   bool use3d = true;
   bool valid = false;
