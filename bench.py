@@ -293,18 +293,27 @@ def run_b200(args):
         roof = {"bound": "hbm", "achieved": bytes_alg / t_s / 1e9, "peak": hbm_gbs, "unit": "GB/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["traffic"] = None
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel from the committed ncu --set full capture
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("targets_per_gpu") == n_local and tj.get("queries") == Q:
+            roof["traffic"] = tj["scan_filter_dram_bytes"]
+            roof["traffic_source"] = tj.get("source")
+    except Exception:
+        pass
     roof["peak_source"] = src
     roof["kernel"] = "search (prep+sample scan+select_tau+filter scan+finalize)" if use_tc else "search_simt_kernel+merge"
     roof["ms_per_launch"] = ms_search
     roof["algorithmic"] = {"flops": flops, "bytes": bytes_alg}
     roof["encoder"] = {"ms": ms_enc, "flops": Q * F_LSTM, "achieved_tflops": Q * F_LSTM / (ms_enc * 1e-3) / 1e12,
-                       "kernel": "lstm_step_kernel x T (fp32 SIMT) + sgemm + l2norm"}
+                       "achieved_frac_of_bf16_peak": Q * F_LSTM / (ms_enc * 1e-3) / 1e12 / bf16_tf,
+                       "kernel": "lstm_tc_kernel (tcgen05, fp16 operands; %d-row tiles at this batch) + sgemm + l2norm" % (128 if Q >= 9472 else (64 if Q >= 4736 else 32))}
 
     total_q = Q * args.steps
     out = {
         "metric": "queries/sec encode+cosine-top-k", "value": total_q / (ms_dev * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 scan + fp32 re-rank; fp32 encoder" if use_tc else "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05 scan + LSTM), exact f32 re-rank of the top-k" if use_tc else "f32",
         "data": "synthetic",
         "config": {"workload": "dual LSTM encoder V=32000 We=H=E=256 T=50 (FULL-length rows), Q=%d queries/step, "
                                "cosine top-%d over N=%d targets per GPU (%d total)" % (Q, k, n_local, n_local * world),

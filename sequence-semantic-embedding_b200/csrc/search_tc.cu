@@ -450,14 +450,24 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
 
 // --------------------------------------------------------------- small kernels
 // q fp32 [Q,E] -> fp16 [Qp,E] (rows >= Q zero), qnorm[Qp]
-__global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, __half* __restrict__ qb,
-                                    float* __restrict__ qnorm) {
+// Padded row p = g * gstride + l  <->  query row g * rpg + l  (l < rpg): every m-group holds the same number
+// of query rows, so all groups cost the same and sweep the index in lock-step (their re-reads hit L2).
+__device__ __forceinline__ int padded_to_query_row(int p, int gstride, int rpg, int Q) {
+  const int g = p / gstride, l = p - g * gstride;
+  const int r = g * rpg + l;
+  return (l < rpg && r < Q) ? r : -1;
+}
+
+// q fp32 [Q,E] -> fp16 [Qp,E] in padded row order (unused rows zero), qnorm[Qp]
+__global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, int gstride, int rpg,
+                                    __half* __restrict__ qb, float* __restrict__ qnorm) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= Qp) return;
+  const int qr = padded_to_query_row(row, gstride, rpg, Q);
   float ss = 0.f;
   for (int j = lane; j < E; j += 32) {
-    float v = row < Q ? q[(size_t)row * E + j] : 0.f;
+    float v = qr >= 0 ? q[(size_t)qr * E + j] : 0.f;
     ss = fmaf(v, v, ss);
     qb[(size_t)row * E + j] = __float2half_rn(v);
   }
@@ -483,13 +493,13 @@ __global__ void max_row_norm_kernel(const float* __restrict__ x, int64_t N, int 
 
 // warp per row: tau[r] = (k-th largest of tilemax[0..n_s)[r]) - 2*eps_r ; rows >= Q: +inf.
 // Each lane keeps its <= 32 strided samples in registers; k rounds of warp arg-max with removal.
-__global__ void select_tau_kernel(const float* __restrict__ tilemax, int n_s, int Qp, int Q, int k,
+__global__ void select_tau_kernel(const float* __restrict__ tilemax, int n_s, int Qp, int Q, int k, int gstride, int rpg,
                                   const float* __restrict__ qnorm, const float* __restrict__ tnorm_max,
                                   float* __restrict__ tau, float* __restrict__ margin) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= Qp) return;
-  if (row >= Q) { if (lane == 0) { tau[row] = CUDART_INF_F; margin[row] = 0.f; } return; }
+  if (padded_to_query_row(row, gstride, rpg, Q) < 0) { if (lane == 0) { tau[row] = CUDART_INF_F; margin[row] = 0.f; } return; }
   float v[32];
 #pragma unroll
   for (int t = 0; t < 32; ++t) {
@@ -524,6 +534,7 @@ __global__ void select_tau_kernel(const float* __restrict__ tilemax, int n_s, in
 
 struct FinParams {
   int n_groups, mtg;
+  int rpg;                 // query rows per m-group
   int group_first_item[MAX_GROUPS];
   int group_items[MAX_GROUPS];
   const float* cand_s;
@@ -569,7 +580,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
   const int rows_per_group = P.mtg * TILE_M;
-  const int g = row / rows_per_group, lrow = row % rows_per_group;
+  const int g = row / P.rpg, lrow = row % P.rpg;
   const int first = P.group_first_item[g], R = P.group_items[g];
   if (tid == 0) { s_total = 0; s_over = 0; }
   __syncthreads();
@@ -598,7 +609,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   if (tid == 0) {
     int m = total;
     if (total >= k) {
-      float cut = cs[k - 1] - P.margin[row];
+      float cut = cs[k - 1] - P.margin[g * rows_per_group + lrow];
       int lo = k, hi = total;          // first index with cs < cut (sorted descending)
       while (lo < hi) { int mid = (lo + hi) >> 1; if (cs[mid] >= cut) lo = mid + 1; else hi = mid; }
       m = lo;
@@ -787,6 +798,8 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   const int n_groups = cdiv(m_tiles, mtg);
   if (n_groups > MAX_GROUPS) { set_error("search_tc: Q=%d too large for one call (max %d rows)", Q, MAX_GROUPS * 2 * TILE_M); return SSE_EINVAL; }
   const int Qp = n_groups * mtg * TILE_M;
+  const int gstride = mtg * TILE_M;                 // padded rows per group
+  const int rpg = cdiv(Q, n_groups);                // query rows per group (equal for all groups)
   const int n_tiles = (int)cdiv64(N, tn);
   int n_s = (int)(N / 16 / tn);
   if (n_s < 64) n_s = 64;
@@ -808,24 +821,16 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   sp.N = N; sp.Qp = Qp; sp.global_offset = global_offset;
   int items = 0;
   {
-    // split ~num_sms CTAs over the m-groups in proportion to their measured cost per index tile:
-    // ~1100 cycles of feed / fixed work + ~475 cycles per resident m-tile (MMA + TMEM read-out).
-    int budget = max(num_sms, n_groups);
-    double wsum = 0.0, w[MAX_GROUPS];
-    for (int g = 0; g < n_groups; ++g) { int mtc = min(mtg, m_tiles - g * mtg); w[g] = 1100.0 + 475.0 * mtc; wsum += w[g]; }
-    int assigned_items = 0;
-    double acc = 0.0;
+    // every group holds rpg query rows (same cost) and gets the same number of work items with IDENTICAL tile
+    // ranges: the CTAs of different groups that share a range run concurrently, so the index is fetched from HBM
+    // about once and the other groups' reads of the same tiles hit L2.
+    const int R = max(1, max(num_sms, n_groups) / n_groups);
     for (int g = 0; g < n_groups; ++g) {
-      int mtc = min(mtg, m_tiles - g * mtg);
-      acc += w[g];
-      int upto = (g == n_groups - 1) ? budget : (int)(budget * acc / wsum + 0.5);
-      int cnt = max(1, upto - assigned_items);
-      sp.group_first_item[g] = assigned_items;
-      sp.group_items[g] = cnt;
-      sp.group_mt[g] = mtc;
-      assigned_items += cnt;
+      sp.group_first_item[g] = g * R;
+      sp.group_items[g] = R;
+      sp.group_mt[g] = min(mtg, cdiv(min(rpg, Q - g * rpg), TILE_M));
     }
-    items = assigned_items;
+    items = n_groups * R;
   }
 
   // workspace carve
@@ -851,7 +856,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   float* tm = reinterpret_cast<float*>(w + o_tm);
   float* tnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.h16) + align_up((size_t)N * E * 2, 16));
 
-  prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E, qb, qn);
+  prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E, gstride, rpg, qb, qn);
   if (launches) ++*launches;
 
   const CUtensorMap& tmi = ti.use3d ? *reinterpret_cast<const CUtensorMap*>(tn == 128 ? ti.tmap3d : ti.tmap3d64)
@@ -872,7 +877,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   sp.n_j = n_s; sp.tile_step = s_step; sp.tilemax = tm; sp.tau = nullptr;
   fn_tilemax<<<items, SCAN_THREADS, smem, st>>>(tmi, sp);
   if (launches) ++*launches;
-  select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, qn, tnorm, tau, mg);
+  select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, gstride, rpg, qn, tnorm, tau, mg);
   if (launches) ++*launches;
 
   // pass B: filter over all tiles
@@ -887,7 +892,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
 
   FinParams fp;
   memset(&fp, 0, sizeof(fp));
-  fp.n_groups = n_groups; fp.mtg = mtg;
+  fp.n_groups = n_groups; fp.mtg = mtg; fp.rpg = rpg;
   for (int g = 0; g < n_groups; ++g) { fp.group_first_item[g] = sp.group_first_item[g]; fp.group_items[g] = sp.group_items[g]; }
   fp.cand_s = sp.cand_s; fp.cand_i = sp.cand_i; fp.cand_cnt = sp.cand_cnt; fp.margin = mg;
   fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E; fp.k = k;
