@@ -44,10 +44,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--targets", type=int, default=1_000_000, help="index rows PER GPU (weak scaling)")
-    ap.add_argument("--queries", type=int, default=600, help="query rows per step (sse_evaluator.py:104 batch)")
+    ap.add_argument("--targets", type=int, default=1_000_000, help="TOTAL index rows (sharded by rows over the GPUs)")
+    ap.add_argument("--queries", type=int, default=600, help="query rows per step PER GPU (sse_evaluator.py:104 batch); a step of an N-GPU job carries N x this many queries")
     ap.add_argument("--search", type=int, default=0, help="0 auto (tcgen05), 1 fp32 SIMT, 2 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="run encode and search of a step back to back on one stream "
+                    "(default: 2-stage software pipeline over steps: encoder of batch s+1 overlaps the scan of batch s)")
+    ap.add_argument("--search-ctas", type=int, default=126, help="scan grid cap when pipelining (rest of the SMs run the encoder)")
     ap.add_argument("--train-steps", type=int, default=5, help="timed train steps for the secondary train-step/s figure (0 = skip)")
     ap.add_argument("--train-rows", type=int, default=1024, help="pair rows per GPU per train step (512 pos + 512 neg, data.py:95-115 layout)")
     ap.add_argument("--cpu-sample-targets", type=int, default=1_000_000)
@@ -137,13 +140,21 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything libraries print (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    Q, k = args.queries, K_TOP
-    n_local = args.targets
+    # N-GPU job: the 1M-target index is sharded by rows (N/G per rank, resident in HBM); a step carries G x 600
+    # queries, every rank encodes all of them (200 B of tokens per query: cheaper than a collective), scans its
+    # shard for all of them, and ONE NCCL all-gather of the packed per-shard top-k is followed by the merge
+    # kernel.  Per-GPU scan work (G*Q x N/G) is constant in G -> weak scaling; value = G*Q*steps / time.
+    Q, k = args.queries * world, K_TOP
+    n_local = args.targets // world
     h = sse_ffi.Handle("dual-encoder", V, WE, E, H, H, T, predict_nbest=k, device=local, precision=sse_ffi.PRECISION_TC)
     h.set_params(init_weights())
     h.set_option("search", args.search)
@@ -169,9 +180,40 @@ def run_b200(args):
     out_i_host = torch.empty(Q, k, dtype=torch.int32).pin_memory()
     stream = torch.cuda.current_stream()
 
+    pipeline = not args.no_pipeline
+    enc2 = [enc, torch.empty_like(enc)]
+    enc_stream = torch.cuda.Stream() if pipeline else stream
+    enc_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    enc_free = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"primed": False, "n": 0}
+    if pipeline:
+        h.set_option("search_ctas", args.search_ctas)
+
+    def issue_encode(b, slot):
+        with torch.cuda.stream(enc_stream):
+            enc_stream.wait_event(enc_free[slot])          # the scan that last read this slot has finished
+            h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Q, enc2[slot], True, enc_stream)
+            enc_ready[slot].record(enc_stream)
+
     def step_device(b):
-        h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Q, enc, True, stream)
-        h.search(enc, Q, k, sc, ix, stream)
+        if pipeline:
+            # software pipeline over steps: this step's scan runs while the NEXT step's batch is encoded on the
+            # other stream (every step still encodes one batch and scans the index once for one batch)
+            n = state["n"]
+            if not state["primed"]:
+                for sl in range(2):
+                    enc_free[sl].record(stream)
+                enc_stream.wait_stream(stream)
+                issue_encode(b, n & 1)
+                state["primed"] = True
+            stream.wait_event(enc_ready[n & 1])
+            issue_encode((b + 1) % n_batches, (n + 1) & 1)
+            h.search(enc2[n & 1], Q, k, sc, ix, stream)
+            enc_free[n & 1].record(stream)
+            state["n"] = n + 1
+        else:
+            h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Q, enc, True, stream)
+            h.search(enc, Q, k, sc, ix, stream)
         if world > 1:
             packed[:, :k] = sc
             packed[:, k:] = ix.view(torch.float32)
@@ -182,7 +224,11 @@ def run_b200(args):
             h.merge_topk(cs, ci, Q, world * k, k, fs, fi, stream)
 
     def step_e2e(b):
-        tok_dev[b].copy_(tok_host[b], non_blocking=True)               # H2D of the step's inputs
+        if pipeline:
+            with torch.cuda.stream(enc_stream):                          # H2D of the NEXT step's inputs, ahead of its encode
+                tok_dev[(b + 1) % n_batches].copy_(tok_host[(b + 1) % n_batches], non_blocking=True)
+        else:
+            tok_dev[b].copy_(tok_host[b], non_blocking=True)           # H2D of the step's inputs
         step_device(b)
         src_s, src_i = (fs, fi) if world > 1 else (sc, ix)
         out_s_host.copy_(src_s, non_blocking=True)                     # D2H of the step's result
@@ -193,6 +239,8 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        state["primed"] = False
+        state["n"] = 0
 
     def timed(fn, steps, warmup):
         for w in range(warmup):
@@ -221,6 +269,8 @@ def run_b200(args):
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
 
     # dominant kernel (the index scan) timed alone, CUDA events on the launching stream, for the roofline
+    h.set_option("search_ctas", 0)
+    torch.cuda.synchronize()
     h.encode(sse_ffi.SIDE_SRC, tok_dev[0], Q, enc, True, stream)
     for _ in range(3):
         h.search(enc, Q, k, sc, ix, stream)
@@ -316,9 +366,12 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05 scan + LSTM), exact f32 re-rank of the top-k" if use_tc else "f32",
         "data": "synthetic",
         "config": {"workload": "dual LSTM encoder V=32000 We=H=E=256 T=50 (FULL-length rows), Q=%d queries/step, "
-                               "cosine top-%d over N=%d targets per GPU (%d total)" % (Q, k, n_local, n_local * world),
-                   "targets_per_gpu": n_local, "targets_total": n_local * world, "queries_per_step": Q, "k": k,
-                   "parallelism": "index-shard x%d + 1 NCCL all-gather of [Q,k]" % world if world > 1 else "single GPU",
+                               "cosine top-%d over N=%d targets (%d per GPU shard)" % (Q, k, n_local * world, n_local),
+                   "targets_per_gpu": n_local, "targets_total": n_local * world, "queries_per_step": Q,
+                   "queries_per_step_per_gpu": args.queries, "k": k,
+                   "parallelism": "index row-shard x%d, %d queries/step (600 per GPU), 1 NCCL all-gather of per-shard [Q,k]" % (world, Q) if world > 1 else "single GPU",
+                   "pipeline": ("2-stage over steps: encoder of batch s+1 (its own stream, %d SMs left free by the scan grid cap %d) overlaps the scan of batch s"
+                                % (148 - args.search_ctas, args.search_ctas)) if pipeline else "none (encode then scan on one stream)",
                    "l2": "index shard (%.0f MB) is re-streamed every step and exceeds L2 (126 MB); query batches rotate" %
                          (bytes_alg / 1e6)},
         "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * T * 4,
@@ -330,7 +383,7 @@ def run_b200(args):
     }
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_reference(args.cpu_sample_queries, args.cpu_sample_targets, runs=1)
-    print(json.dumps(out))
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

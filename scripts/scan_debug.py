@@ -9,7 +9,7 @@ h = sse_ffi.Handle("dual-encoder", 50, 8, E, 8, 8, 8, precision=sse_ffi.PRECISIO
 g = torch.Generator(device="cuda").manual_seed(7)
 idx = torch.randn(N, E, device="cuda", generator=g); idx /= idx.norm(dim=1, keepdim=True)
 h.index_set(idx, N, 0)
-for Q in (600, 128, 256):
+for Q in [int(x) for x in os.environ.get("SCAN_Q", "600,128,256").split(",")]:
     q = torch.randn(Q, E, device="cuda", generator=g); q /= q.norm(dim=1, keepdim=True)
     s = torch.empty(Q, k, device="cuda"); i = torch.empty(Q, k, device="cuda", dtype=torch.int32)
     for flags in ("0", "2"):

@@ -247,8 +247,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w3, const __grid_constan
   const uint32_t slot_bytes = (uint32_t)SKB * TILE_BYTES;
 
   const int XB = P.xbufs;
-  uint8_t* x_smem = smem;                                     // [XB buffers][KBx] tiles [128 x 64] fp16 SW128
-  uint8_t* w_smem = x_smem + (size_t)XB * KBx * TILE_BYTES;   // [NS] slots of SKB tiles
+  // x tiles hold only this CTA's RPC rows: the MMA still reads 128 rows per tile, the rows past RPC are whatever
+  // follows in shared memory (finite fp16 weight bits) and only feed accumulator lanes nobody reads.
+  const uint32_t x_tile_bytes = (uint32_t)RPC * 128;
+  uint8_t* x_smem = smem;                                     // [XB buffers][KBx] tiles [RPC x 64] fp16 SW128
+  uint8_t* w_smem = x_smem + (size_t)XB * KBx * x_tile_bytes; // [NS] slots of SKB tiles
   float* bias_s = reinterpret_cast<float*>(w_smem + (size_t)NS * slot_bytes);   // [4H] (only if P.bias_smem)
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + (P.bias_smem ? (size_t)4 * P.H * 4 : 0));
   // bars: full[NS], empty[NS], x_full[2], x_empty[2], h_full, acc_full[2], acc_empty[2]
@@ -329,7 +332,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w3, const __grid_constan
       const bool has_state = has_init || t > t0;
       // h_{t-1} lives in h buffer (t+1)&1 ; epilogue of step t writes buffer t&1
       const uint32_t h_src = tmem_base + (uint32_t)(((t + 1) & 1) * 128);
-      const uint32_t x_lo = (uint32_t)make_sw128_desc(smem_u32(x_smem + (size_t)xb * KBx * TILE_BYTES));
+      const uint32_t x_lo = (uint32_t)make_sw128_desc(smem_u32(x_smem + (size_t)xb * KBx * x_tile_bytes));
       for (int cp = 0; cp < NC; cp += 2, gchunk += 2) {
         const uint32_t use = gchunk >> 1;                 // NC is even: chunk c always uses accumulator c & 1
         // ---- x parts of chunks cp (acc 0) and cp+1 (acc 1)
@@ -346,12 +349,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w3, const __grid_constan
             if (elect_one_sync()) {
               const uint64_t b0 = make_sw128_desc(smem_u32(w_smem + (size_t)s * slot_bytes));
               const uint32_t blo = (uint32_t)b0, hi = (uint32_t)(b0 >> 32);
-              const uint32_t alo = x_lo + (uint32_t)(sl * SKB) * (TILE_BYTES >> 4);
+              const uint32_t alo = x_lo + (uint32_t)(sl * SKB) * (x_tile_bytes >> 4);
 #pragma unroll 2
               for (int kb = 0; kb < SKB; ++kb)
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
-                  tc_mma_ss2(d, alo + (uint32_t)(kb * (TILE_BYTES >> 4) + 2 * k4), blo + (uint32_t)(kb * (TILE_BYTES >> 4) + 2 * k4), hi, idesc,
+                  tc_mma_ss2(d, alo + (uint32_t)(kb * (x_tile_bytes >> 4) + 2 * k4), blo + (uint32_t)(kb * (TILE_BYTES >> 4) + 2 * k4), hi, idesc,
                              (sl | kb | k4) ? 1u : 0u);
               tc_commit(bar_empty + 8 * s);
               if (c == NC - 1 && sl == nsx - 1) tc_commit(bar_xe + 8 * xb);   // x_t fully consumed once these MMAs retire
@@ -416,13 +419,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w3, const __grid_constan
       const int xb = XB == 2 ? (step & 1) : 0;
       const uint32_t xuse = XB == 2 ? (uint32_t)(step >> 1) : (uint32_t)step;
       mbar_wait(bar_xe + 8 * xb, (xuse & 1) ^ 1, 128);
-      const uint32_t xbase = smem_u32(x_smem + (size_t)xb * KBx * TILE_BYTES);
+      const uint32_t xbase = smem_u32(x_smem + (size_t)xb * KBx * x_tile_bytes);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (q * 64 + gl >= RPC) continue;                 // rows beyond this CTA's tile: MMA rows are independent, leave them
         const __half* src = P.emb + (size_t)tok[q] * P.We;
         for (int kb = 0; kb < KBx; ++kb) {
-          const uint32_t tile = xbase + (uint32_t)kb * TILE_BYTES + row_off[q];
+          const uint32_t tile = xbase + (uint32_t)kb * x_tile_bytes + row_off[q];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t dst = tile + (uint32_t)(((j ^ sw[q]) * 16));
@@ -662,13 +665,18 @@ int lstm_forward_tc(const int32_t* tokens, int B, int T, int t_start, const __ha
   LstmTcParams p;
   p.tokens = tokens; p.emb = emb_f16; p.bias_r = tt.bias_r; p.init_h = init_h; p.init_c = init_c;
   p.c_scratch = c_scratch; p.h_out = h_out; p.B = B; p.T = T; p.t_start = t_start; p.We = We; p.H = H;
+  // small batches: 64- / 32-row tiles spread the rows over more SMs (the step latency, not the MMA rate, bounds them)
+  const int rpc_auto = (cdiv(B, 128) * 2 >= 148) ? 128 : ((cdiv(B, 64) * 2 >= 148) ? 64 : 32);
+  p.rows_per_cta = getenv("SSE_LSTM_ROWS") ? atoi(getenv("SSE_LSTM_ROWS")) : rpc_auto;
   // shared-memory plan (tunable for experiments): x buffers, weight-ring slot size, bias table placement
   auto envi = [](const char* k, int dflt) { const char* v = getenv(k); return v ? atoi(v) : dflt; };
   p.xbufs = envi("SSE_LSTM_XBUFS", 1);
   p.bias_smem = envi("SSE_LSTM_BIAS_SMEM", 1);
   p.gate_math = envi("SSE_LSTM_GATE_MATH", 0);
   const int slot_kb = tt.slot_kb;
-  const size_t fixed = 1024 + (size_t)p.xbufs * (We / KBLK) * TILE_BYTES + (p.bias_smem ? (size_t)4 * H * 4 : 0) + 512;
+  const size_t x_bytes = (size_t)p.xbufs * (We / KBLK) * p.rows_per_cta * 128;
+  // the last x tile is read 128 rows deep: keep that window inside the allocation (the ring follows it)
+  const size_t fixed = 1024 + x_bytes + (p.bias_smem ? (size_t)4 * H * 4 : 0) + 512;
   const size_t slot = (size_t)slot_kb * TILE_BYTES;
   int NS = (int)((232448 - fixed) / slot);
   if (NS > 8) NS = 8;
@@ -679,8 +687,6 @@ int lstm_forward_tc(const int32_t* tokens, int B, int T, int t_start, const __ha
   p.dbg = nullptr;
   const bool want_dbg = getenv("SSE_LSTM_DEBUG") != nullptr;
   long long* d_dbg = nullptr;
-  const int rpc = (cdiv(B, 128) * 2 >= 148) ? 128 : ((cdiv(B, 64) * 2 >= 148) ? 64 : 32);
-  p.rows_per_cta = getenv("SSE_LSTM_ROWS") ? atoi(getenv("SSE_LSTM_ROWS")) : rpc;
   const int grid = cdiv(B, p.rows_per_cta);
   if (want_dbg) { cudaMalloc(&d_dbg, (size_t)grid * 64); cudaMemset(d_dbg, 0, (size_t)grid * 64); p.dbg = d_dbg; }
   const size_t smem = fixed + (size_t)NS * slot;

@@ -36,8 +36,9 @@ namespace {
 
 constexpr int TILE_M = 128;          // query rows per m-tile
 constexpr int KBLK = 64;             // fp16 elements per 128-byte swizzle row
-constexpr int CAND_CAP = 64;         // candidates per (CTA item, row)
+constexpr int CAND_CAP = 128;        // candidates per (CTA item, row); compacted in-kernel when fewer than 32 slots remain
 constexpr int MAX_GROUPS = 32;
+constexpr int DBG_N = 12;            // debug cycle counters per work item
 constexpr int SCAN_THREADS = 384;
 constexpr int FIN_MAXC = 2048;       // candidates per row the finalize kernel can sort
 constexpr int FIN_MAXR = 256;        // candidates per row re-scored exactly
@@ -53,7 +54,7 @@ struct ScanParams {
   int tn;                          // index rows per MMA tile (64 or 128)
   int a_cols;                      // TMEM columns holding the fp16 queries: mtg * E / 2
   const __half* qb;         // [Qp, E] fp16 queries
-  long long* dbg;                  // optional [items][8] cycle counters (nullptr = off)
+  long long* dbg;                  // optional [items][DBG_N] cycle counters (nullptr = off)
   int dbg_flags;                   // timing experiments only: 1 = no TMA loads, 2 = no MMA issue
   int use3d;                       // one 3-D TMA instruction per index tile (else KB 2-D loads)
   int group_first_item[MAX_GROUPS];
@@ -65,6 +66,8 @@ struct ScanParams {
   int Qp;                          // padded query rows
   int64_t global_offset;
   const float* tau;                // [Qp]        (FILTER)
+  const float* margin;             // [Qp]        (FILTER) 2*eps per row, for the in-kernel threshold tightening
+  int k;
   float* tilemax;                  // [n_j][Qp]   (TILEMAX)
   float* cand_s;                   // [items][mtg*128][CAND_CAP]
   int32_t* cand_i;
@@ -226,6 +229,86 @@ __device__ __forceinline__ void tc_mma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem,
 }
 
 // KBT / TNT: compile-time E/64 and tile width (0 = take them from the params at run time)
+// A row's candidate list is about to run out of slots (rare: the sampled threshold was loose for this row).
+// Move its k best to the front, tighten the row's threshold to (k-th best approximate score - 2 eps) -- still a
+// lower bound of what any true top-k member scores in fp16 -- and drop everything below.  cnt = CAND_CAP + 1 is
+// the overflow sentinel (-> exact fallback) when that frees no room (mass ties).
+struct Compacted { int cnt; float thr; };
+__device__ __noinline__ Compacted compact_candidates(float* s, int32_t* id, int cnt, int k, float mg, float thr) {
+  Compacted out;
+  out.thr = thr;
+  out.cnt = CAND_CAP + 1;
+  if (k > CAND_CAP / 4) return out;
+  for (int r = 0; r < k; ++r) {
+    int best = r;
+    float bs = s[r];
+    for (int x = r + 1; x < cnt; ++x) { float v = s[x]; if (v > bs) { bs = v; best = x; } }
+    if (best != r) { float t = s[r]; s[r] = bs; s[best] = t; int32_t ti = id[r]; id[r] = id[best]; id[best] = ti; }
+  }
+  const float nt = s[k - 1] - mg;
+  if (nt > thr) thr = nt;
+  int w = k;
+  for (int x = k; x < cnt; ++x) {
+    float v = s[x];
+    if (v > thr) { s[w] = v; id[w] = id[x]; ++w; }
+  }
+  out.thr = thr;
+  if (w <= CAND_CAP - 64) out.cnt = w;
+  return out;
+}
+
+// max of 32 fp32 accumulator values held as raw bits
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
+  float m[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+    m[o] = fmaxf(fmaxf(__uint_as_float(v[o * 4 + 0]), __uint_as_float(v[o * 4 + 1])),
+                 fmaxf(__uint_as_float(v[o * 4 + 2]), __uint_as_float(v[o * 4 + 3])));
+  return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+}
+
+// predicated (branch-free) append of one value: no divergence stack traffic inside the candidate path
+__device__ __forceinline__ int append_if(float s, float thr, float* cs, int32_t* ci, int cnt, int32_t id) {
+  uint32_t took;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.gt.f32 p, %1, %2;\n"
+      "@p st.global.f32 [%3], %1;\n"
+      "@p st.global.s32 [%4], %5;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(took)
+      : "f"(s), "f"(thr), "l"(cs + cnt), "l"(ci + cnt), "r"(id)
+      : "memory");
+  return cnt + (int)took;
+}
+
+// append every value of the 32-wide chunk that beats thr to the row's candidate list; one 8-wide octet at a time,
+// only the octets whose maximum beats thr (thread == query row, so lanes diverge only at octet granularity)
+__device__ __forceinline__ int chunk_filter(const uint32_t (&v)[32], float thr, float* cs, int32_t* ci, int cnt, int32_t id0) {
+  float mq[4];
+#pragma unroll
+  for (int qd = 0; qd < 4; ++qd) {
+    float a = fmaxf(__uint_as_float(v[qd * 8 + 0]), __uint_as_float(v[qd * 8 + 1]));
+    float b = fmaxf(__uint_as_float(v[qd * 8 + 2]), __uint_as_float(v[qd * 8 + 3]));
+    float c = fmaxf(__uint_as_float(v[qd * 8 + 4]), __uint_as_float(v[qd * 8 + 5]));
+    float d = fmaxf(__uint_as_float(v[qd * 8 + 6]), __uint_as_float(v[qd * 8 + 7]));
+    mq[qd] = fmaxf(fmaxf(a, b), fmaxf(c, d));
+  }
+  const float m = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
+  if (m > thr) {
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+      if (mq[qd] > thr) {
+#pragma unroll
+        for (int i = qd * 8; i < qd * 8 + 8; ++i) cnt = append_if(__uint_as_float(v[i]), thr, cs, ci, cnt, id0 + i);
+      }
+    }
+  }
+  return cnt;
+}
+
 template <int MODE, int KBT, int TNT>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant__ ScanParams P) {
@@ -299,7 +382,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         }
         __syncwarp();
       }
-      if (P.dbg && lane == 0) { P.dbg[item * 8 + 0] = w_empty; P.dbg[item * 8 + 1] = clock64() - t_begin; }
+      if (P.dbg && lane == 0) { P.dbg[item * DBG_N + 0] = w_empty; P.dbg[item * DBG_N + 1] = clock64() - t_begin; }
     }
   } else if (warp == 8) {
     // ===== MMA issuer (one thread): all MMAs of a tile back to back, ONE tcgen05.commit per tile =====
@@ -347,7 +430,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         }
         __syncwarp();
       }
-      if (P.dbg && lane == 0) { P.dbg[item * 8 + 2] = w_full; P.dbg[item * 8 + 3] = w_acce; P.dbg[item * 8 + 4] = clock64() - t_begin; P.dbg[item * 8 + 5] = w_a; }
+      if (P.dbg && lane == 0) { P.dbg[item * DBG_N + 2] = w_full; P.dbg[item * DBG_N + 3] = w_acce; P.dbg[item * DBG_N + 4] = clock64() - t_begin; P.dbg[item * DBG_N + 5] = w_a; }
     }
   } else if (warp < 8) {
     // ===== epilogue: thread == query row =====
@@ -386,7 +469,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         my_i = P.cand_i + base;
       }
       const int n_chunks = TN / 32;
-      long long w_accf = 0, t_begin = clock64();
+      long long w_accf = 0, w_ld = 0, w_cmp = 0, t_begin = clock64();
       for (int j = j0; j < j1; ++j) {
         const int jj = j - j0;
         const int buf = jj & 1;
@@ -400,42 +483,50 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         if (e == 0 && lane == 0) mbar_arrive(bar_empty + 8 * ((uint32_t)jj % NG));
         const uint32_t taddr = lane_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
         float tmax = -CUDART_INF_F;
+        // 64 accumulator columns per round: both TMEM loads in flight together; after the last round's data has
+        // landed in registers the accumulator buffer goes straight back to the MMA warp, and the compares run
+        // from registers while the next-but-one tile's MMAs already overwrite it.
 #pragma unroll 1
-        for (int ch = 0; ch < n_chunks; ++ch) {
-          uint32_t v[32];
-          TMEM_LD_32(taddr + ch * 32, v);
+        for (int ch = 0; ch < n_chunks; ch += 2) {
+          uint32_t va[32], vb[32];
+          long long t_c0 = 0;
+          if (P.dbg) t_c0 = clock64();
+          TMEM_LD_32(taddr + ch * 32, va);
+          TMEM_LD_32(taddr + ch * 32 + 32, vb);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ch + 2 >= n_chunks) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+          }
+          if (P.dbg) { long long t = clock64(); w_ld += t - t_c0; t_c0 = t; }
+          const int64_t cbase = col0 + ch * 32;
           if (ragged) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + ch * 32 + i >= P.N) v[i] = 0xff800000u;   // -inf
-          }
-          float m = __uint_as_float(v[0]);
-#pragma unroll
-          for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-          if (MODE == MODE_TILEMAX) {
-            tmax = fmaxf(tmax, m);
-          } else if (m > thr) {
-#pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float s = __uint_as_float(v[i]);
-              if (s > thr) {
-                if (cnt < CAND_CAP) {
-                  my_s[cnt] = s;
-                  my_i[cnt] = (int32_t)(P.global_offset + col0 + ch * 32 + i);
-                }
-                ++cnt;
-              }
+              if (cbase + i >= P.N) va[i] = 0xff800000u;   // -inf
+              if (cbase + 32 + i >= P.N) vb[i] = 0xff800000u;
             }
           }
+          if (MODE == MODE_TILEMAX) {
+            tmax = fmaxf(tmax, fmaxf(chunk_max(va), chunk_max(vb)));
+          } else {
+            const int32_t id0 = (int32_t)(P.global_offset + cbase);
+            cnt = chunk_filter(va, thr, my_s, my_i, cnt, id0);
+            cnt = chunk_filter(vb, thr, my_s, my_i, cnt, id0 + 32);
+            // keep >= 64 free slots for the next round
+            if (cnt > CAND_CAP - 64) {
+              Compacted cc = compact_candidates(my_s, my_i, cnt, P.k, P.margin[grow], thr);
+              cnt = cc.cnt;
+              thr = cc.cnt > CAND_CAP ? CUDART_INF_F : cc.thr;   // overflow sentinel: stop collecting, finalize flags the row
+            }
+          }
+          if (P.dbg) w_cmp += clock64() - t_c0;
         }
         if (MODE == MODE_TILEMAX) P.tilemax[(size_t)j * P.Qp + grow] = tmax;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
       }
       if (MODE == MODE_FILTER) P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + lrow] = cnt;
-      if (P.dbg && e == 0 && lane == 0) { P.dbg[item * 8 + 6] = w_accf; P.dbg[item * 8 + 7] = clock64() - t_begin; }
+      if (P.dbg && e == 0 && lane == 0) { P.dbg[item * DBG_N + 6] = w_accf; P.dbg[item * DBG_N + 7] = clock64() - t_begin; P.dbg[item * DBG_N + 8] = w_ld; P.dbg[item * DBG_N + 9] = w_cmp; P.dbg[item * DBG_N + 10] = cnt; }
     } else if (mt < mt_count && MODE == MODE_FILTER) {
       P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + mt * TILE_M + quarter * 32 + lane] = 0;
     }
@@ -846,7 +937,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   size_t o_cc = carve((size_t)items * mtg * TILE_M * 4);
   size_t o_ov = carve((size_t)Qp * 4);
   const bool want_dbg = getenv("SSE_SCAN_DEBUG") != nullptr;
-  size_t o_dbg = carve(want_dbg ? (size_t)items * 8 * 8 : 8);
+  size_t o_dbg = carve(want_dbg ? (size_t)items * DBG_N * 8 : 8);
   SSE_TRY(ws.ensure(off));
   uint8_t* w = ws.as<uint8_t>();
   __half* qb = reinterpret_cast<__half*>(w + o_qb);
@@ -881,7 +972,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   if (launches) ++*launches;
 
   // pass B: filter over all tiles
-  sp.n_j = n_tiles; sp.tile_step = 1; sp.tilemax = nullptr; sp.tau = tau;
+  sp.n_j = n_tiles; sp.tile_step = 1; sp.tilemax = nullptr; sp.tau = tau; sp.margin = mg; sp.k = k;
   sp.dbg = want_dbg ? reinterpret_cast<long long*>(w + o_dbg) : nullptr;
   sp.dbg_flags = (want_dbg && getenv("SSE_SCAN_FLAGS")) ? atoi(getenv("SSE_SCAN_FLAGS")) : 0;
   sp.cand_s = reinterpret_cast<float*>(w + o_cs);
@@ -898,13 +989,14 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E; fp.k = k;
   fp.out_s = out_scores; fp.out_i = out_idx; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov);
   if (want_dbg) {
-    std::vector<long long> hd((size_t)items * 8);
+    std::vector<long long> hd((size_t)items * DBG_N);
     cudaStreamSynchronize(st);
     cudaMemcpy(hd.data(), w + o_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
-    const char* nm[8] = {"prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_acce", "mma_total", "mma_wait_a", "epi_wait_accf", "epi_total"};
-    for (int c = 0; c < 8; ++c) {
+    const char* nm[DBG_N] = {"prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_acce", "mma_total", "mma_wait_a", "epi_wait_accf", "epi_total",
+                             "epi_tmem_ld", "epi_compare", "epi_cand_lane0", "-"};
+    for (int c = 0; c < 11; ++c) {
       long long mn = 1LL << 62, mx = 0, sm = 0;
-      for (int i = 0; i < items; ++i) { long long v = hd[(size_t)i * 8 + c]; mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
+      for (int i = 0; i < items; ++i) { long long v = hd[(size_t)i * DBG_N + c]; mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
       fprintf(stderr, "[scan dbg] %-16s min %10lld avg %10lld max %10lld  (items %d, tiles/item ~%d, tn %d, NS %d)\n", nm[c], mn, sm / items, mx, items, n_tiles / items * n_groups, tn, NS);
     }
   }

@@ -204,7 +204,8 @@ int search_device(sse_handle* h, const float* q, int Q, int k, float* scores, in
     for (int q0 = 0; q0 < Q; q0 += maxq) {
       int nq = std::min(maxq, Q - q0);
       SSE_TRY(search_tc(q + (size_t)q0 * E, nq, E, h->index_f32, h->tc, h->index_off, k, scores + (size_t)q0 * k,
-                        idx + (size_t)q0 * k, h->search_ws, h->num_sms, st, &h->launches));
+                        idx + (size_t)q0 * k, h->search_ws,
+                        h->opt_search_ctas > 0 ? std::min(h->opt_search_ctas, h->num_sms) : h->num_sms, st, &h->launches));
     }
     return SSE_OK;
   }
@@ -508,6 +509,7 @@ int sse_set_option(sse_handle* h, const char* key, int value) {
   if (!strcmp(key, "search")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_search = value; return SSE_OK; }
   if (!strcmp(key, "encoder")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_encoder = value; return SSE_OK; }
   if (!strcmp(key, "pad_skip")) { h->opt_pad_skip = value != 0; return SSE_OK; }
+  if (!strcmp(key, "search_ctas")) { if (value < 0) return SSE_EINVAL; h->opt_search_ctas = value; return SSE_OK; }
   set_error("sse_set_option: unknown key '%s'", key);
   return SSE_EINVAL;
 }

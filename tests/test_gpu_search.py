@@ -123,6 +123,35 @@ def test_tc_search_duplicate_targets_tie_rule_and_overflow_fallback():
     h.close()
 
 
+def test_tc_search_clustered_block_forces_in_kernel_compaction():
+    """A contiguous run of 3000 targets all close to the queries (distinct scores) is mostly invisible to the
+    strided threshold sample, so thousands of rows pass the sampled threshold: the scan must tighten each row's
+    threshold in place (candidate compaction) and still return the exact top-k, without the brute-force fallback
+    dominating.  Also covers many m-groups (Q = 2500 -> 10 groups)."""
+    rng = np.random.default_rng(11)
+    E, N, Q, k = 256, 60000, 2500, 10
+    tgt, q = unit_rows(rng, N, E), unit_rows(rng, Q, E)
+    centre = unit_rows(rng, 1, E)[0]
+    lo = 20000 + 64 * 3
+    blk = centre[None, :] + 0.6 * rng.standard_normal((3000, E)).astype(np.float32) / np.sqrt(E)
+    tgt[lo:lo + 3000] = blk / np.linalg.norm(blk, axis=1, keepdims=True)
+    q[:1200] = centre[None, :] + 0.5 * rng.standard_normal((1200, E)).astype(np.float32) / np.sqrt(E)
+    h = handle(E)
+    h.index_set(tgt)
+    h.set_option("search", 2)
+    s, i = run_search(h, q, k)
+    d = q.astype(np.float64) @ tgt.astype(np.float64).T
+    want_i = np.argsort(-d, axis=1, kind="stable")[:, :k]
+    want_s = np.take_along_axis(d, want_i, 1)
+    assert np.abs(s - want_s).max() < 1e-5
+    srt = -np.sort(-d, axis=1)[:, : k + 1]
+    wide = np.min(np.abs(np.diff(srt, axis=1)), axis=1) > 2e-6       # rows whose top-(k+1) has no fp32-level near-ties
+    assert wide.mean() > 0.9
+    assert np.array_equal(i[wide], want_i[wide])
+    assert np.all((i[:1200] >= lo) & (i[:1200] < lo + 3000))
+    h.close()
+
+
 def test_merge_topk_fake_shards_equals_single():
     import torch
     rng = np.random.default_rng(9)
