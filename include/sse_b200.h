@@ -179,8 +179,11 @@ int sse_set_scalars(sse_handle* h, float learning_rate, int64_t global_step);
 /* ---- introspection for benchmarks / tests -------------------------------- */
 /* number of kernels this library launched on the handle since creation */
 int64_t sse_launch_count(sse_handle* h);
-/* select kernel variants at run time: key in {"search", "encoder", "pad_skip", "search_ctas"};
- * search: 0 auto, 1 simt-fp32, 2 tcgen05-bf16;  encoder: 0 auto, 1 simt-fp32, 2 tcgen05;
+/* select kernel variants at run time: key in {"search", "encoder", "lstm_kernel", "pad_skip", "search_ctas"};
+ * search: 0 auto, 1 simt-fp32, 2 tcgen05-fp16;  encoder: 0 auto, 1 simt-fp32, 2 tcgen05;
+ * lstm_kernel (tcgen05 encoder only): 0 auto, 1 weight-streaming kernel, 2 cluster kernel (weights resident in
+ * the shared memory of a thread-block cluster), 3 cluster kernel with the input projection tabulated per
+ * vocabulary entry (V x 4H fp32 table, rebuilt when parameters change; the default when it fits in 2 GiB);
  * pad_skip: 0 off, 1 on (host-token entry points only);  search_ctas: cap on the scan grid (0 = all SMs),
  * so that an encoder launched on another stream can run concurrently on the remaining SMs. */
 int sse_set_option(sse_handle* h, const char* key, int value);

@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libsse_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default --expt-relaxed-constexpr -Xptxas -v"
-SRCS="sse_api.cu lstm_simt.cu lstm_tc.cu search_simt.cu search_tc.cu cnn.cu util.cu train.cu"
+SRCS="sse_api.cu lstm_simt.cu lstm_tc.cu lstm_cluster.cu search_simt.cu search_tc.cu cnn.cu util.cu train.cu"
 mkdir -p build
 pids=()
 for s in $SRCS; do

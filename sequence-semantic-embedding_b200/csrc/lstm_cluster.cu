@@ -1,0 +1,870 @@
+// LSTM tower for small / medium batches (query encoding): a thread-block CLUSTER of H/32 CTAs owns 64 batch
+// rows for all T steps, and the fp16 weights never move after the first microsecond.
+// Restates BasicLSTMCell(forget_bias=1)+static_rnn (reference sse_model.py:222-224,240-242,248-250,262-264,
+// 273-274), same numerics as lstm_tc.cu (fp16 operands, fp32 accumulate, fp32 cell state and gate math).
+//
+// Why a second kernel: lstm_tc.cu streams the whole [4H, We+H] weight matrix (1 MB at We=H=256) through every
+// CTA on every step.  That is the right trade when all 148 SMs hold full 128-row tiles (index build), but a
+// 600-row query batch then runs at the per-SM L2->smem rate: ~16 us per step, 0.8 ms per batch.  Here
+//   * CTA `rank` of the cluster keeps the weight slice of hidden units [32 rank, 32 rank + 32) -- 128 gate
+//     columns (i|j|f|o x 32), [128 x (We+H)] fp16 = 128 KB -- RESIDENT in shared memory (one TMA load),
+//   * per step it issues 4 (We/64 + H/64) tcgen05.mma (M=128 with 64 live rows, N=128, A and B from smem),
+//   * its four epilogue warps (thread == batch row x 16 units, c in registers) apply the gate math and store the new
+//     h slice (fp16) straight into the h_t operand tile of EVERY CTA of the cluster through distributed shared
+//     memory, already in the 128B-swizzled K-major layout the next step's MMA reads,
+//   * one remote mbarrier arrival per (warp, destination) publishes it; h tiles ping-pong so there is exactly
+//     one cluster-wide dependency per step and no cluster barrier.
+// The x_{t+1} part of the next step is issued before h_t is complete (it does not depend on the recurrence),
+// so the tensor pipe works through the exchange latency.
+//
+// shared memory (We=H=256): x tile 32 KB | h ping 32 KB | h pong 32 KB | Wx slice 64 KB | Wh slice 64 KB | bias
+// TMEM: two [128 lanes x 128 col] fp32 accumulators.
+// warps: 0,1,4,5 epilogue (TMEM lanes 0-63, 16 units per thread) | 2 MMA issuer + TMEM alloc + weight load |
+//        3,7 embedding gather | 6 idle (so that gather / MMA / epilogue warps sit on different SM sub-partitions).
+#include "sse_common.cuh"
+#include <algorithm>
+#include <cuda.h>
+#include <math_constants.h>
+#include <stdlib.h>
+#include <vector>
+
+namespace sse {
+
+namespace {
+
+constexpr int KBLK = 64;
+constexpr int W_TILE_BYTES = 128 * KBLK * 2;   // [128 gate cols x 64 k] fp16, SW128
+constexpr int CL_ROWS = 64;                    // batch rows per cluster
+constexpr int A_TILE_BYTES = CL_ROWS * 128;    // [64 rows x 64 k] fp16, SW128
+constexpr int CL_THREADS = 256;
+constexpr int SLICE_BYTES = CL_ROWS * 64;       // one CTA's h slice: [64 rows x 32 units] fp16, 64B-swizzled K-major atom
+
+struct LstmClParams {
+  const int32_t* tokens;      // [B, T]
+  const __half* emb;          // [V, We] fp16
+  const float* bias_r;        // [4H] chunk-major, pre-scaled for the ex2 gate math (lstm_tc.cu prep_weights_kernel)
+  const float* init_h;        // optional [H] broadcast initial state (pad-prefix table row)
+  const float* init_c;
+  float* h_out;               // [B, H] fp32 (last step)
+  int B, T, t_start, We, H;
+  long long* dbg;             // optional [grid][8] cycle counters
+  int dbg_flags;              // timing experiments only: 1 = store h to the own CTA only, 2 = skip the MUFU gate math
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+// arrival on a barrier that lives in ANOTHER CTA of the cluster; releases this thread's (and, after a
+// __syncwarp, its warp's) distributed-shared-memory stores at cluster scope
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// CLUSTER = true: acquire at cluster scope (the barrier is completed by remote arrivals that publish DSMEM stores)
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 32) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    if (CLUSTER)
+      asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    else
+      asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (backoff_ns) __nanosleep(backoff_ns);
+    if ((spins & 0xfff) == 0xfff) {          // watchdog: a protocol bug becomes a trap, not a hung GPU
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, long long& acc, uint32_t backoff_ns = 32) {
+  long long t = clock64();
+  mbar_wait<CLUSTER>(bar, parity, backoff_ns);
+  acc += clock64() - t;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %1;\n@%%px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major tile whose rows are 64 bytes (32 fp16): SWIZZLE_64B atoms, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// shared memory of this CTA -> shared memory of a peer CTA through the bulk-copy engine; completes (bytes) on the
+// PEER's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t peer_dst, uint32_t local_src, uint32_t bytes, uint32_t peer_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(peer_dst), "r"(local_src),
+               "r"(bytes), "r"(peer_bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D=f32, A=B=f16
+}
+// descriptor given as (lo, hi) words: only the low word (address field) varies per MMA
+// A and B descriptors with different high words (different swizzle modes)
+__device__ __forceinline__ void tc_mma_ss3(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %6, 0;\nmov.b64 ad, {%1, %2};\nmov.b64 bd, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n}\n" ::"r"(d),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss2(uint32_t d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 ad, {%1, %3};\nmov.b64 bd, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, p;\n}\n" ::"r"(d),
+      "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void lds_v4(uint32_t addr, float* v) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
+#define TMEM_LD_8(taddr, v)                                                                                         \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                             \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])      \
+               : "r"(taddr))
+
+// ------------------------------------------------------------------ the kernel
+// grid = n_clusters * CL CTAs, cluster = CL = H / 32 CTAs.  Cluster q owns batch rows [64 q, 64 q + 64).
+__global__ void __launch_bounds__(CL_THREADS, 1)
+lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_constant__ LstmClParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KBx = P.We / KBLK, KBh = P.H / KBLK;
+  const int CL = P.H / 32;
+  const uint32_t rank = cluster_ctarank();
+  const int row0 = (blockIdx.x / CL) * CL_ROWS;
+  const int t0 = P.t_start;
+  const int nsteps = P.T - t0;
+  const bool has_init = P.init_h != nullptr;
+
+  // The A tiles hold 64 rows; every MMA still reads 128 rows per k-block, i.e. 8 KB past the tile: those bytes are
+  // the next tile / the weight slices (finite fp16 bit patterns) and only feed accumulator lanes 64..127 nobody reads.
+  uint8_t* x_smem = smem;                                          // [KBx] tiles [64 x 64] fp16 SW128
+  uint8_t* h_smem = x_smem + (size_t)KBx * A_TILE_BYTES;           // [2 tiles][CL slices] of [64 rows x 32 k] fp16 SW64 (slice q = CTA q's units)
+  uint8_t* wx_smem = h_smem + (size_t)2 * CL * SLICE_BYTES;        // [KBx] tiles [128 x 64]
+  uint8_t* wh_smem = wx_smem + (size_t)KBx * W_TILE_BYTES;         // [KBh] tiles
+  float* bias_s = reinterpret_cast<float*>(wh_smem + (size_t)KBh * W_TILE_BYTES);   // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 128);
+  const uint32_t bar_wf = smem_u32(bars + 0);
+  const uint32_t bar_xf = smem_u32(bars + 1);
+  const uint32_t bar_xe = smem_u32(bars + 2);
+  const uint32_t bar_accf = smem_u32(bars + 3);    // [2]
+  const uint32_t bar_acce = smem_u32(bars + 5);    // [2]
+  const uint32_t bar_hr = smem_u32(bars + 7);      // [2] h tile complete: own slice in place + expect_tx of the CL-1 peer slices
+  const uint32_t bar_sl = smem_u32(bars + 9);      // [2] own slice written by the 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  if (threadIdx.x < 128) bias_s[threadIdx.x] = P.bias_r[rank * 128 + threadIdx.x];
+  if (threadIdx.x == 0) {
+    mbar_init(bar_wf, 1);
+    mbar_init(bar_xf, 64);
+    mbar_init(bar_xe, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accf + 8 * b, 1);
+      mbar_init(bar_acce + 8 * b, 4);
+      mbar_init(bar_hr + 8 * b, 2);
+      mbar_init(bar_sl + 8 * b, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();                    // every CTA's barriers exist before anyone stores / arrives remotely
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 2) {
+    // ===== weight slice load (once) + MMA issuer: warp converged, one elected lane issues =====
+    if (elect_one_sync()) {
+      mbar_expect_tx(bar_wf, (uint32_t)(KBx + KBh) * W_TILE_BYTES);
+      for (int kb = 0; kb < KBx; ++kb) tma_load_2d(smem_u32(wx_smem + (size_t)kb * W_TILE_BYTES), &tmap_w2d, bar_wf, kb * KBLK, (int)rank * 128);
+      for (int kb = 0; kb < KBh; ++kb) tma_load_2d(smem_u32(wh_smem + (size_t)kb * W_TILE_BYTES), &tmap_w2d, bar_wf, (KBx + kb) * KBLK, (int)rank * 128);
+    }
+    __syncwarp();
+    const uint32_t idesc = make_idesc_f16(128, 128);
+    const uint64_t xd = make_sw128_desc(smem_u32(x_smem)), wxd = make_sw128_desc(smem_u32(wx_smem)), whd = make_sw128_desc(smem_u32(wh_smem));
+    const uint32_t hi = (uint32_t)(xd >> 32);
+    const uint32_t x_lo = (uint32_t)xd, wx_lo = (uint32_t)wxd, wh_lo = (uint32_t)whd;
+    const uint64_t hd = make_sw64_desc(smem_u32(h_smem));
+    const uint32_t h_lo0 = (uint32_t)hd, h_hi = (uint32_t)(hd >> 32);
+    long long w_hr = 0, w_xf = 0, w_acce = 0, w_ih = 0, w_ix = 0, t_begin = clock64();
+    mbar_wait<false>(bar_wf, 0);
+
+    // x part of step s (local index) into accumulator s & 1
+    auto issue_x = [&](int s) {
+      const int buf = s & 1;
+      if (s >= 2) { mbar_wait_timed<false>(bar_acce + 8 * buf, (uint32_t)(((s >> 1) - 1) & 1), w_acce); }
+      mbar_wait_timed<false>(bar_xf, (uint32_t)(s & 1), w_xf);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t d = tmem_base + (uint32_t)(buf * 128);
+        for (int kb = 0; kb < KBx; ++kb)
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            tc_mma_ss2(d, x_lo + (uint32_t)(kb * (A_TILE_BYTES >> 4) + 2 * k4), wx_lo + (uint32_t)(kb * (W_TILE_BYTES >> 4) + 2 * k4), hi, idesc,
+                       (kb | k4) ? 1u : 0u);
+        tc_commit(bar_xe);                                         // x tile consumed once these retire
+        if (s == 0 && !has_init) tc_commit(bar_accf + 8 * buf);    // no recurrent part at the very first step
+      }
+      __syncwarp();
+    };
+
+    issue_x(0);
+    for (int s = 0; s < nsteps; ++s) {
+      const int buf = s & 1;
+      if (s > 0 || has_init) {
+        // h_{s-1} was written into tile (s-1)&1 (the initial state counts as step -1 -> tile 1)
+        const int hb = (s - 1) & 1;
+        const uint32_t n = s == 0 ? 0u : (uint32_t)(((s - 1) >> 1) + ((hb == 1 && has_init) ? 1 : 0));
+        // this phase of h_ready needs: the own slice (copy-issuer warp's arrival) + the CL-1 peer slices (bytes)
+        if (elect_one_sync()) {
+          if (s == 0) mbar_arrive(bar_hr + 8 * hb);                       // initial state: filled locally, no copies
+          else mbar_expect_tx(bar_hr + 8 * hb, (uint32_t)(CL - 1) * SLICE_BYTES);
+        }
+        __syncwarp();
+        mbar_wait_timed<false>(bar_hr + 8 * hb, n & 1, w_hr);
+        long long ti0 = clock64();
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t d = tmem_base + (uint32_t)(buf * 128);
+          const uint32_t h_lo = h_lo0 + (uint32_t)(hb * CL * (SLICE_BYTES >> 4));
+          // k-step m covers hidden units [16 m, 16 m + 16): A = slice m/2 (SW64 rows, half m%2), B = k-block m/4 (SW128 rows, quarter m%4)
+          for (int m = 0; m < 2 * CL; ++m)
+            tc_mma_ss3(d, h_lo + (uint32_t)((m >> 1) * (SLICE_BYTES >> 4) + 2 * (m & 1)), h_hi,
+                       wh_lo + (uint32_t)((m >> 2) * (W_TILE_BYTES >> 4) + 2 * (m & 3)), hi, idesc, 1u);
+          tc_commit(bar_accf + 8 * buf);
+        }
+        __syncwarp();
+        w_ih += clock64() - ti0;
+      }
+      if (s + 1 < nsteps) { long long tx0 = clock64(); issue_x(s + 1); w_ix += clock64() - tx0; }
+    }
+    if (P.dbg && lane == 0) {
+      long long* o = P.dbg + blockIdx.x * 16;
+      o[0] = w_hr; o[1] = w_xf; o[2] = w_acce; o[3] = clock64() - t_begin; o[10] = w_ih; o[11] = w_ix;
+    }
+  } else if (warp == 3 || warp == 7) {
+    // ===== embedding gather (1 row per lane): cp.async 16 B chunks into the 128B-swizzled x tile =====
+    const int r = (warp == 7 ? 32 : 0) + lane;
+    const int grow = min(row0 + r, P.B - 1);
+    const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    const uint32_t sw = (uint32_t)(r & 7);
+    const uint32_t xbase = smem_u32(x_smem) + row_off;
+    int tok = __ldg(P.tokens + (size_t)grow * P.T + t0);
+    for (int s = 0; s < nsteps; ++s) {
+      if (s > 0) mbar_wait<false>(bar_xe, (uint32_t)((s - 1) & 1), 64);
+      const __half* src = P.emb + (size_t)tok * P.We;
+      for (int kb = 0; kb < KBx; ++kb) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = xbase + (uint32_t)kb * A_TILE_BYTES + (((uint32_t)j ^ sw) * 16);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + kb * KBLK + j * 8) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (s + 1 < nsteps) tok = __ldg(P.tokens + (size_t)grow * P.T + t0 + s + 1);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_xf);
+    }
+  } else if (warp == 6) {
+    // ===== slice exchange: once the four epilogue warps have written this CTA's h_s slice into the local tile,
+    //       push it to the same place in every peer with the bulk-copy engine (completes on the peer's h_ready)
+    uint32_t peer_h = map_to_cta(smem_u32(h_smem), (uint32_t)(lane < CL ? lane : 0));
+    uint32_t peer_bar = map_to_cta(bar_hr, (uint32_t)(lane < CL ? lane : 0));
+    if (has_init) {
+      mbar_wait<false>(bar_sl + 8, 0);
+      if (lane == 0) mbar_arrive(bar_hr + 8);
+    }
+    for (int s = 0; s + 1 < nsteps; ++s) {
+      const int tb = s & 1;
+      const uint32_t n = (uint32_t)((s >> 1) + ((tb == 1 && has_init) ? 1 : 0));
+      mbar_wait<false>(bar_sl + 8 * tb, n & 1);
+      const uint32_t off = (uint32_t)(tb * CL * SLICE_BYTES) + rank * SLICE_BYTES;
+      if (lane < CL && lane != (int)rank) bulk_copy_to_peer(peer_h + off, smem_u32(h_smem) + off, SLICE_BYTES, peer_bar + 8 * tb);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hr + 8 * tb);
+    }
+  } else if ((warp & 3) < 2) {
+    // ===== epilogue: warps 0,1,4,5; thread == (batch row, 16 of this CTA's 32 hidden units), c in registers.
+    //       Two warps per SM sub-partition hide each other's MUFU / TMEM latencies.
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const int grow = row0 + r;
+    const bool valid = grow < P.B;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    const uint32_t sw = (uint32_t)(r & 7);
+    const int ub = half * 16;                      // first of this thread's units within the CTA slice
+    float c[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) c[u] = has_init ? __ldg(P.init_c + rank * 32 + ub + u) : 0.f;
+    // row r of a slice: 64 bytes at r*64, 16-byte chunk c stored at c ^ ((r >> 1) & 3)  (SWIZZLE_64B)
+    const uint32_t row_off64 = (uint32_t)(r * 64);
+    const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
+    if (has_init) {
+      // the broadcast initial state is the same for every row: each CTA fills its own tile 1 (= "step -1"), all slices
+      const uint32_t t1 = smem_u32(h_smem) + (uint32_t)(CL * SLICE_BYTES) + row_off64;
+      for (int q = half; q < CL; q += 2)
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(P.init_h + q * 32 + j * 8 + 2 * e), __ldg(P.init_h + q * 32 + j * 8 + 2 * e + 1));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t1 + (uint32_t)q * SLICE_BYTES + (((uint32_t)j ^ sw64) * 16)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sl + 8);       // completion 0 of slice_ready[1] == "initial state staged"
+    }
+    // this thread's 16 units inside the CTA's own slice: 16-byte chunks half*2 + p
+    const uint32_t own_slice = smem_u32(h_smem) + rank * SLICE_BYTES + row_off64;
+    const uint32_t bias_a = smem_u32(bias_s) + (uint32_t)(ub * 4);
+    constexpr float NL2E = -1.4426950408889634f;
+    long long w_accf = 0, w_ld = 0, w_math = 0, w_st = 0, w_pub = 0, tq = 0, t_begin = clock64();
+    const bool dbgt = P.dbg != nullptr;
+    for (int s = 0; s < nsteps; ++s) {
+      const int buf = s & 1;
+      const bool last = s == nsteps - 1;
+      mbar_wait_timed<false>(bar_accf + 8 * buf, (uint32_t)((s >> 1) & 1), w_accf);
+      tc_fence_after();
+      const uint32_t acc = lane_base + (uint32_t)(buf * 128 + ub);
+      const uint32_t tile_own = own_slice + (uint32_t)(buf * CL * SLICE_BYTES);        // h_s goes to tile s & 1
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        uint32_t vi[8], vj[8], vf[8], vo[8];
+        if (dbgt) tq = clock64();
+        TMEM_LD_8(acc + p * 8, vi);
+        TMEM_LD_8(acc + 32 + p * 8, vj);
+        TMEM_LD_8(acc + 64 + p * 8, vf);
+        TMEM_LD_8(acc + 96 + p * 8, vo);
+        // this pass's 32 bias values (warp-uniform addresses: broadcast reads)
+        float bi[8], bj[8], bf[8], bo[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          lds_v4(bias_a + (uint32_t)((p * 8 + q * 4) * 4), bi + q * 4);
+          lds_v4(bias_a + (uint32_t)((32 + p * 8 + q * 4) * 4), bj + q * 4);
+          lds_v4(bias_a + (uint32_t)((64 + p * 8 + q * 4) * 4), bf + q * 4);
+          lds_v4(bias_a + (uint32_t)((96 + p * 8 + q * 4) * 4), bo + q * 4);
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (p == 1) {                       // the accumulator sits in registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+        }
+        if (dbgt) { long long t = clock64(); w_ld += t - tq; tq = t; }
+        // gate math, 8 MUFU per (row, unit) -- see lstm_tc.cu: sig(i) tanh(j) = (1-Ej)/((1+Ei)(1+Ej)) etc.,
+        // the bias table is pre-scaled by -log2 e (-2 log2 e for j, forget bias folded in)
+        float hv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int u = p * 8 + i;
+          if (P.dbg_flags & 2) { c[u] += __uint_as_float(vi[i]) + __uint_as_float(vj[i]); hv[i] = c[u] * __uint_as_float(vf[i]) + __uint_as_float(vo[i]); continue; }
+          const float ei = ex2_approx(fminf(fmaf(__uint_as_float(vi[i]), NL2E, bi[i]), 57.f));
+          const float ej = ex2_approx(fminf(fmaf(__uint_as_float(vj[i]), 2.f * NL2E, bj[i]), 57.f));
+          const float ef = ex2_approx(fminf(fmaf(__uint_as_float(vf[i]), NL2E, bf[i]), 57.f));
+          const float eo = ex2_approx(fminf(fmaf(__uint_as_float(vo[i]), NL2E, bo[i]), 57.f));
+          const float pj = (1.f - ej) * rcp_approx((1.f + ei) * (1.f + ej));
+          c[u] = fmaf(c[u], rcp_approx(1.f + ef), pj);
+          const float ec = ex2_approx(fminf(c[u] * (2.f * NL2E), 57.f));
+          hv[i] = (1.f - ec) * rcp_approx((1.f + ec) * (1.f + eo));
+        }
+        if (dbgt) { long long t = clock64(); w_math += t - tq; tq = t; }
+        if (!last) {
+          const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]), p2 = pack_f16x2(hv[4], hv[5]), p3 = pack_f16x2(hv[6], hv[7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_own + ((((uint32_t)(half * 2 + p)) ^ sw64) * 16)),
+                       "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+        } else if (valid) {
+          float* ho = P.h_out + (size_t)grow * P.H + rank * 32 + ub + p * 8;
+          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+        }
+        if (dbgt) { long long t = clock64(); w_st += t - tq; tq = t; }
+      }
+      if (!last) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the bulk-copy engine / tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sl + 8 * buf);
+        if (dbgt) { long long t = clock64(); w_pub += t - tq; tq = t; }
+      }
+    }
+    if (P.dbg && lane == 0 && warp == 0) {
+      long long* o = P.dbg + blockIdx.x * 16;
+      o[4] = w_accf; o[5] = clock64() - t_begin; o[6] = w_ld; o[7] = w_math; o[8] = w_st; o[9] = w_pub;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // nobody leaves while a peer may still address its shared memory
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+
+// =====================================================================================================
+// Variant 2: input projection from a table.  x_t W_x + b depends only on the token id, so it is tabulated once
+// per weight set: P[v, :] = scale_g * (Emb[v] W_x + b) for every vocabulary entry v (fp32, chunk-major gate
+// columns, already in the ex2 argument scale).  The step then needs NO x tile, NO W_x slice and no gather warps:
+//   z = scale_g * (h_{t-1} W_h)  +  P[token]          (one FMA per gate value in the epilogue)
+// which frees enough shared memory for 128 batch rows per cluster (all four TMEM lane quarters / SM sub-partitions
+// carry live rows: 8 epilogue warps, 16 units per thread), halves the tensor work per step and makes the x part
+// exact fp32.  Everything else is the scheme above: W_h slice resident, h slices exchanged with the bulk-copy
+// engine into SWIZZLE_64B K-major tiles, one dependency per step.
+// shared memory (H=256): h ping 64 KB | h pong 64 KB | Wh slice 64 KB.  TMEM: one [128 x 128] fp32 accumulator.
+// warps: 0-7 epilogue (warp w: lane quarter w%4, unit half w/4) | 8 MMA issuer + TMEM alloc + weight load | 9 slice exchange
+constexpr int P2_ROWS = 128;
+constexpr int P2_THREADS = 320;
+constexpr int P2_SLICE_BYTES = P2_ROWS * 64;
+
+struct LstmP2Params {
+  const int32_t* tokens;      // [B, T]
+  const float* ptable;        // [V, 4H] fp32, chunk-major, scaled, bias folded in
+  const float* init_h;
+  const float* init_c;
+  float* h_out;               // [B, H]
+  int B, T, t_start, H;
+  long long* dbg;
+};
+
+__global__ void __launch_bounds__(P2_THREADS, 1)
+lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_constant__ LstmP2Params P, int kb_first) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KBh = P.H / KBLK;
+  const int CL = P.H / 32;
+  const uint32_t rank = cluster_ctarank();
+  const int row0 = (blockIdx.x / CL) * P2_ROWS;
+  const int t0 = P.t_start;
+  const int nsteps = P.T - t0;
+  const bool has_init = P.init_h != nullptr;
+
+  uint8_t* h_smem = smem;                                            // [2 tiles][CL slices] of [128 rows x 32 k] fp16 SW64
+  uint8_t* wh_smem = h_smem + (size_t)2 * CL * P2_SLICE_BYTES;       // [KBh] tiles [128 x 64] SW128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wh_smem + (size_t)KBh * W_TILE_BYTES);
+  const uint32_t bar_wf = smem_u32(bars + 0);
+  const uint32_t bar_accf = smem_u32(bars + 1);
+  const uint32_t bar_hr = smem_u32(bars + 2);      // [2]
+  const uint32_t bar_sl = smem_u32(bars + 4);      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_wf, 1);
+    mbar_init(bar_accf, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_hr + 8 * b, 2); mbar_init(bar_sl + 8 * b, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===== W_h slice load (once) + MMA issuer =====
+    if (elect_one_sync()) {
+      mbar_expect_tx(bar_wf, (uint32_t)KBh * W_TILE_BYTES);
+      for (int kb = 0; kb < KBh; ++kb) tma_load_2d(smem_u32(wh_smem + (size_t)kb * W_TILE_BYTES), &tmap_w2d, bar_wf, (kb_first + kb) * KBLK, (int)rank * 128);
+    }
+    __syncwarp();
+    const uint32_t idesc = make_idesc_f16(128, 128);
+    const uint64_t whd = make_sw128_desc(smem_u32(wh_smem)), hd = make_sw64_desc(smem_u32(h_smem));
+    const uint32_t wh_lo = (uint32_t)whd, wh_hi = (uint32_t)(whd >> 32), h_lo0 = (uint32_t)hd, h_hi = (uint32_t)(hd >> 32);
+    long long w_hr = 0, t_begin = clock64();
+    mbar_wait<false>(bar_wf, 0);
+    for (int s = has_init ? 0 : 1; s < nsteps; ++s) {
+      const int hb = (s - 1) & 1;
+      const uint32_t n = s == 0 ? 0u : (uint32_t)(((s - 1) >> 1) + ((hb == 1 && has_init) ? 1 : 0));
+      if (elect_one_sync()) {
+        if (s == 0) mbar_arrive(bar_hr + 8 * hb);
+        else mbar_expect_tx(bar_hr + 8 * hb, (uint32_t)(CL - 1) * P2_SLICE_BYTES);
+      }
+      __syncwarp();
+      mbar_wait_timed<false>(bar_hr + 8 * hb, n & 1, w_hr);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t h_lo = h_lo0 + (uint32_t)(hb * CL * (P2_SLICE_BYTES >> 4));
+        for (int m = 0; m < 2 * CL; ++m)
+          tc_mma_ss3(tmem_base, h_lo + (uint32_t)((m >> 1) * (P2_SLICE_BYTES >> 4) + 2 * (m & 1)), h_hi,
+                     wh_lo + (uint32_t)((m >> 2) * (W_TILE_BYTES >> 4) + 2 * (m & 3)), wh_hi, idesc, m ? 1u : 0u);
+        tc_commit(bar_accf);
+      }
+      __syncwarp();
+    }
+    if (P.dbg && lane == 0) { P.dbg[blockIdx.x * 16 + 0] = w_hr; P.dbg[blockIdx.x * 16 + 3] = clock64() - t_begin; }
+  } else if (warp == 9) {
+    // ===== slice exchange =====
+    const uint32_t peer_h = map_to_cta(smem_u32(h_smem), (uint32_t)(lane < CL ? lane : 0));
+    const uint32_t peer_bar = map_to_cta(bar_hr, (uint32_t)(lane < CL ? lane : 0));
+    if (has_init) {
+      mbar_wait<false>(bar_sl + 8, 0);
+      if (lane == 0) mbar_arrive(bar_hr + 8);
+    }
+    for (int s = 0; s + 1 < nsteps; ++s) {
+      const int tb = s & 1;
+      const uint32_t n = (uint32_t)((s >> 1) + ((tb == 1 && has_init) ? 1 : 0));
+      mbar_wait<false>(bar_sl + 8 * tb, n & 1);
+      const uint32_t off = (uint32_t)(tb * CL * P2_SLICE_BYTES) + rank * P2_SLICE_BYTES;
+      if (lane < CL && lane != (int)rank) bulk_copy_to_peer(peer_h + off, smem_u32(h_smem) + off, P2_SLICE_BYTES, peer_bar + 8 * tb);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hr + 8 * tb);
+    }
+  } else {
+    // ===== epilogue: thread == (batch row, 16 of this CTA's 32 hidden units), c in registers =====
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const int grow = row0 + r;
+    const bool valid = grow < P.B;
+    const int32_t* trow = P.tokens + (size_t)min(grow, P.B - 1) * P.T + t0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int ub = half * 16;
+    const uint32_t row_off64 = (uint32_t)(r * 64);
+    const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
+    float c[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) c[u] = has_init ? __ldg(P.init_c + rank * 32 + ub + u) : 0.f;
+    if (has_init) {
+      const uint32_t t1 = smem_u32(h_smem) + (uint32_t)(CL * P2_SLICE_BYTES) + row_off64;
+      for (int q = half; q < CL; q += 2)
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(P.init_h + q * 32 + j * 8 + 2 * e), __ldg(P.init_h + q * 32 + j * 8 + 2 * e + 1));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t1 + (uint32_t)q * P2_SLICE_BYTES + (((uint32_t)j ^ sw64) * 16)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sl + 8);
+    }
+    const uint32_t own_slice = smem_u32(h_smem) + rank * P2_SLICE_BYTES + row_off64;
+    const size_t pcol = (size_t)rank * 128 + ub;
+    constexpr float NL2E = -1.4426950408889634f;
+    long long w_accf = 0, w_math = 0, tq = 0, t_begin = clock64();
+    const bool dbgt = P.dbg != nullptr;
+    int tok = __ldg(trow);
+    uint32_t accf_uses = 0;
+    for (int s = 0; s < nsteps; ++s) {
+      const bool last = s == nsteps - 1;
+      const bool has_state = s > 0 || has_init;
+      // this step's table row: 4 gates x 16 units (issued before the accumulator wait -- the loads fly during the MMAs)
+      const float4* prow = reinterpret_cast<const float4*>(P.ptable + (size_t)tok * 4 * P.H + pcol);
+      float4 pv[4][4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pv[g][q] = __ldg(prow + g * 8 + q);
+      if (!last) tok = __ldg(trow + s + 1);
+      if (has_state) {
+        mbar_wait_timed<false>(bar_accf, accf_uses & 1, w_accf);
+        ++accf_uses;
+        tc_fence_after();
+      }
+      if (dbgt) tq = clock64();
+      const uint32_t tile_own = own_slice + (uint32_t)((s & 1) * CL * P2_SLICE_BYTES);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        uint32_t vi[8], vj[8], vf[8], vo[8];
+        if (has_state) {
+          const uint32_t acc = lane_base + (uint32_t)(ub + p * 8);
+          TMEM_LD_8(acc, vi);
+          TMEM_LD_8(acc + 32, vj);
+          TMEM_LD_8(acc + 64, vf);
+          TMEM_LD_8(acc + 96, vo);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vi[i] = vj[i] = vf[i] = vo[i] = 0u;
+        }
+        float hv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int u = p * 8 + i;
+          const float4 qi = pv[0][p * 2 + (i >> 2)], qj = pv[1][p * 2 + (i >> 2)], qf = pv[2][p * 2 + (i >> 2)], qo = pv[3][p * 2 + (i >> 2)];
+          const float bi = (i & 3) == 0 ? qi.x : (i & 3) == 1 ? qi.y : (i & 3) == 2 ? qi.z : qi.w;
+          const float bj = (i & 3) == 0 ? qj.x : (i & 3) == 1 ? qj.y : (i & 3) == 2 ? qj.z : qj.w;
+          const float bf = (i & 3) == 0 ? qf.x : (i & 3) == 1 ? qf.y : (i & 3) == 2 ? qf.z : qf.w;
+          const float bo = (i & 3) == 0 ? qo.x : (i & 3) == 1 ? qo.y : (i & 3) == 2 ? qo.z : qo.w;
+          const float ei = ex2_approx(fminf(fmaf(__uint_as_float(vi[i]), NL2E, bi), 57.f));
+          const float ej = ex2_approx(fminf(fmaf(__uint_as_float(vj[i]), 2.f * NL2E, bj), 57.f));
+          const float ef = ex2_approx(fminf(fmaf(__uint_as_float(vf[i]), NL2E, bf), 57.f));
+          const float eo = ex2_approx(fminf(fmaf(__uint_as_float(vo[i]), NL2E, bo), 57.f));
+          const float pj = (1.f - ej) * rcp_approx((1.f + ei) * (1.f + ej));
+          c[u] = fmaf(c[u], rcp_approx(1.f + ef), pj);
+          const float ec = ex2_approx(fminf(c[u] * (2.f * NL2E), 57.f));
+          hv[i] = (1.f - ec) * rcp_approx((1.f + ec) * (1.f + eo));
+        }
+        if (!last) {
+          const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]), p2 = pack_f16x2(hv[4], hv[5]), p3 = pack_f16x2(hv[6], hv[7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_own + ((((uint32_t)(half * 2 + p)) ^ sw64) * 16)),
+                       "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+        } else if (valid) {
+          float* ho = P.h_out + (size_t)grow * P.H + rank * 32 + ub + p * 8;
+          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+        }
+      }
+      if (!last) {
+        // (the TMEM reads above are complete: wait::ld) -> own slice visible to the copy engine / tensor core
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sl + 8 * (s & 1));
+      }
+      if (dbgt) w_math += clock64() - tq;
+    }
+    if (P.dbg && lane == 0 && warp == 0) {
+      long long* o = P.dbg + blockIdx.x * 16;
+      o[4] = w_accf; o[5] = clock64() - t_begin; o[7] = w_math;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+  }
+}
+
+// Wxp[k][n'] = scale_g * K[k][g*H + 32c + j]   (n' = c*128 + g*32 + j), k < We
+__global__ void ptable_wx_kernel(const float* __restrict__ K, int We, int H, float* __restrict__ Wxp) {
+  const int64_t total = (int64_t)We * 4 * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / (4 * H)), np = (int)(i - (int64_t)k * 4 * H);
+    const int c = np >> 7, g = (np >> 5) & 3, j = np & 31;
+    Wxp[i] = (g == 1 ? -2.885390081777927f : -1.4426950408889634f) * K[(size_t)k * 4 * H + g * H + c * 32 + j];
+  }
+}
+// P[v][n'] = bias_r[n']  (the GEMM then accumulates the projection on top)
+__global__ void ptable_bias_kernel(const float* __restrict__ bias_r, int64_t V, int H4, float* __restrict__ Pt) {
+  const int64_t total = V * H4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) Pt[i] = bias_r[i % H4];
+}
+
+}  // namespace
+
+// H = 64 / 128 / 256 (cluster of 2 / 4 / 8 CTAs), We a multiple of 64 up to 256
+bool lstm_cluster_supported(int We, int H) { return We % 64 == 0 && We >= 64 && We <= 256 && (H == 64 || H == 128 || H == 256); }
+
+int lstm_forward_cluster(const int32_t* tokens, int B, int T, int t_start, const __half* emb_f16, int We, int H,
+                         const TcTower& tt, const float* init_h, const float* init_c, float* h_out, cudaStream_t st,
+                         int64_t* launches) {
+  if (B <= 0 || T - t_start <= 0) return SSE_OK;
+  LstmClParams p;
+  p.tokens = tokens; p.emb = emb_f16; p.bias_r = tt.bias_r; p.init_h = init_h; p.init_c = init_c; p.h_out = h_out;
+  p.B = B; p.T = T; p.t_start = t_start; p.We = We; p.H = H; p.dbg = nullptr;
+  p.dbg_flags = getenv("SSE_LSTM_CL_FLAGS") ? atoi(getenv("SSE_LSTM_CL_FLAGS")) : 0;
+  const int CL = H / 32, KBx = We / KBLK, KBh = H / KBLK;
+  const int n_clusters = cdiv(B, CL_ROWS);
+  const int grid = n_clusters * CL;
+  const size_t smem = 1024 + (size_t)KBx * A_TILE_BYTES + (size_t)2 * KBh * A_TILE_BYTES + (size_t)(KBx + KBh) * W_TILE_BYTES + 512 + 256;
+  const bool want_dbg = getenv("SSE_LSTM_DEBUG") != nullptr;
+  long long* d_dbg = nullptr;
+  if (want_dbg) { cudaMalloc(&d_dbg, (size_t)grid * 128); cudaMemset(d_dbg, 0, (size_t)grid * 128); p.dbg = d_dbg; }
+  SSE_CUDA_OK(cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(CL_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SSE_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel, *reinterpret_cast<const CUtensorMap*>(tt.tmap2d), p));
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  if (want_dbg) {
+    std::vector<long long> hd((size_t)grid * 16);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_dbg);
+    const char* nm[12] = {"mma_wait_hready", "mma_wait_xfull", "mma_wait_acce", "mma_total", "epi_wait_accf", "epi_total",
+                          "epi_tmem_ld", "epi_math", "epi_store", "epi_publish", "mma_issue_h", "mma_issue_x(+waits)"};
+    for (int c = 0; c < 12; ++c) {
+      long long sm = 0;
+      for (int i = 0; i < grid; ++i) sm += hd[(size_t)i * 16 + c];
+      fprintf(stderr, "[lstm cluster dbg] %-16s avg %10lld cycles  (grid %d = %d clusters x %d, steps %d)\n", nm[c], sm / grid, grid, n_clusters, CL, T - t_start);
+    }
+  }
+  return SSE_OK;
+}
+
+// ---- variant 2 host side ------------------------------------------------------------------------------
+bool lstm_ptable_supported(int64_t V, int We, int H) {
+  (void)We;
+  return (H == 64 || H == 128 || H == 256) && V * 4 * H * 4 <= ((int64_t)2 << 30);      // table <= 2 GiB
+}
+
+void lstm_ptable_release(TcTower& tt) {
+  if (tt.ptable) cudaFree(tt.ptable);
+  if (tt.wxp) cudaFree(tt.wxp);
+  tt.wxp = nullptr;
+  tt.ptable = nullptr; tt.ptable_valid = false; tt.ptable_rows = 0;
+}
+
+// P = scale * (Emb W_x + b), fp32 (one SIMT GEMM per weight set; the recurrent part keeps using tt.wt / tt.bias_r)
+int lstm_ptable_prepare(TcTower& tt, const float* emb, int64_t V, const float* K, int We, int H, cudaStream_t st, int64_t* launches) {
+  if (!tt.valid) { set_error("lstm_ptable_prepare: tower weights not prepared"); return SSE_ESTATE; }
+  if (tt.ptable && tt.ptable_rows != V) { cudaFree(tt.ptable); tt.ptable = nullptr; }
+  if (!tt.ptable) { SSE_CUDA_OK(cudaMalloc(&tt.ptable, (size_t)V * 4 * H * 4)); tt.ptable_rows = V; }
+  if (!tt.wxp) SSE_CUDA_OK(cudaMalloc(&tt.wxp, (size_t)We * 4 * H * 4));
+  float* wxp = tt.wxp;
+  ptable_wx_kernel<<<148, 256, 0, st>>>(K, We, H, wxp);
+  if (launches) ++*launches;
+  ptable_bias_kernel<<<148 * 8, 256, 0, st>>>(tt.bias_r, V, 4 * H, tt.ptable);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  // rows in slabs that keep the GEMM's M within int range and friendly to the SIMT kernel
+  for (int64_t v0 = 0; v0 < V; v0 += 65536) {
+    const int nv = (int)std::min<int64_t>(65536, V - v0);
+    SSE_TRY(sgemm(false, false, nv, 4 * H, We, 1.f, emb + (size_t)v0 * We, We, wxp, 4 * H, 1.f, tt.ptable + (size_t)v0 * 4 * H, 4 * H, st, launches));
+  }
+  tt.ptable_valid = true;
+  return SSE_OK;
+}
+
+int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We, int H, const TcTower& tt, const float* init_h,
+                        const float* init_c, float* h_out, cudaStream_t st, int64_t* launches) {
+  if (B <= 0 || T - t_start <= 0) return SSE_OK;
+  if (!tt.ptable_valid) { set_error("lstm_forward_ptable: table not prepared"); return SSE_ESTATE; }
+  LstmP2Params p;
+  p.tokens = tokens; p.ptable = tt.ptable; p.init_h = init_h; p.init_c = init_c; p.h_out = h_out;
+  p.B = B; p.T = T; p.t_start = t_start; p.H = H; p.dbg = nullptr;
+  const int CL = H / 32, KBh = H / KBLK;
+  const int n_clusters = cdiv(B, P2_ROWS);
+  const int grid = n_clusters * CL;
+  const size_t smem = 1024 + (size_t)2 * CL * P2_SLICE_BYTES + (size_t)KBh * W_TILE_BYTES + 256;
+  const bool want_dbg = getenv("SSE_LSTM_DEBUG") != nullptr;
+  long long* d_dbg = nullptr;
+  if (want_dbg) { cudaMalloc(&d_dbg, (size_t)grid * 128); cudaMemset(d_dbg, 0, (size_t)grid * 128); p.dbg = d_dbg; }
+  SSE_CUDA_OK(cudaFuncSetAttribute(lstm_ptable_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(P2_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SSE_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_ptable_kernel, *reinterpret_cast<const CUtensorMap*>(tt.tmap2d), p, We / KBLK));
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  if (want_dbg) {
+    std::vector<long long> hd((size_t)grid * 16);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_dbg);
+    const char* nm[8] = {"mma_wait_hready", "-", "-", "mma_total", "epi_wait_accf", "epi_total", "-", "epi_ld+math+store"};
+    for (int c = 0; c < 8; ++c) {
+      if (nm[c][0] == '-') continue;
+      long long sm = 0;
+      for (int i = 0; i < grid; ++i) sm += hd[(size_t)i * 16 + c];
+      fprintf(stderr, "[lstm ptable dbg] %-18s avg %10lld cycles  (grid %d = %d clusters x %d, steps %d)\n", nm[c], sm / grid, grid, n_clusters, CL, T - t_start);
+    }
+  }
+  return SSE_OK;
+}
+
+}  // namespace sse

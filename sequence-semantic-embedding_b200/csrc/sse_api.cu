@@ -70,6 +70,7 @@ void refresh_pointers(sse_handle* h) {
 void invalidate_derived(sse_handle* h) {
   h->pad[0].valid = h->pad[1].valid = false;
   h->tct[0].valid = h->tct[1].valid = false;
+  h->tct[0].ptable_valid = h->tct[1].ptable_valid = false;
   h->emb_f16_valid = false;
 }
 
@@ -157,7 +158,22 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens, int B, float* 
     SSE_TRY(h->enc_ws.ensure((Bpad * H + (size_t)B * H) * 4));
     float* cs = h->enc_ws.as<float>();
     float* hout = cs + Bpad * H;
-    SSE_TRY(lstm_forward_tc(tokens, B, T, t_start, h->emb_f16, We, H, tt, ih, ic, cs, hout, st, &h->launches));
+    // kernel choice (lstm_kernel option): 3 = cluster kernel with the tabulated input projection (default whenever the
+    // table fits), 2 = cluster kernel with resident W_x and gathered x tiles, 1 = weight-streaming kernel
+    const bool cluster_ok = lstm_cluster_supported(We, H);
+    const bool ptable_ok = lstm_ptable_supported(c.vocab_size, We, H);
+    int kern = h->opt_lstm_kernel;
+    if (kern == 2 && !cluster_ok) { set_error("cluster LSTM kernel needs H in {64,128,256}, We%%64==0, We<=256 (We=%d H=%d)", We, H); return SSE_EINVAL; }
+    if (kern == 3 && !ptable_ok) { set_error("table LSTM kernel needs H in {64,128,256} and V*4H*4 <= 2 GiB (V=%d H=%d)", c.vocab_size, H); return SSE_EINVAL; }
+    if (kern == 0) kern = ptable_ok ? 3 : ((cluster_ok && B < 128 * (h->num_sms / 2)) ? 2 : 1);
+    if (kern == 3) {
+      if (!tt.ptable_valid) SSE_TRY(lstm_ptable_prepare(tt, emb, c.vocab_size, tw.K, We, H, st, &h->launches));
+      SSE_TRY(lstm_forward_ptable(tokens, B, T, t_start, We, H, tt, ih, ic, hout, st, &h->launches));
+    } else if (kern == 2) {
+      SSE_TRY(lstm_forward_cluster(tokens, B, T, t_start, h->emb_f16, We, H, tt, ih, ic, hout, st, &h->launches));
+    } else {
+      SSE_TRY(lstm_forward_tc(tokens, B, T, t_start, h->emb_f16, We, H, tt, ih, ic, cs, hout, st, &h->launches));
+    }
     SSE_TRY(sgemm(false, false, B, E, H, 1.f, hout, H, tw.M, E, 0.f, out, E, st, &h->launches));
     if (normalize) SSE_TRY(l2norm_rows(out, B, E, st, &h->launches));
     return SSE_OK;
@@ -321,6 +337,7 @@ int sse_destroy(sse_handle* h) {
   if (h->grad_arena) cudaFree(h->grad_arena);
   search_tc_release(h->tc);
   lstm_tc_release(h->tct[0]); lstm_tc_release(h->tct[1]);
+  lstm_ptable_release(h->tct[0]); lstm_ptable_release(h->tct[1]);
   if (h->emb_f16) cudaFree(h->emb_f16);
   delete h;
   return SSE_OK;
@@ -509,6 +526,7 @@ int sse_set_option(sse_handle* h, const char* key, int value) {
   if (!strcmp(key, "search")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_search = value; return SSE_OK; }
   if (!strcmp(key, "encoder")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_encoder = value; return SSE_OK; }
   if (!strcmp(key, "pad_skip")) { h->opt_pad_skip = value != 0; return SSE_OK; }
+  if (!strcmp(key, "lstm_kernel")) { if (value < 0 || value > 3) return SSE_EINVAL; h->opt_lstm_kernel = value; return SSE_OK; }
   if (!strcmp(key, "search_ctas")) { if (value < 0) return SSE_EINVAL; h->opt_search_ctas = value; return SSE_OK; }
   set_error("sse_set_option: unknown key '%s'", key);
   return SSE_EINVAL;

@@ -123,6 +123,10 @@ struct TcTower {
   alignas(64) unsigned char tmap2d[128];   // 2-D map, box = one [128 x 64] sub-tile (fallback)
   bool use3d = true;
   bool valid = false;
+  float* ptable = nullptr;         // [V, 4H] fp32 input-projection table (lstm_cluster.cu variant 2); rebuilt when the weights change
+  int64_t ptable_rows = 0;
+  float* wxp = nullptr;            // [We, 4H] permuted + scaled W_x (GEMM operand of the table build)
+  bool ptable_valid = false;
 };
 bool lstm_tc_supported(int We, int H);
 int lstm_tc_prepare(TcTower& tt, const float* K, const float* b, int We, int H, cudaStream_t st, int64_t* launches);
@@ -130,6 +134,19 @@ void lstm_tc_release(TcTower& tt);
 int lstm_forward_tc(const int32_t* tokens, int B, int T, int t_start, const __half* emb_f16, int We, int H,
                     const TcTower& tt, const float* init_h, const float* init_c, float* c_scratch, float* h_out,
                     cudaStream_t st, int64_t* launches);
+
+// cluster variant for small / medium batches (lstm_cluster.cu): weights resident in the shared memory of a cluster
+bool lstm_cluster_supported(int We, int H);
+int lstm_forward_cluster(const int32_t* tokens, int B, int T, int t_start, const __half* emb_f16, int We, int H,
+                         const TcTower& tt, const float* init_h, const float* init_c, float* h_out, cudaStream_t st,
+                         int64_t* launches);
+
+// variant 2 (lstm_cluster.cu): input projection tabulated per vocabulary entry, 128 rows per cluster
+bool lstm_ptable_supported(int64_t V, int We, int H);
+int lstm_ptable_prepare(TcTower& tt, const float* emb, int64_t V, const float* K, int We, int H, cudaStream_t st, int64_t* launches);
+void lstm_ptable_release(TcTower& tt);
+int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We, int H, const TcTower& tt, const float* init_h,
+                        const float* init_c, float* h_out, cudaStream_t st, int64_t* launches);
 
 // small utilities (util.cu)
 int fill_f32(float* p, int64_t n, float v, cudaStream_t st, int64_t* launches);

@@ -41,6 +41,7 @@ struct sse_handle {
   int64_t arena_floats = 0;
 
   int opt_search = 0, opt_encoder = 0;
+  int opt_lstm_kernel = 0;          // 0 = auto by batch size; 1 = weight-streaming kernel (lstm_tc.cu); 2 = cluster kernel (lstm_cluster.cu)
   int opt_search_ctas = 0;          // 0 = all SMs; else cap on the scan grid (leaves SMs to a concurrent encoder)
   bool opt_pad_skip = false;
   int64_t launches = 0;

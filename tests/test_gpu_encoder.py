@@ -125,16 +125,20 @@ def test_param_round_trip_and_errors():
 
 
 # ---------------------------------------------------------------------------------------------
-# tensor-core (tcgen05, bf16 operands / fp32 accumulate + state) LSTM tower: north_star tolerance
+# tensor-core (tcgen05, fp16 operands / fp32 accumulate + state) LSTM tower: north_star tolerance
 TOL_TC = 1e-3
 
 
 @pytest.mark.parametrize("We,H,E,T,B", [(256, 256, 256, 50, 300), (64, 64, 32, 12, 128), (128, 192, 64, 20, 77),
                                         (256, 128, 256, 50, 1), (192, 256, 128, 30, 513)])
-def test_tc_lstm_encode_within_tolerance(We, H, E, T, B):
+@pytest.mark.parametrize("kern", [1, 2, 3])   # 1 = weight-streaming kernel (lstm_tc.cu), 2 / 3 = cluster kernels (lstm_cluster.cu; 3 = tabulated input projection)
+def test_tc_lstm_encode_within_tolerance(We, H, E, T, B, kern):
+    if kern >= 2 and H not in (64, 128, 256):
+        pytest.skip("cluster kernel: H in {64,128,256}")
     mode, V = "dual-encoder", 5000
     h, p = make(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
     h.set_option("encoder", 2)          # force the tcgen05 path (raise if unsupported)
+    h.set_option("lstm_kernel", kern)
     rng = np.random.default_rng(We + H + B)
     for side, name in ((sse_ffi.SIDE_SRC, "src"), (sse_ffi.SIDE_TGT, "tgt")):
         tok = np.concatenate([O.synth_tokens(rng, B - B // 2, T, V, "full"), O.synth_tokens(rng, B // 2, T, V, "real", 4.0)]) \
@@ -150,13 +154,15 @@ def test_tc_lstm_encode_within_tolerance(We, H, E, T, B):
     h.close()
 
 
-def test_tc_lstm_pad_skip_and_exact_mode_switch():
+@pytest.mark.parametrize("kern", [1, 2, 3])
+def test_tc_lstm_pad_skip_and_exact_mode_switch(kern):
     mode, V, We, H, E, T, B = "shared-encoder", 3000, 128, 128, 64, 40, 200
     h, p = make(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
     rng = np.random.default_rng(12)
     tok = O.synth_tokens(rng, B, T, V, "real", 3.0)
     want = O.encode(p, mode, "src", tok, True)
     h.set_option("encoder", 2)
+    h.set_option("lstm_kernel", kern)
     a = h.encode_host(0, tok, True)
     h.set_option("pad_skip", 1)
     b = h.encode_host(0, tok, True)           # starts every row from the pad-prefix state table
@@ -168,4 +174,23 @@ def test_tc_lstm_pad_skip_and_exact_mode_switch():
         h2, _ = make(mode, 100, 50, 64, 96, 96, 20, precision=sse_ffi.PRECISION_TC)
         h2.set_option("encoder", 2)
         h2.encode_host(0, np.zeros((2, 20), np.int32), True)
+    h.close()
+
+
+def test_tc_lstm_table_follows_parameter_updates():
+    """The tabulated input projection (lstm_kernel 3) is derived state: it must be rebuilt after set_param."""
+    mode, V, We, H, E, T, B = "dual-encoder", 900, 64, 64, 32, 10, 70
+    h, p = make(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
+    h.set_option("encoder", 2)
+    h.set_option("lstm_kernel", 3)
+    rng = np.random.default_rng(5)
+    tok = O.synth_tokens(rng, B, T, V, "real", 2.0)
+    a = h.encode_host(0, tok, True)
+    assert np.abs(a - O.encode(p, mode, "src", tok, True)).max() < TOL_TC
+    p2 = dict(p)
+    p2["word_embedding"] = (p["word_embedding"] * 0.5 + 0.01).astype(np.float32)
+    h.set_params({"word_embedding": p2["word_embedding"]})
+    b = h.encode_host(0, tok, True)
+    assert np.abs(b - O.encode(p2, mode, "src", tok, True)).max() < TOL_TC
+    assert np.abs(a - b).max() > 1e-2
     h.close()
