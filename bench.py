@@ -12,10 +12,10 @@ cosine top-k (k=10) of the whole index.  Tokens are synthetic in the FULL-length
         the reference's own CPU path (numpy restatement of the TF1 encoder + the
         reference's np.dot / full-argsort ranking) on the host cores, bounded sample.
 
-N > 1: launched under torchrun, one rank per GPU; the index is sharded by rows
-(N/G per rank, weak scaling = fixed N_local per GPU), every rank encodes the same Q
-queries, searches its shard, and ONE NCCL all-gather of the packed per-shard top-k
-([Q,k] scores + ids) is followed by the merge kernel.
+N > 1: launched under torchrun, one rank per GPU; the 1M-target index is sharded by rows
+(N/G per rank) and a step carries G x 600 queries: each rank encodes its own 600, an NCCL
+all-gather distributes the encodings, every rank scans its shard for all G x 600, and an NCCL
+all-gather of the packed per-shard top-k ([Q,k] scores + ids) is followed by the merge kernel.
 """
 from __future__ import annotations
 
@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="run encode and search of a step back to back on one stream "
                     "(default: 2-stage software pipeline over steps: encoder of batch s+1 overlaps the scan of batch s)")
-    ap.add_argument("--search-ctas", type=int, default=126, help="scan grid cap when pipelining (rest of the SMs run the encoder)")
+    ap.add_argument("--search-ctas", type=int, default=108, help="scan grid cap when pipelining (rest of the SMs run the encoder)")
     ap.add_argument("--train-steps", type=int, default=5, help="timed train steps for the secondary train-step/s figure (0 = skip)")
     ap.add_argument("--train-rows", type=int, default=1024, help="pair rows per GPU per train step (512 pos + 512 neg, data.py:95-115 layout)")
     ap.add_argument("--cpu-sample-targets", type=int, default=1_000_000)
@@ -150,9 +150,10 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # N-GPU job: the 1M-target index is sharded by rows (N/G per rank, resident in HBM); a step carries G x 600
-    # queries, every rank encodes all of them (200 B of tokens per query: cheaper than a collective), scans its
-    # shard for all of them, and ONE NCCL all-gather of the packed per-shard top-k is followed by the merge
-    # kernel.  Per-GPU scan work (G*Q x N/G) is constant in G -> weak scaling; value = G*Q*steps / time.
+    # queries: rank r encodes its own 600, one NCCL all-gather hands every rank all G x 600 encodings (0.6 MB per
+    # rank), every rank scans its shard for all of them, and one NCCL all-gather of the packed per-shard top-k is
+    # followed by the merge kernel.  Per-GPU work (600 encodes, G*600 x N/G scan) is constant in G -> weak scaling;
+    # value = G*600*steps / time.
     Q, k = args.queries * world, K_TOP
     n_local = args.targets // world
     h = sse_ffi.Handle("dual-encoder", V, WE, E, H, H, T, predict_nbest=k, device=local, precision=sse_ffi.PRECISION_TC)
@@ -165,11 +166,13 @@ def run_b200(args):
     idx = idx / idx.norm(dim=1, keepdim=True)
     h.index_set(idx, n_local, global_offset=rank * n_local)
     del idx
-    rng = np.random.default_rng(42)             # same queries on every rank
+    rng = np.random.default_rng(42)             # the step's G x 600 queries; rank r encodes rows [600 r, 600 r + 600)
     n_batches = 4                                # rotate batches; the index (>= 256 MB bf16) exceeds nothing smaller than L2 at 100k+
-    tok_host = [torch.from_numpy(synth_tokens(rng, Q)).pin_memory() for _ in range(n_batches)]
+    Ql = args.queries                            # query rows this rank encodes per step
+    tok_host = [torch.from_numpy(synth_tokens(rng, Q)[rank * Ql:(rank + 1) * Ql].copy()).pin_memory() for _ in range(n_batches)]
     tok_dev = [t.cuda() for t in tok_host]
     enc = torch.empty(Q, E, device="cuda")
+    enc_local = [torch.empty(Ql, E, device="cuda") for _ in range(2)]
     sc = torch.empty(Q, k, device="cuda")
     ix = torch.empty(Q, k, device="cuda", dtype=torch.int32)
     packed = torch.empty(Q, 2 * k, device="cuda")
@@ -189,10 +192,19 @@ def run_b200(args):
     if pipeline:
         h.set_option("search_ctas", args.search_ctas)
 
+    def encode_all(b, out, scratch, st):
+        """this rank's 600 queries through the source encoder; N > 1: all-gather of the [600, E] encodings so that
+        every rank holds the step's G x 600 query vectors for its index shard"""
+        if world == 1:
+            h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Ql, out, True, st)
+        else:
+            h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Ql, scratch, True, st)
+            dist.all_gather_into_tensor(out, scratch)
+
     def issue_encode(b, slot):
         with torch.cuda.stream(enc_stream):
             enc_stream.wait_event(enc_free[slot])          # the scan that last read this slot has finished
-            h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Q, enc2[slot], True, enc_stream)
+            encode_all(b, enc2[slot], enc_local[slot], enc_stream)
             enc_ready[slot].record(enc_stream)
 
     def step_device(b):
@@ -212,7 +224,7 @@ def run_b200(args):
             enc_free[n & 1].record(stream)
             state["n"] = n + 1
         else:
-            h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Q, enc, True, stream)
+            encode_all(b, enc, enc_local[0], stream)
             h.search(enc, Q, k, sc, ix, stream)
         if world > 1:
             packed[:, :k] = sc
@@ -271,7 +283,7 @@ def run_b200(args):
     # dominant kernel (the index scan) timed alone, CUDA events on the launching stream, for the roofline
     h.set_option("search_ctas", 0)
     torch.cuda.synchronize()
-    h.encode(sse_ffi.SIDE_SRC, tok_dev[0], Q, enc, True, stream)
+    encode_all(0, enc, enc_local[0], stream)
     for _ in range(3):
         h.search(enc, Q, k, sc, ix, stream)
     torch.cuda.synchronize()
@@ -285,7 +297,7 @@ def run_b200(args):
     ms_search = e0.elapsed_time(e1) / reps
     e0.record()
     for _ in range(reps):
-        h.encode(sse_ffi.SIDE_SRC, tok_dev[0], Q, enc, True, stream)
+        h.encode(sse_ffi.SIDE_SRC, tok_dev[0], Ql, enc_local[0], True, stream)
     e1.record()
     torch.cuda.synchronize()
     ms_enc = e0.elapsed_time(e1) / reps
@@ -355,9 +367,10 @@ def run_b200(args):
     roof["kernel"] = "search (prep+sample scan+select_tau+filter scan+finalize)" if use_tc else "search_simt_kernel+merge"
     roof["ms_per_launch"] = ms_search
     roof["algorithmic"] = {"flops": flops, "bytes": bytes_alg}
-    roof["encoder"] = {"ms": ms_enc, "flops": Q * F_LSTM, "achieved_tflops": Q * F_LSTM / (ms_enc * 1e-3) / 1e12,
-                       "achieved_frac_of_bf16_peak": Q * F_LSTM / (ms_enc * 1e-3) / 1e12 / bf16_tf,
-                       "kernel": "lstm_tc_kernel (tcgen05, fp16 operands; %d-row tiles at this batch) + sgemm + l2norm" % (128 if Q >= 9472 else (64 if Q >= 4736 else 32))}
+    roof["encoder"] = {"ms": ms_enc, "rows": Ql, "flops": Ql * F_LSTM, "achieved_tflops": Ql * F_LSTM / (ms_enc * 1e-3) / 1e12,
+                       "achieved_frac_of_bf16_peak": Ql * F_LSTM / (ms_enc * 1e-3) / 1e12 / bf16_tf,
+                       "kernel": "lstm_ptable_kernel (clusters of 8 CTAs x 128 rows, W_h slices resident in shared memory, tcgen05 fp16 operands, "
+                                 "input projection from the per-token table) + sgemm + l2norm; flops counted as the full LSTM (x and h parts)"}
 
     total_q = Q * args.steps
     out = {
@@ -369,12 +382,13 @@ def run_b200(args):
                                "cosine top-%d over N=%d targets (%d per GPU shard)" % (Q, k, n_local * world, n_local),
                    "targets_per_gpu": n_local, "targets_total": n_local * world, "queries_per_step": Q,
                    "queries_per_step_per_gpu": args.queries, "k": k,
-                   "parallelism": "index row-shard x%d, %d queries/step (600 per GPU), 1 NCCL all-gather of per-shard [Q,k]" % (world, Q) if world > 1 else "single GPU",
+                   "parallelism": ("index row-shard x%d, %d queries/step: each rank encodes its 600, NCCL all-gather of the [600,E] encodings, "
+                                   "every rank scans its shard for all %d, NCCL all-gather of the per-shard [Q,k] + merge" % (world, Q, Q)) if world > 1 else "single GPU",
                    "pipeline": ("2-stage over steps: encoder of batch s+1 (its own stream, %d SMs left free by the scan grid cap %d) overlaps the scan of batch s"
                                 % (148 - args.search_ctas, args.search_ctas)) if pipeline else "none (encode then scan on one stream)",
                    "l2": "index shard (%.0f MB) is re-streamed every step and exceeds L2 (126 MB); query batches rotate" %
                          (bytes_alg / 1e6)},
-        "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * T * 4,
+        "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Ql * T * 4,
                 "d2h_bytes_per_step": Q * k * 8, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "clocks": clocks,
