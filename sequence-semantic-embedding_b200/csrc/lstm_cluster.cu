@@ -140,6 +140,16 @@ __device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
+// K-major tile whose rows are 32 bytes (16 fp16 = one k-step): SWIZZLE_32B atoms, 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t make_sw32_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
 // shared memory of this CTA -> shared memory of a peer CTA through the bulk-copy engine; completes (bytes) on the
 // PEER's mbarrier
 __device__ __forceinline__ void bulk_copy_to_peer(uint32_t peer_dst, uint32_t local_src, uint32_t bytes, uint32_t peer_bar) {
@@ -171,6 +181,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -193,6 +208,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 __device__ __forceinline__ void lds_v4(uint32_t addr, float* v) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
+// 256-bit read-only global load (sm_100: LDG.E.256): one 32-byte sector per lane per instruction
+__device__ __forceinline__ void ldg_v8(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
 }
 
 #define TMEM_LD_8(taddr, v)                                                                                         \
@@ -500,7 +522,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_c
 // warps: 0-7 epilogue (warp w: lane quarter w%4, unit half w/4) | 8 MMA issuer + TMEM alloc + weight load | 9 slice exchange
 constexpr int P2_ROWS = 128;
 constexpr int P2_THREADS = 320;
-constexpr int P2_SLICE_BYTES = P2_ROWS * 64;
+constexpr int P2_SUB_BYTES = P2_ROWS * 32;      // one sub-slice: [128 rows x 16 units] fp16, SWIZZLE_32B K-major
 
 struct LstmP2Params {
   const int32_t* tokens;      // [B, T]
@@ -509,6 +531,8 @@ struct LstmP2Params {
   const float* init_c;
   float* h_out;               // [B, H]
   int B, T, t_start, H;
+  int gate_math;              // 0: ex2/rcp form (8 MUFU per unit); 1: tanh.approx form (5 MUFU per unit) -- same accuracy on the
+                              // encodings (4.5e-5 vs the fp32 oracle) but measured 15% SLOWER per step, kept as an experiment knob
   long long* dbg;
 };
 
@@ -525,24 +549,26 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   const int nsteps = P.T - t0;
   const bool has_init = P.init_h != nullptr;
 
-  uint8_t* h_smem = smem;                                            // [2 tiles][CL slices] of [128 rows x 32 k] fp16 SW64
-  uint8_t* wh_smem = h_smem + (size_t)2 * CL * P2_SLICE_BYTES;       // [KBh] tiles [128 x 64] SW128
+  // h tile = 2*CL sub-slices of 16 hidden units: sub-slice m = units [16 m, 16 m + 16) = CTA m/2's pass m%2,
+  // [128 rows x 32 B] fp16, SWIZZLE_32B K-major -- exactly the A operand of k-step m.
+  uint8_t* h_smem = smem;                                            // [2 tiles][2 CL sub-slices]
+  uint8_t* wh_smem = h_smem + (size_t)2 * 2 * CL * P2_SUB_BYTES;     // [KBh] tiles [128 x 64] SW128
   uint64_t* bars = reinterpret_cast<uint64_t*>(wh_smem + (size_t)KBh * W_TILE_BYTES);
   const uint32_t bar_wf = smem_u32(bars + 0);
-  const uint32_t bar_accf = smem_u32(bars + 1);
-  const uint32_t bar_hr = smem_u32(bars + 2);      // [2]
-  const uint32_t bar_sl = smem_u32(bars + 4);      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const uint32_t bar_accf = smem_u32(bars + 1);    // [2 accumulators]
+  const uint32_t bar_hr = smem_u32(bars + 3);      // [2 tiles][2 passes]: all CL sub-slices of that pass have landed
+  const uint32_t bar_sl = smem_u32(bars + 7);      // [2 tiles][2 passes]: own sub-slice written by the 8 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_wf, 1);
-    mbar_init(bar_accf, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_hr + 8 * b, 2); mbar_init(bar_sl + 8 * b, 8); }
+    for (int b = 0; b < 2; ++b) mbar_init(bar_accf + 8 * b, 1);
+    for (int b = 0; b < 4; ++b) { mbar_init(bar_hr + 8 * b, 2); mbar_init(bar_sl + 8 * b, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -559,105 +585,119 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
     }
     __syncwarp();
     const uint32_t idesc = make_idesc_f16(128, 128);
-    const uint64_t whd = make_sw128_desc(smem_u32(wh_smem)), hd = make_sw64_desc(smem_u32(h_smem));
+    const uint64_t whd = make_sw128_desc(smem_u32(wh_smem)), hd = make_sw32_desc(smem_u32(h_smem));
     const uint32_t wh_lo = (uint32_t)whd, wh_hi = (uint32_t)(whd >> 32), h_lo0 = (uint32_t)hd, h_hi = (uint32_t)(hd >> 32);
     long long w_hr = 0, t_begin = clock64();
     mbar_wait<false>(bar_wf, 0);
     for (int s = has_init ? 0 : 1; s < nsteps; ++s) {
       const int hb = (s - 1) & 1;
       const uint32_t n = s == 0 ? 0u : (uint32_t)(((s - 1) >> 1) + ((hb == 1 && has_init) ? 1 : 0));
-      if (elect_one_sync()) {
-        if (s == 0) mbar_arrive(bar_hr + 8 * hb);
-        else mbar_expect_tx(bar_hr + 8 * hb, (uint32_t)(CL - 1) * P2_SLICE_BYTES);
+      const uint32_t d = tmem_base + (uint32_t)((s & 1) * 128);
+      const uint32_t h_lo = h_lo0 + (uint32_t)(hb * 2 * CL * (P2_SUB_BYTES >> 4));
+      for (int p = 0; p < 2; ++p) {
+        // pass-p sub-slices of h_{s-1}: the k-steps m = 2 q + p can start while the peers still compute / send pass 1
+        const uint32_t bar = bar_hr + 8 * (hb * 2 + p);
+        if (elect_one_sync()) {
+          if (s == 0) mbar_arrive(bar);
+          else mbar_expect_tx(bar, (uint32_t)(CL - 1) * P2_SUB_BYTES);
+        }
+        __syncwarp();
+        mbar_wait_timed<false>(bar, n & 1, w_hr);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          for (int q = 0; q < CL; ++q) {
+            const int m = 2 * q + p;
+            tc_mma_ss3(d, h_lo + (uint32_t)(m * (P2_SUB_BYTES >> 4)), h_hi, wh_lo + (uint32_t)((m >> 2) * (W_TILE_BYTES >> 4) + 2 * (m & 3)), wh_hi, idesc,
+                       (p | q) ? 1u : 0u);
+          }
+          if (p == 1) tc_commit(bar_accf + 8 * (s & 1));
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait_timed<false>(bar_hr + 8 * hb, n & 1, w_hr);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint32_t h_lo = h_lo0 + (uint32_t)(hb * CL * (P2_SLICE_BYTES >> 4));
-        for (int m = 0; m < 2 * CL; ++m)
-          tc_mma_ss3(tmem_base, h_lo + (uint32_t)((m >> 1) * (P2_SLICE_BYTES >> 4) + 2 * (m & 1)), h_hi,
-                     wh_lo + (uint32_t)((m >> 2) * (W_TILE_BYTES >> 4) + 2 * (m & 3)), wh_hi, idesc, m ? 1u : 0u);
-        tc_commit(bar_accf);
-      }
-      __syncwarp();
     }
     if (P.dbg && lane == 0) { P.dbg[blockIdx.x * 16 + 0] = w_hr; P.dbg[blockIdx.x * 16 + 3] = clock64() - t_begin; }
   } else if (warp == 9) {
-    // ===== slice exchange =====
+    // ===== sub-slice exchange =====
     const uint32_t peer_h = map_to_cta(smem_u32(h_smem), (uint32_t)(lane < CL ? lane : 0));
     const uint32_t peer_bar = map_to_cta(bar_hr, (uint32_t)(lane < CL ? lane : 0));
     if (has_init) {
-      mbar_wait<false>(bar_sl + 8, 0);
-      if (lane == 0) mbar_arrive(bar_hr + 8);
+      for (int p = 0; p < 2; ++p) {
+        mbar_wait<false>(bar_sl + 8 * (2 + p), 0);
+        if (lane == 0) mbar_arrive(bar_hr + 8 * (2 + p));
+      }
     }
     for (int s = 0; s + 1 < nsteps; ++s) {
       const int tb = s & 1;
       const uint32_t n = (uint32_t)((s >> 1) + ((tb == 1 && has_init) ? 1 : 0));
-      mbar_wait<false>(bar_sl + 8 * tb, n & 1);
-      const uint32_t off = (uint32_t)(tb * CL * P2_SLICE_BYTES) + rank * P2_SLICE_BYTES;
-      if (lane < CL && lane != (int)rank) bulk_copy_to_peer(peer_h + off, smem_u32(h_smem) + off, P2_SLICE_BYTES, peer_bar + 8 * tb);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_hr + 8 * tb);
+      for (int p = 0; p < 2; ++p) {
+        mbar_wait<false>(bar_sl + 8 * (tb * 2 + p), n & 1);
+        const uint32_t off = (uint32_t)((tb * 2 * CL + 2 * (int)rank + p) * P2_SUB_BYTES);
+        if (lane < CL && lane != (int)rank) bulk_copy_to_peer(peer_h + off, smem_u32(h_smem) + off, P2_SUB_BYTES, peer_bar + 8 * (tb * 2 + p));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_hr + 8 * (tb * 2 + p));
+      }
     }
   } else {
-    // ===== epilogue: thread == (batch row, 16 of this CTA's 32 hidden units), c in registers =====
+    // ===== epilogue: thread == (batch row, 16 of this CTA's 32 hidden units), c in registers.
+    //       pass p of unit-half `half` covers units 16 p + 8 half + [0, 8) of the slice, so that the two halves of
+    //       pass p together complete sub-slice 2 rank + p, which leaves for the peers while pass 1 is still computing
     const int quarter = warp & 3, half = warp >> 2;
     const int r = quarter * 32 + lane;
     const int grow = row0 + r;
     const bool valid = grow < P.B;
     const int32_t* trow = P.tokens + (size_t)min(grow, P.B - 1) * P.T + t0;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int ub = half * 16;
-    const uint32_t row_off64 = (uint32_t)(r * 64);
-    const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
+    const uint32_t row_off32 = (uint32_t)(r * 32);
+    const uint32_t sw32 = (uint32_t)((r >> 2) & 1);            // SWIZZLE_32B: 16-byte chunk c of row r sits at c ^ ((r >> 2) & 1)
     float c[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) c[u] = has_init ? __ldg(P.init_c + rank * 32 + ub + u) : 0.f;
+    for (int u = 0; u < 16; ++u) c[u] = has_init ? __ldg(P.init_c + rank * 32 + (u >> 3) * 16 + half * 8 + (u & 7)) : 0.f;
     if (has_init) {
-      const uint32_t t1 = smem_u32(h_smem) + (uint32_t)(CL * P2_SLICE_BYTES) + row_off64;
-      for (int q = half; q < CL; q += 2)
-        for (int j = 0; j < 4; ++j) {
+      // the broadcast initial state is the same for every row: each CTA fills its own tile 1 (= "step -1"), all sub-slices
+      const uint32_t t1 = smem_u32(h_smem) + (uint32_t)(2 * CL * P2_SUB_BYTES) + row_off32;
+      for (int m = half; m < 2 * CL; m += 2)
+        for (int j = 0; j < 2; ++j) {
           uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(P.init_h + q * 32 + j * 8 + 2 * e), __ldg(P.init_h + q * 32 + j * 8 + 2 * e + 1));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t1 + (uint32_t)q * P2_SLICE_BYTES + (((uint32_t)j ^ sw64) * 16)),
+          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(P.init_h + m * 16 + j * 8 + 2 * e), __ldg(P.init_h + m * 16 + j * 8 + 2 * e + 1));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t1 + (uint32_t)m * P2_SUB_BYTES + (((uint32_t)j ^ sw32) * 16)),
                        "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sl + 8);
+      if (lane == 0) { mbar_arrive(bar_sl + 8 * 2); mbar_arrive(bar_sl + 8 * 3); }
     }
-    const uint32_t own_slice = smem_u32(h_smem) + rank * P2_SLICE_BYTES + row_off64;
-    const size_t pcol = (size_t)rank * 128 + ub;
+    const uint32_t own_sub = smem_u32(h_smem) + (2 * rank) * P2_SUB_BYTES + row_off32 + (((uint32_t)half ^ sw32) * 16);
+    const size_t pcol = (size_t)rank * 128 + half * 8;
     constexpr float NL2E = -1.4426950408889634f;
     long long w_accf = 0, w_math = 0, tq = 0, t_begin = clock64();
     const bool dbgt = P.dbg != nullptr;
-    int tok = __ldg(trow);
-    uint32_t accf_uses = 0;
+    // table row of step s: pg[g][p * 8 + i] = P[token][gate g, unit 16 p + 8 half + i].  The pass-1 half of step s is
+    // fetched at the start of pass 0 of step s, the pass-0 half of step s + 1 at the start of pass 1 of step s: each
+    // half lands in registers that are dead at that point, and the gathers trickle into the load/store unit under the
+    // MUFU work instead of queueing up in front of it.
+    float pg[4][16];
+    int tok_cur = __ldg(trow);
+    int tok_next = nsteps > 1 ? __ldg(trow + 1) : 0;
+    {
+      const float* prow = P.ptable + (size_t)tok_cur * 4 * P.H + pcol;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) ldg_v8(prow + g * 32, pg[g]);
+    }
     for (int s = 0; s < nsteps; ++s) {
       const bool last = s == nsteps - 1;
       const bool has_state = s > 0 || has_init;
-      // this step's table row: 4 gates x 16 units (issued before the accumulator wait -- the loads fly during the MMAs)
-      const float4* prow = reinterpret_cast<const float4*>(P.ptable + (size_t)tok * 4 * P.H + pcol);
-      float4 pv[4][4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) pv[g][q] = __ldg(prow + g * 8 + q);
-      if (!last) tok = __ldg(trow + s + 1);
       if (has_state) {
-        mbar_wait_timed<false>(bar_accf, accf_uses & 1, w_accf);
-        ++accf_uses;
+        mbar_wait_timed<false>(bar_accf + 8 * (s & 1), (uint32_t)(((s - (has_init ? 0 : 1)) >> 1) & 1), w_accf);
         tc_fence_after();
       }
       if (dbgt) tq = clock64();
-      const uint32_t tile_own = own_slice + (uint32_t)((s & 1) * CL * P2_SLICE_BYTES);
+      const uint32_t tile_sub = own_sub + (uint32_t)((s & 1) * 2 * CL * P2_SUB_BYTES);
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         uint32_t vi[8], vj[8], vf[8], vo[8];
         if (has_state) {
-          const uint32_t acc = lane_base + (uint32_t)(ub + p * 8);
+          const uint32_t acc = lane_base + (uint32_t)((s & 1) * 128 + p * 16 + half * 8);
           TMEM_LD_8(acc, vi);
           TMEM_LD_8(acc + 32, vj);
           TMEM_LD_8(acc + 64, vf);
@@ -667,15 +707,30 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
 #pragma unroll
           for (int i = 0; i < 8; ++i) vi[i] = vj[i] = vf[i] = vo[i] = 0u;
         }
+        if (p == 0) {
+          const float* prow = P.ptable + (size_t)tok_cur * 4 * P.H + pcol + 16;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) ldg_v8(prow + g * 32, pg[g] + 8);
+        } else if (!last) {
+          const float* prow = P.ptable + (size_t)tok_next * 4 * P.H + pcol;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) ldg_v8(prow + g * 32, pg[g]);
+        }
         float hv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int u = p * 8 + i;
-          const float4 qi = pv[0][p * 2 + (i >> 2)], qj = pv[1][p * 2 + (i >> 2)], qf = pv[2][p * 2 + (i >> 2)], qo = pv[3][p * 2 + (i >> 2)];
-          const float bi = (i & 3) == 0 ? qi.x : (i & 3) == 1 ? qi.y : (i & 3) == 2 ? qi.z : qi.w;
-          const float bj = (i & 3) == 0 ? qj.x : (i & 3) == 1 ? qj.y : (i & 3) == 2 ? qj.z : qj.w;
-          const float bf = (i & 3) == 0 ? qf.x : (i & 3) == 1 ? qf.y : (i & 3) == 2 ? qf.z : qf.w;
-          const float bo = (i & 3) == 0 ? qo.x : (i & 3) == 1 ? qo.y : (i & 3) == 2 ? qo.z : qo.w;
+          const float bi = pg[0][u], bj = pg[1][u], bf = pg[2][u], bo = pg[3][u];
+          if (P.gate_math == 1) {
+            // table scaled by 1/2 (1 for the candidate gate): sigmoid(z) = 0.5 tanh(z / 2) + 0.5
+            const float ti = tanh_approx(fmaf(__uint_as_float(vi[i]), 0.5f, bi));
+            const float tj = tanh_approx(__uint_as_float(vj[i]) + bj);
+            const float tf = tanh_approx(fmaf(__uint_as_float(vf[i]), 0.5f, bf));
+            const float to = tanh_approx(fmaf(__uint_as_float(vo[i]), 0.5f, bo));
+            c[u] = fmaf(c[u], fmaf(0.5f, tf, 0.5f), fmaf(0.5f, ti, 0.5f) * tj);
+            hv[i] = fmaf(0.5f, to, 0.5f) * tanh_approx(c[u]);
+            continue;
+          }
           const float ei = ex2_approx(fminf(fmaf(__uint_as_float(vi[i]), NL2E, bi), 57.f));
           const float ej = ex2_approx(fminf(fmaf(__uint_as_float(vj[i]), 2.f * NL2E, bj), 57.f));
           const float ef = ex2_approx(fminf(fmaf(__uint_as_float(vf[i]), NL2E, bf), 57.f));
@@ -687,21 +742,20 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
         }
         if (!last) {
           const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]), p2 = pack_f16x2(hv[4], hv[5]), p3 = pack_f16x2(hv[6], hv[7]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_own + ((((uint32_t)(half * 2 + p)) ^ sw64) * 16)),
-                       "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_sub + (uint32_t)(p * P2_SUB_BYTES)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+          // this pass's half sub-slice is in place (and, for p == 1, the accumulator fully read): publish it
+          if (p == 1) tc_fence_before();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sl + 8 * ((s & 1) * 2 + p));
         } else if (valid) {
-          float* ho = P.h_out + (size_t)grow * P.H + rank * 32 + ub + p * 8;
+          float* ho = P.h_out + (size_t)grow * P.H + rank * 32 + p * 16 + half * 8;
           *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
           *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
         }
       }
-      if (!last) {
-        // (the TMEM reads above are complete: wait::ld) -> own slice visible to the copy engine / tensor core
-        tc_fence_before();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_sl + 8 * (s & 1));
-      }
+      tok_cur = tok_next;
+      if (s + 2 < nsteps) tok_next = __ldg(trow + s + 2);
       if (dbgt) w_math += clock64() - tq;
     }
     if (P.dbg && lane == 0 && warp == 0) {
@@ -714,23 +768,29 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   cluster_sync_all();
   if (warp == 8) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
   }
 }
 
 // Wxp[k][n'] = scale_g * K[k][g*H + 32c + j]   (n' = c*128 + g*32 + j), k < We
-__global__ void ptable_wx_kernel(const float* __restrict__ K, int We, int H, float* __restrict__ Wxp) {
+__global__ void ptable_wx_kernel(const float* __restrict__ K, int We, int H, int gate_math, float* __restrict__ Wxp) {
   const int64_t total = (int64_t)We * 4 * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i / (4 * H)), np = (int)(i - (int64_t)k * 4 * H);
     const int c = np >> 7, g = (np >> 5) & 3, j = np & 31;
-    Wxp[i] = (g == 1 ? -2.885390081777927f : -1.4426950408889634f) * K[(size_t)k * 4 * H + g * H + c * 32 + j];
+    const float sc = gate_math == 1 ? (g == 1 ? 1.f : 0.5f) : (g == 1 ? -2.885390081777927f : -1.4426950408889634f);
+    Wxp[i] = sc * K[(size_t)k * 4 * H + g * H + c * 32 + j];
   }
 }
 // P[v][n'] = bias_r[n']  (the GEMM then accumulates the projection on top)
-__global__ void ptable_bias_kernel(const float* __restrict__ bias_r, int64_t V, int H4, float* __restrict__ Pt) {
+__global__ void ptable_bias_kernel(const float* __restrict__ bias_r, int64_t V, int H4, int gate_math, float* __restrict__ Pt) {
   const int64_t total = V * H4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) Pt[i] = bias_r[i % H4];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int np = (int)(i % H4);
+    float b = bias_r[np];                       // -log2e (-2 log2e for g == 1) x (b [+1 forget])
+    if (gate_math == 1) b *= -0.34657359027997264f;   // (-log2e)(b) -> b/2 for i,f,o and (-2 log2e)(b) -> b for j: the same factor -ln2/2
+    Pt[i] = b;
+  }
 }
 
 }  // namespace
@@ -806,9 +866,11 @@ int lstm_ptable_prepare(TcTower& tt, const float* emb, int64_t V, const float* K
   if (!tt.ptable) { SSE_CUDA_OK(cudaMalloc(&tt.ptable, (size_t)V * 4 * H * 4)); tt.ptable_rows = V; }
   if (!tt.wxp) SSE_CUDA_OK(cudaMalloc(&tt.wxp, (size_t)We * 4 * H * 4));
   float* wxp = tt.wxp;
-  ptable_wx_kernel<<<148, 256, 0, st>>>(K, We, H, wxp);
+  const int gate_math = getenv("SSE_LSTM_GATE_MATH") ? atoi(getenv("SSE_LSTM_GATE_MATH")) : 0;
+  tt.ptable_mode = gate_math;
+  ptable_wx_kernel<<<148, 256, 0, st>>>(K, We, H, gate_math, wxp);
   if (launches) ++*launches;
-  ptable_bias_kernel<<<148 * 8, 256, 0, st>>>(tt.bias_r, V, 4 * H, tt.ptable);
+  ptable_bias_kernel<<<148 * 8, 256, 0, st>>>(tt.bias_r, V, 4 * H, gate_math, tt.ptable);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
   // rows in slabs that keep the GEMM's M within int range and friendly to the SIMT kernel
@@ -827,10 +889,11 @@ int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We
   LstmP2Params p;
   p.tokens = tokens; p.ptable = tt.ptable; p.init_h = init_h; p.init_c = init_c; p.h_out = h_out;
   p.B = B; p.T = T; p.t_start = t_start; p.H = H; p.dbg = nullptr;
+  p.gate_math = tt.ptable_mode;
   const int CL = H / 32, KBh = H / KBLK;
   const int n_clusters = cdiv(B, P2_ROWS);
   const int grid = n_clusters * CL;
-  const size_t smem = 1024 + (size_t)2 * CL * P2_SLICE_BYTES + (size_t)KBh * W_TILE_BYTES + 256;
+  const size_t smem = 1024 + (size_t)2 * 2 * CL * P2_SUB_BYTES + (size_t)KBh * W_TILE_BYTES + 256;
   const bool want_dbg = getenv("SSE_LSTM_DEBUG") != nullptr;
   long long* d_dbg = nullptr;
   if (want_dbg) { cudaMalloc(&d_dbg, (size_t)grid * 128); cudaMemset(d_dbg, 0, (size_t)grid * 128); p.dbg = d_dbg; }

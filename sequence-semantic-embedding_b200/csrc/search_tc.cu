@@ -892,7 +892,11 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   const int gstride = mtg * TILE_M;                 // padded rows per group
   const int rpg = cdiv(Q, n_groups);                // query rows per group (equal for all groups)
   const int n_tiles = (int)cdiv64(N, tn);
-  int n_s = (int)(N / 16 / tn);
+  // sample = every 16th tile: tau = k-th largest sampled tile maximum - 2 eps keeps ~16 k candidates per query
+  // (measured: 1/32 and 1/64 samples cost more in candidate handling than they save in the sample pass); rows whose
+  // sampled threshold is loose tighten it inside the scan (compact_candidates)
+  static const int sample_div = getenv("SSE_SCAN_SAMPLE_DIV") ? std::max(1, atoi(getenv("SSE_SCAN_SAMPLE_DIV"))) : 16;
+  int n_s = (int)(N / sample_div / tn);
   if (n_s < 64) n_s = 64;
   if (n_s > 1024) n_s = 1024;
   if (n_s > n_tiles) n_s = n_tiles;

@@ -127,6 +127,7 @@ struct TcTower {
   int64_t ptable_rows = 0;
   float* wxp = nullptr;            // [We, 4H] permuted + scaled W_x (GEMM operand of the table build)
   bool ptable_valid = false;
+  int ptable_mode = 0;             // gate-math variant the table was scaled for
 };
 bool lstm_tc_supported(int We, int H);
 int lstm_tc_prepare(TcTower& tt, const float* K, const float* b, int We, int H, cudaStream_t st, int64_t* launches);
