@@ -1,12 +1,12 @@
-# final evidence for one GPU: tests, bench, ncu launch list, ncu --set full of the two dominant kernels
+# final evidence for one GPU: tests, bench, reference arm, ncu launch list, ncu --set full of the dominant kernels
 set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
+timeout 900 python bench.py --steps 20 --warmup 3 --no-pipeline --no-cpu-baseline --train-steps 0 > gpurun_out/bench_n1_nopipe.json 2> gpurun_out/bench_n1_nopipe.err; tail -c 300 gpurun_out/bench_n1_nopipe.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>&1; tail -c 700 gpurun_out/bench_ref.json
-timeout 600 python bench.py --steps 10 --warmup 3 --targets 100000 --no-cpu-baseline --train-steps 0 > gpurun_out/bench_n1_100k.json 2>&1; tail -c 400 gpurun_out/bench_n1_100k.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --train-steps 0 > gpurun_out/ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 4 -c 2 -o gpurun_out/prof_scan python bench.py --steps 2 --warmup 3 --no-cpu-baseline --train-steps 0 > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc_kernel -s 2 -c 1 -o gpurun_out/prof_lstm_tc python bench.py --steps 2 --warmup 3 --no-cpu-baseline --train-steps 0 > gpurun_out/ncu_full2.log 2>&1; tail -1 gpurun_out/ncu_full2.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none -k regex:lstm_tc_kernel -s 1 -c 1 -o gpurun_out/prof_lstm_tc_fullwave python scripts/lstm_debug.py > gpurun_out/ncu_full3.log 2>&1; tail -2 gpurun_out/ncu_full3.log | cut -c1-200
-ls -la gpurun_out | head -30
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-pipeline --no-cpu-baseline --train-steps 0 > gpurun_out/ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 4 -c 2 -o gpurun_out/prof_scan python bench.py --steps 2 --warmup 3 --no-pipeline --no-cpu-baseline --train-steps 0 > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_ptable_kernel -s 2 -c 1 -o gpurun_out/prof_lstm python bench.py --steps 2 --warmup 3 --no-pipeline --no-cpu-baseline --train-steps 0 > gpurun_out/ncu_full2.log 2>&1; tail -1 gpurun_out/ncu_full2.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none -k regex:lstm_tc_kernel -s 1 -c 1 -o gpurun_out/prof_lstm_tc_fullwave python scripts/lstm_debug.py 18944 > gpurun_out/ncu_full3.log 2>&1; tail -2 gpurun_out/ncu_full3.log | cut -c1-200
+ls -la gpurun_out | head -40

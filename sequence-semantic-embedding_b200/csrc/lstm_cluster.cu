@@ -672,17 +672,16 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
     constexpr float NL2E = -1.4426950408889634f;
     long long w_accf = 0, w_math = 0, tq = 0, t_begin = clock64();
     const bool dbgt = P.dbg != nullptr;
-    // table row of step s: pg[g][p * 8 + i] = P[token][gate g, unit 16 p + 8 half + i].  The pass-1 half of step s is
-    // fetched at the start of pass 0 of step s, the pass-0 half of step s + 1 at the start of pass 1 of step s: each
-    // half lands in registers that are dead at that point, and the gathers trickle into the load/store unit under the
-    // MUFU work instead of queueing up in front of it.
+    // table row of step s: pg[g][p * 8 + i] = P[token][gate g, unit 16 p + 8 half + i].  Each half of the NEXT step's
+    // row is fetched right after the corresponding pass of this step has been published: it lands in registers that
+    // just died, and no global load is in flight when the next publish executes its memory barrier
+    // (fence.proxy.async lowers to MEMBAR.ALL.CTA, which would otherwise wait out the L2 latency on the critical path).
     float pg[4][16];
-    int tok_cur = __ldg(trow);
     int tok_next = nsteps > 1 ? __ldg(trow + 1) : 0;
     {
-      const float* prow = P.ptable + (size_t)tok_cur * 4 * P.H + pcol;
+      const float* prow = P.ptable + (size_t)__ldg(trow) * 4 * P.H + pcol;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) ldg_v8(prow + g * 32, pg[g]);
+      for (int g = 0; g < 4; ++g) { ldg_v8(prow + g * 32, pg[g]); ldg_v8(prow + g * 32 + 16, pg[g] + 8); }
     }
     for (int s = 0; s < nsteps; ++s) {
       const bool last = s == nsteps - 1;
@@ -706,15 +705,6 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) vi[i] = vj[i] = vf[i] = vo[i] = 0u;
-        }
-        if (p == 0) {
-          const float* prow = P.ptable + (size_t)tok_cur * 4 * P.H + pcol + 16;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) ldg_v8(prow + g * 32, pg[g] + 8);
-        } else if (!last) {
-          const float* prow = P.ptable + (size_t)tok_next * 4 * P.H + pcol;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) ldg_v8(prow + g * 32, pg[g]);
         }
         float hv[8];
 #pragma unroll
@@ -748,13 +738,17 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_sl + 8 * ((s & 1) * 2 + p));
+          {
+            const float* prow = P.ptable + (size_t)tok_next * 4 * P.H + pcol + p * 16;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ldg_v8(prow + g * 32, pg[g] + p * 8);
+          }
         } else if (valid) {
           float* ho = P.h_out + (size_t)grow * P.H + rank * 32 + p * 16 + half * 8;
           *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
           *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
         }
       }
-      tok_cur = tok_next;
       if (s + 2 < nsteps) tok_next = __ldg(trow + s + 2);
       if (dbgt) w_math += clock64() - tq;
     }
