@@ -50,9 +50,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="run encode and search of a step back to back on one stream "
                     "(default: 2-stage software pipeline over steps: encoder of batch s+1 overlaps the scan of batch s)")
-    ap.add_argument("--search-ctas", type=int, default=108, help="scan grid cap when pipelining (rest of the SMs run the encoder)")
+    ap.add_argument("--search-ctas", type=int, default=-1, help="scan grid cap when pipelining (the remaining SMs run the encoder clusters); "
+                    "-1 = auto: 108 (= 148 - 5 clusters x 8 CTAs) up to 4 GPUs, uncapped beyond (measured on the per-rank shapes), 0 = uncapped")
     ap.add_argument("--train-steps", type=int, default=5, help="timed train steps for the secondary train-step/s figure (0 = skip)")
     ap.add_argument("--train-rows", type=int, default=1024, help="pair rows per GPU per train step (512 pos + 512 neg, data.py:95-115 layout)")
+    ap.add_argument("--emulate-world", type=int, default=0, help="development aid: run ONE rank's share of a G-GPU step on one GPU "
+                    "(600 encodes, G*600 x N/G scan, merge of G*k candidates; collectives replaced by local copies); the line is marked emulated")
     ap.add_argument("--cpu-sample-targets", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=64)
     return ap.parse_args()
@@ -68,45 +71,86 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed regions: NVML polled every ~2 ms from a thread (started
+    before the first timed region, stopped after the last); falls back to `nvidia-smi -lms` if NVML is unavailable."""
 
-    def __init__(self, index=0):
-        self.rows = []
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, index=0, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.sm, self.mx, self.reasons = [], 0, set()
+        self.stop_flag = False
+        self.thread = None
         self.proc = None
-        self.index = index
+        self.source = None
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for name, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = None
+            if self.uuid:
+                for cand in ("GPU-" + str(self.uuid), str(self.uuid)):
+                    try:
+                        handle = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        handle = None
+            if handle is None:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _smi_loop(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 6:
                 continue
             try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+                self.sm.append(float(f[0])); self.mx = max(self.mx, float(f[1]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx or None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def synth_tokens(rng, B):
@@ -154,8 +198,10 @@ def run_b200(args):
     # rank), every rank scans its shard for all of them, and one NCCL all-gather of the packed per-shard top-k is
     # followed by the merge kernel.  Per-GPU work (600 encodes, G*600 x N/G scan) is constant in G -> weak scaling;
     # value = G*600*steps / time.
-    Q, k = args.queries * world, K_TOP
-    n_local = args.targets // world
+    emu = args.emulate_world if world == 1 and args.emulate_world > 1 else 0
+    G = emu or world                             # ranks whose queries this rank scans for
+    Q, k = args.queries * G, K_TOP
+    n_local = args.targets // G
     h = sse_ffi.Handle("dual-encoder", V, WE, E, H, H, T, predict_nbest=k, device=local, precision=sse_ffi.PRECISION_TC)
     h.set_params(init_weights())
     h.set_option("search", args.search)
@@ -176,11 +222,13 @@ def run_b200(args):
     sc = torch.empty(Q, k, device="cuda")
     ix = torch.empty(Q, k, device="cuda", dtype=torch.int32)
     packed = torch.empty(Q, 2 * k, device="cuda")
-    gathered = torch.empty(world * Q, 2 * k, device="cuda") if world > 1 else None
+    gathered = torch.empty(G * Q, 2 * k, device="cuda") if G > 1 else None
     fs = torch.empty(Q, k, device="cuda")
     fi = torch.empty(Q, k, device="cuda", dtype=torch.int32)
-    out_s_host = torch.empty(Q, k).pin_memory()
-    out_i_host = torch.empty(Q, k, dtype=torch.int32).pin_memory()
+    out_s_host2 = [torch.empty(Q, k).pin_memory() for _ in range(2)]
+    out_i_host2 = [torch.empty(Q, k, dtype=torch.int32).pin_memory() for _ in range(2)]
+    e2e_done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"n": 0}
     stream = torch.cuda.current_stream()
 
     pipeline = not args.no_pipeline
@@ -189,17 +237,22 @@ def run_b200(args):
     enc_ready = [torch.cuda.Event(), torch.cuda.Event()]
     enc_free = [torch.cuda.Event(), torch.cuda.Event()]
     state = {"primed": False, "n": 0}
+    if args.search_ctas < 0:
+        args.search_ctas = 108 if G <= 4 else 0
     if pipeline:
         h.set_option("search_ctas", args.search_ctas)
 
     def encode_all(b, out, scratch, st):
         """this rank's 600 queries through the source encoder; N > 1: all-gather of the [600, E] encodings so that
         every rank holds the step's G x 600 query vectors for its index shard"""
-        if world == 1:
+        if G == 1:
             h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Ql, out, True, st)
         else:
             h.encode(sse_ffi.SIDE_SRC, tok_dev[b], Ql, scratch, True, st)
-            dist.all_gather_into_tensor(out, scratch)
+            if emu:
+                out.view(G, Ql, E).copy_(scratch.unsqueeze(0).expand(G, Ql, E))
+            else:
+                dist.all_gather_into_tensor(out, scratch)
 
     def issue_encode(b, slot):
         with torch.cuda.stream(enc_stream):
@@ -226,14 +279,17 @@ def run_b200(args):
         else:
             encode_all(b, enc, enc_local[0], stream)
             h.search(enc, Q, k, sc, ix, stream)
-        if world > 1:
+        if G > 1:
             packed[:, :k] = sc
             packed[:, k:] = ix.view(torch.float32)
-            dist.all_gather_into_tensor(gathered, packed)
-            g3 = gathered.view(world, Q, 2 * k)
-            cs = g3[:, :, :k].permute(1, 0, 2).reshape(Q, world * k).contiguous()
-            ci = g3[:, :, k:].permute(1, 0, 2).reshape(Q, world * k).contiguous().view(torch.int32)
-            h.merge_topk(cs, ci, Q, world * k, k, fs, fi, stream)
+            if emu:
+                gathered.view(G, Q, 2 * k).copy_(packed.unsqueeze(0).expand(G, Q, 2 * k))
+            else:
+                dist.all_gather_into_tensor(gathered, packed)
+            g3 = gathered.view(G, Q, 2 * k)
+            cs = g3[:, :, :k].permute(1, 0, 2).reshape(Q, G * k).contiguous()
+            ci = g3[:, :, k:].permute(1, 0, 2).reshape(Q, G * k).contiguous().view(torch.int32)
+            h.merge_topk(cs, ci, Q, G * k, k, fs, fi, stream)
 
     def step_e2e(b):
         if pipeline:
@@ -242,10 +298,19 @@ def run_b200(args):
         else:
             tok_dev[b].copy_(tok_host[b], non_blocking=True)           # H2D of the step's inputs
         step_device(b)
-        src_s, src_i = (fs, fi) if world > 1 else (sc, ix)
-        out_s_host.copy_(src_s, non_blocking=True)                     # D2H of the step's result
-        out_i_host.copy_(src_i, non_blocking=True)
-        stream.synchronize()
+        src_s, src_i = (fs, fi) if G > 1 else (sc, ix)
+        n = e2e_state["n"]
+        out_s_host2[n & 1].copy_(src_s, non_blocking=True)             # D2H of the step's result
+        out_i_host2[n & 1].copy_(src_i, non_blocking=True)
+        if pipeline:
+            # the host consumes step s-1's result while step s runs (every step's result is still read on the host:
+            # double-buffered pinned outputs; the last one is awaited by the closing barrier)
+            e2e_done[n & 1].record(stream)
+            if n > 0:
+                e2e_done[(n - 1) & 1].synchronize()
+        else:
+            stream.synchronize()
+        e2e_state["n"] = n + 1
 
     def barrier():
         if world > 1:
@@ -253,6 +318,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         state["primed"] = False
         state["n"] = 0
+        e2e_state["n"] = 0
 
     def timed(fn, steps, warmup):
         for w in range(warmup):
@@ -271,7 +337,11 @@ def run_b200(args):
             ms = float(t.item())
         return ms
 
-    sampler = ClockSampler(local)
+    try:
+        dev_uuid = torch.cuda.get_device_properties(local).uuid
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local, dev_uuid)
     if rank == 0:
         sampler.start()
     l0 = h.launch_count()
@@ -374,6 +444,7 @@ def run_b200(args):
 
     total_q = Q * args.steps
     out = {
+        **({"emulated": "one rank's share of a %d-GPU step on one GPU; collectives replaced by local copies -- NOT a multi-GPU result" % emu} if emu else {}),
         "metric": "queries/sec encode+cosine-top-k", "value": total_q / (ms_dev * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05 scan + LSTM), exact f32 re-rank of the top-k" if use_tc else "f32",
@@ -385,7 +456,7 @@ def run_b200(args):
                    "parallelism": ("index row-shard x%d, %d queries/step: each rank encodes its 600, NCCL all-gather of the [600,E] encodings, "
                                    "every rank scans its shard for all %d, NCCL all-gather of the per-shard [Q,k] + merge" % (world, Q, Q)) if world > 1 else "single GPU",
                    "pipeline": ("2-stage over steps: encoder of batch s+1 (its own stream, %d SMs left free by the scan grid cap %d) overlaps the scan of batch s"
-                                % (148 - args.search_ctas, args.search_ctas)) if pipeline else "none (encode then scan on one stream)",
+                                % (148 - (args.search_ctas or 148), args.search_ctas or 148)) if pipeline else "none (encode then scan on one stream)",
                    "l2": "index shard (%.0f MB) is re-streamed every step and exceeds L2 (126 MB); query batches rotate" %
                          (bytes_alg / 1e6)},
         "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Ql * T * 4,
