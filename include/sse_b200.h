@@ -189,6 +189,22 @@ int64_t sse_launch_count(sse_handle* h);
 int sse_set_option(sse_handle* h, const char* key, int value);
 /* names + durations of the last timed kernels are not kept here: time with CUDA events on `stream`. */
 
+/* ---- targetEncodingIndex.tsv fast writer / reader (host only) -------------------------------
+ * Replaces the python loops of reference sse_index.py:93-97 (writer: id \t text \t ','.join(str(np.float32)))
+ * and sse_evaluator.py:79-88 (reader: line.strip().split('\t'), rows without three fields are skipped).
+ * Formatting is numpy's str(np.float32) byte for byte; parsing is correctly rounded, so a written index reads
+ * back bit-exactly.  Rows are split over `threads` host threads (<= 0: all hardware threads). */
+const char* sse_tsv_last_error(void);
+/* n floats -> their decimal strings packed back to back (no separators); ends[i] = end offset of value i. */
+int sse_tsv_format_f32(const float* values, int64_t n, char* out, size_t cap, int64_t* ends);
+int sse_tsv_write_index(const char* path, const char* const* ids, const char* const* texts, const float* rows,
+                        int64_t n_rows, int E, int append, int threads);
+/* buf = whole file contents.  out: [max_rows, E]; spans: [max_rows, 4] byte offsets (id_begin, id_end, text_begin,
+ * text_end) of every accepted row, in file order; n_skipped counts rows rejected by the three-field rule.  A row
+ * with three fields whose vector does not hold exactly E floats is an error (the reference raises there). */
+int sse_tsv_parse_index(const char* buf, size_t len, int E, int64_t max_rows, float* out, int64_t* spans,
+                        int64_t* n_rows, int64_t* n_skipped, int threads);
+
 #ifdef __cplusplus
 }
 #endif

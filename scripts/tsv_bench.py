@@ -1,0 +1,24 @@
+"""Index-file I/O measurement (host only): native writer / reader (csrc/tsv_io.cpp) next to the reference's python loops
+(restated in oracle/sse_oracle.py: format_index_row / parse_index_lines).  usage: tsv_bench.py [rows] [E]"""
+import json, os, sys, time
+import numpy as np
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "sequence-semantic-embedding_b200")); sys.path.insert(0, os.path.join(REPO, "oracle"))
+import sse_ffi, sse_oracle as O
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+E = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+rng = np.random.default_rng(0)
+enc = rng.standard_normal((N, E)).astype(np.float32); enc /= np.linalg.norm(enc, axis=1, keepdims=True)
+ids = ["id%d" % i for i in range(N)]; texts = ["target text number %d" % i for i in range(N)]
+p = ("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp") + "/sse_idx_bench.tsv"
+t = time.perf_counter(); sse_ffi.tsv_write_index(p, ids, texts, enc); tw = time.perf_counter() - t
+t = time.perf_counter(); gi, gt, ge, _ = sse_ffi.tsv_read_index(p); tr = time.perf_counter() - t
+assert np.array_equal(ge.view(np.uint32), enc.view(np.uint32)) and gi == ids
+n2 = min(N, 5000)
+t = time.perf_counter(); s = "".join(O.format_index_row(i, tx, r) for i, tx, r in zip(ids[:n2], texts[:n2], enc[:n2])); tpw = time.perf_counter() - t
+lines = s.splitlines(True)
+t = time.perf_counter(); O.parse_index_lines(lines); tpr = time.perf_counter() - t
+print(json.dumps({"rows": N, "E": E, "file_MB": os.path.getsize(p) / 1e6, "host_threads": os.cpu_count(),
+                  "native_write_rows_per_s": N / tw, "native_read_rows_per_s": N / tr,
+                  "python_write_rows_per_s": n2 / tpw, "python_read_rows_per_s": n2 / tpr, "round_trip": "bit-exact"}))
+os.remove(p)

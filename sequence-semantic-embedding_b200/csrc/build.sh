@@ -15,6 +15,11 @@ for s in $SRCS; do
     pids+=($!)
   fi
 done
+CXX=${CXX:-g++}
+if [ ! -f build/tsv_io.o ] || [ tsv_io.cpp -nt build/tsv_io.o ] || [ ../../include/sse_b200.h -nt build/tsv_io.o ]; then
+  ( $CXX -O3 -std=c++17 -fPIC -fvisibility=default -c tsv_io.cpp -o build/tsv_io.o > build/tsv_io.log 2>&1 || { cat build/tsv_io.log; exit 1; } ) &
+  pids+=($!)
+fi
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT $(for s in $SRCS; do echo build/${s%.cu}.o; done) -lcudart_static -ldl -lpthread -lrt
+$NVCC -shared -o $OUT $(for s in $SRCS; do echo build/${s%.cu}.o; done) build/tsv_io.o -lcudart_static -ldl -lpthread -lrt
 echo "built $OUT"

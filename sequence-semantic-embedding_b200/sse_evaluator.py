@@ -23,22 +23,15 @@ class Evaluator(object):
         self.model = model
         self.srcSeq_batch = [entry[0] for entry in eval_corpus]
         self.session = session
-        self.targetIDs, encs = [], []
-        self.idLabelMap = {}
-        idx = 0
-        for line in codecs.open(tgtIndexFile, "r", "utf-8").readlines():
-            info = line.strip().split("\t")
-            if len(info) != 3:
-                print("Error in targetIndexFile! %s" % line)
-                continue
-            tgtid, _tgtseq, tgtEncoding = info
-            self.targetIDs.append(tgtid)
-            encs.append(np.array(tgtEncoding.strip().split(","), dtype=np.float64))
-            self.idLabelMap[tgtid] = idx
-            idx += 1
+        # reference sse_evaluator.py:79-88: strip, split on tabs, rows without three fields are reported and skipped.
+        # Parsed by the native reader (csrc/tsv_io.cpp): float32, bit-exact inverse of the writer.
+        self.targetIDs, _texts, enc32, skipped = sse_ffi.tsv_read_index(tgtIndexFile)
+        if skipped:
+            print("Error in targetIndexFile! %d malformed line(s) skipped" % skipped)
+        self.idLabelMap = {tgtid: idx for idx, tgtid in enumerate(self.targetIDs)}
         self.eval_Labels = [[self.idLabelMap[tgtid] for tgtid in entry[1]] for entry in eval_corpus]
-        self.targetEncodings = np.array(encs)                       # float64 [N,E], as the reference keeps it
-        self.model.handle.index_set(self.targetEncodings.astype(np.float32), global_offset=0)
+        self.targetEncodings = enc32.astype(np.float64)             # float64 [N,E], the dtype the reference keeps
+        self.model.handle.index_set(enc32, global_offset=0)
 
     def eval(self, top_n=(1, 3, 10)):
         acc = [[] for _ in top_n]

@@ -87,6 +87,10 @@ _SIGNATURES = {
     "sse_set_scalars": (C.c_int, [_P, C.c_float, C.c_int64]),
     "sse_launch_count": (C.c_int64, [_P]),
     "sse_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "sse_tsv_last_error": (C.c_char_p, []),
+    "sse_tsv_format_f32": (C.c_int, [_P, C.c_int64, _P, C.c_size_t, _P]),
+    "sse_tsv_write_index": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _P, C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "sse_tsv_parse_index": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int64, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -339,3 +343,62 @@ class Handle:
 
     def set_option(self, key: str, value: int):
         self._check(self.lib.sse_set_option(self._h, key.encode(), int(value)))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# targetEncodingIndex.tsv fast writer / reader (host only: works without a GPU)
+def _tsv_check(rc):
+    if rc != SSE_OK:
+        raise SseError(load_library().sse_tsv_last_error().decode("utf-8", "replace"))
+
+
+def tsv_format_f32(values) -> List[str]:
+    """str(np.float32(v)) for every value, formatted by the native writer (test / small-scale helper)."""
+    lib = load_library()
+    v = np.ascontiguousarray(values, dtype=np.float32).ravel()
+    out = C.create_string_buffer(int(v.size) * 16 + 16)
+    ends = np.zeros(v.size, np.int64)
+    _tsv_check(lib.sse_tsv_format_f32(v.ctypes.data, v.size, C.addressof(out), len(out), ends.ctypes.data))
+    raw = out.raw
+    res, b = [], 0
+    for e in ends.tolist():
+        res.append(raw[b:e].decode("ascii")); b = e
+    return res
+
+
+def tsv_write_index(path: str, ids: Sequence[str], texts: Sequence[str], rows, append: bool = False, threads: int = 0) -> None:
+    """Write rows `id \\t text \\t comma-joined str(np.float32)` exactly as reference sse_index.py:93-97 does."""
+    lib = load_library()
+    r = np.ascontiguousarray(rows, dtype=np.float32)
+    n = len(ids)
+    if r.ndim != 2 or r.shape[0] != n or len(texts) != n:
+        raise ValueError("ids / texts / rows disagree: %d %d %s" % (n, len(texts), r.shape))
+    a_ids = (C.c_char_p * n)(*[s.encode("utf-8") for s in ids])
+    a_txt = (C.c_char_p * n)(*[s.encode("utf-8") for s in texts])
+    _tsv_check(lib.sse_tsv_write_index(path.encode("utf-8"), a_ids, a_txt, r.ctypes.data, n, r.shape[1], 1 if append else 0, threads))
+
+
+def tsv_read_index(path: str, threads: int = 0) -> Tuple[List[str], List[str], np.ndarray, int]:
+    """Parse an index file as reference sse_evaluator.py:79-88 does (strip, split on tabs, rows without three
+    fields are skipped).  Returns (ids, texts, float32 [N,E], n_skipped)."""
+    lib = load_library()
+    with open(path, "rb") as f:
+        buf = f.read()
+    E = 0
+    for line in buf.split(b"\n", 64)[:64]:                 # E from the first well-formed row
+        info = line.strip().split(b"\t")
+        if len(info) == 3:
+            E = info[2].count(b",") + 1
+            break
+    if E == 0:
+        return [], [], np.zeros((0, 0), np.float32), buf.count(b"\n")
+    max_rows = buf.count(b"\n") + 1
+    out = np.empty((max_rows, E), np.float32)
+    spans = np.empty((max_rows, 4), np.int64)
+    n, skipped = C.c_int64(0), C.c_int64(0)
+    _tsv_check(lib.sse_tsv_parse_index(buf, len(buf), E, max_rows, out.ctypes.data, spans.ctypes.data, C.byref(n), C.byref(skipped), threads))
+    n = n.value
+    sp = spans[:n].tolist()
+    ids = [buf[a:b].decode("utf-8") for a, b, _c, _d in sp]
+    texts = [buf[c:d].decode("utf-8") for _a, _b, c, d in sp]
+    return ids, texts, out[:n], skipped.value

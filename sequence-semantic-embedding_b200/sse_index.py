@@ -17,13 +17,14 @@ import numpy as np
 
 import data_utils
 import sse_model
+import sse_ffi
 import text_encoder
 
 
 def createIndexFile(model, encoder, rawfile, max_seq_len, encodeIndexFile, session, batchsize=10000):
     if not os.path.exists(rawfile):
         raise IOError("Error!! Could not find raw target file to be indexed!! :%s" % rawfile)
-    outFile = codecs.open(encodeIndexFile, "w", "utf-8")
+    codecs.open(encodeIndexFile, "w", "utf-8").close()          # truncate; batches are appended by the native writer
     rawdata = codecs.open(rawfile, "r", "utf-8").readlines()
     cnt = 0
     print("Start indexing whole target space entries with current model ...")
@@ -47,12 +48,10 @@ def createIndexFile(model, encoder, rawfile, max_seq_len, encodeIndexFile, sessi
             continue
         feed = model.get_target_encoding_feed_dict(tgtInputs)
         targetsEncodings = np.vstack(session.run([model.norm_tgt_seq_embedding], feed_dict=feed))
-        rows = []
-        for idx in range(len(tgtSentences)):
-            rows.append(tgtIds[idx] + "\t" + tgtSentences[idx] + "\t" + ",".join([str(n) for n in targetsEncodings[idx]]) + "\n")
-        outFile.write("".join(rows))
+        # same bytes as the reference loop (tgtId \t sentence \t ','.join(str(np.float32))), written by the native
+        # multi-threaded formatter (csrc/tsv_io.cpp; python: 5.6 k rows/s at E=256)
+        sse_ffi.tsv_write_index(encodeIndexFile, tgtIds, tgtSentences, targetsEncodings, append=True)
     print("Done of all indexing total count:%d" % cnt)
-    outFile.close()
 
 
 def index(model_dir, rawfile, encodeIndexFile, batchsize=10000):
