@@ -12,22 +12,17 @@ import sys
 import numpy as np
 
 import data_utils
+import sse_ffi
 import sse_model
 import text_encoder
 
 
 def load_index(path):
     """id, text, encoding rows of targetEncodingIndex.tsv (sse_demo.py:79-90)."""
-    ids, names, encs = [], {}, []
-    for line in codecs.open(path, "rt", "utf-8").readlines():
-        info = line.strip().split("\t")
-        if len(info) != 3:
-            print("Error in targetIndexFile! %s" % line)
-            continue
-        ids.append(info[0])
-        names[info[0]] = info[1]
-        encs.append(np.array(info[2].strip().split(","), dtype=np.float32))
-    return ids, names, np.array(encs, dtype=np.float32)
+    ids, texts, encs, skipped = sse_ffi.tsv_read_index(path)      # native reader (csrc/tsv_io.cpp), same row rules
+    if skipped:
+        print("Error in targetIndexFile! %d malformed line(s) skipped" % skipped)
+    return ids, dict(zip(ids, texts)), encs
 
 
 class DemoSession(object):
