@@ -205,6 +205,19 @@ int sse_tsv_write_index(const char* path, const char* const* ids, const char* co
 int sse_tsv_parse_index(const char* buf, size_t len, int E, int64_t max_rows, float* out, int64_t* spans,
                         int64_t* n_rows, int64_t* n_skipped, int threads);
 
+/* ---- batched subword tokenizer + padder (host only) ---------------------------------------------
+ * The ENCODE half of the reference's SubwordTextEncoder for a vocabulary.txt it wrote (text_encoder.py:334-356,
+ * 427-436, 491-532; tokenizer.py:68-90) plus the row rule of data_utils.py:149-155: n lower-cased utf-8 sentences
+ * -> int32 [n,T] rows ([PAD]*(T-len-1) + ids + [EOS], or [PAD] + ids[:T-2] + [EOS]); lengths[i] = subtokens before
+ * padding / truncation.  subtokens_utf8 = the vocabulary lines with their quotes removed, in file order. */
+typedef struct sse_tokenizer sse_tokenizer;
+const char* sse_tok_last_error(void);
+int sse_tok_create(const char* const* subtokens_utf8, int n_subtokens, sse_tokenizer** out);
+int sse_tok_destroy(sse_tokenizer* t);
+int sse_tok_vocab_size(const sse_tokenizer* t);
+int sse_tok_encode_batch(const sse_tokenizer* t, const char* const* texts_utf8, int64_t n, int T, int32_t* rows,
+                         int32_t* lengths, int threads);
+
 #ifdef __cplusplus
 }
 #endif

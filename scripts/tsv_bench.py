@@ -18,7 +18,16 @@ n2 = min(N, 5000)
 t = time.perf_counter(); s = "".join(O.format_index_row(i, tx, r) for i, tx, r in zip(ids[:n2], texts[:n2], enc[:n2])); tpw = time.perf_counter() - t
 lines = s.splitlines(True)
 t = time.perf_counter(); O.parse_index_lines(lines); tpr = time.perf_counter() - t
-print(json.dumps({"rows": N, "E": E, "file_MB": os.path.getsize(p) / 1e6, "host_threads": os.cpu_count(),
+# batched tokenizer + padder (csrc/subword_tok.cpp) vs the python encoder, product-title-like sentences
+import text_encoder
+enc_tok = text_encoder.SubwordTextEncoder(os.path.join(REPO, "tests", "golden", "subword_vocab.txt"))
+words = ["alpha", "beta", "gamma", "delta", "shoes", "women", "iphone", "case", "black", "2019", "new", "size", "xl", "usb-c", "naïve", "日本"]
+sent = [" ".join(rng.choice(words, size=int(rng.integers(3, 12)))) for _ in range(200000)]
+t = time.perf_counter(); rows_tok, _ = enc_tok.encode_batch(sent, 50); tt = time.perf_counter() - t
+t = time.perf_counter(); want = [text_encoder.pad_tokens(enc_tok.encode(x), 50) for x in sent[:5000]]; tp = time.perf_counter() - t
+assert rows_tok[:5000].tolist() == want
+tok = {"sentences": len(sent), "native_sentences_per_s": len(sent) / tt, "python_sentences_per_s": 5000 / tp}
+print(json.dumps({"tokenizer": tok, "rows": N, "E": E, "file_MB": os.path.getsize(p) / 1e6, "host_threads": os.cpu_count(),
                   "native_write_rows_per_s": N / tw, "native_read_rows_per_s": N / tr,
                   "python_write_rows_per_s": n2 / tpw, "python_read_rows_per_s": n2 / tpr, "round_trip": "bit-exact"}))
 os.remove(p)

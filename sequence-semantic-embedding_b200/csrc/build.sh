@@ -16,10 +16,14 @@ for s in $SRCS; do
   fi
 done
 CXX=${CXX:-g++}
-if [ ! -f build/tsv_io.o ] || [ tsv_io.cpp -nt build/tsv_io.o ] || [ ../../include/sse_b200.h -nt build/tsv_io.o ]; then
-  ( $CXX -O3 -std=c++17 -fPIC -fvisibility=default -c tsv_io.cpp -o build/tsv_io.o > build/tsv_io.log 2>&1 || { cat build/tsv_io.log; exit 1; } ) &
-  pids+=($!)
-fi
+HOST_SRCS="tsv_io.cpp subword_tok.cpp"
+for s in $HOST_SRCS; do
+  o=build/${s%.cpp}.o
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ ../../include/sse_b200.h -nt "$o" ] || [ unicode_alnum.inc -nt "$o" ]; then
+    ( $CXX -O3 -std=c++17 -fPIC -fvisibility=default -c "$s" -o "$o" > build/${s%.cpp}.log 2>&1 || { cat build/${s%.cpp}.log; exit 1; } ) &
+    pids+=($!)
+  fi
+done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT $(for s in $SRCS; do echo build/${s%.cu}.o; done) build/tsv_io.o -lcudart_static -ldl -lpthread -lrt
+$NVCC -shared -o $OUT $(for s in $SRCS; do echo build/${s%.cu}.o; done) $(for s in $HOST_SRCS; do echo build/${s%.cpp}.o; done) -lcudart_static -ldl -lpthread -lrt
 echo "built $OUT"

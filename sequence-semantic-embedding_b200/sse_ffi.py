@@ -91,6 +91,11 @@ _SIGNATURES = {
     "sse_tsv_format_f32": (C.c_int, [_P, C.c_int64, _P, C.c_size_t, _P]),
     "sse_tsv_write_index": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _P, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "sse_tsv_parse_index": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int64, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
+    "sse_tok_last_error": (C.c_char_p, []),
+    "sse_tok_create": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.POINTER(_P)]),
+    "sse_tok_destroy": (C.c_int, [_P]),
+    "sse_tok_vocab_size": (C.c_int, [_P]),
+    "sse_tok_encode_batch": (C.c_int, [_P, C.POINTER(C.c_char_p), C.c_int64, C.c_int, _P, _P, C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -402,3 +407,40 @@ def tsv_read_index(path: str, threads: int = 0) -> Tuple[List[str], List[str], n
     ids = [buf[a:b].decode("utf-8") for a, b, _c, _d in sp]
     texts = [buf[c:d].decode("utf-8") for _a, _b, c, d in sp]
     return ids, texts, out[:n], skipped.value
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batched subword tokenizer + padder (host only)
+class NativeTokenizer(object):
+    """Bulk `encode + pad` of lower-cased sentences with a reference vocabulary (csrc/subword_tok.cpp)."""
+
+    def __init__(self, subtoken_strings: Sequence[str]):
+        lib = load_library()
+        arr = (C.c_char_p * len(subtoken_strings))(*[s.encode("utf-8") for s in subtoken_strings])
+        self._h = _P()
+        if lib.sse_tok_create(arr, len(subtoken_strings), C.byref(self._h)) != SSE_OK:
+            raise SseError(lib.sse_tok_last_error().decode("utf-8", "replace"))
+
+    def encode_batch(self, texts: Sequence[str], T: int, threads: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """-> (int32 [n,T] padded rows, int32 [n] subtoken counts before padding / truncation)."""
+        lib = load_library()
+        n = len(texts)
+        rows = np.zeros((n, T), np.int32)
+        lengths = np.zeros(n, np.int32)
+        if n == 0:
+            return rows, lengths
+        arr = (C.c_char_p * n)(*[t.encode("utf-8") for t in texts])
+        if lib.sse_tok_encode_batch(self._h, arr, n, T, rows.ctypes.data, lengths.ctypes.data, threads) != SSE_OK:
+            raise SseError(lib.sse_tok_last_error().decode("utf-8", "replace"))
+        return rows, lengths
+
+    def close(self):
+        if self._h:
+            load_library().sse_tok_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -37,14 +37,17 @@ def createIndexFile(model, encoder, rawfile, max_seq_len, encodeIndexFile, sessi
                 print("Missing field with error line in raw target file: %s " % line)
                 continue
             tgtSentence, tgtId = info[0], info[1]
-            tgt_tokens = encoder.encode(tgtSentence.lower())
-            if len(tgt_tokens) > max_seq_len - 2:
-                print("Error Detected!!! \n Target:\n %s \n Its seq length is:%d,  which is longer than MAX_SEQ_LENTH of %d. "
-                      "Try to increase limit!!!!" % (tgtSentence, len(tgt_tokens), max_seq_len))
-            tgtInputs.append(text_encoder.pad_tokens(tgt_tokens, max_seq_len))
             tgtIds.append(tgtId)
             tgtSentences.append(tgtSentence)
-        if not tgtInputs:
+        if tgtSentences:
+            # tokenise + pad the whole batch natively (csrc/subword_tok.cpp): same ids / row rule as the reference loop
+            # encoder.encode(tgtSentence.lower()) + [PAD]*(T-len-1) + ids + [EOS] (sse_index.py:77-85)
+            tgtInputs, lens = encoder.encode_batch([t.lower() for t in tgtSentences], max_seq_len)
+            for tgtSentence, n in zip(tgtSentences, lens.tolist()):
+                if n > max_seq_len - 2:
+                    print("Error Detected!!! \n Target:\n %s \n Its seq length is:%d,  which is longer than MAX_SEQ_LENTH of %d. "
+                          "Try to increase limit!!!!" % (tgtSentence, n, max_seq_len))
+        if not tgtSentences:
             continue
         feed = model.get_target_encoding_feed_dict(tgtInputs)
         targetsEncodings = np.vstack(session.run([model.norm_tgt_seq_embedding], feed_dict=feed))

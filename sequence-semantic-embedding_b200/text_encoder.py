@@ -114,6 +114,15 @@ class SubwordTextEncoder(object):
             out.extend(ids)
         return out
 
+    def encode_batch(self, raw_texts, max_seq_length: int, threads: int = 0):
+        """Bulk path: encode + pad every sentence (already lower-cased by the caller, as the entry points do) into
+        int32 [n, max_seq_length] rows with the native multi-threaded tokenizer (csrc/subword_tok.cpp); also returns
+        the un-padded subtoken counts.  Same ids as [pad_tokens(self.encode(t), T) for t in raw_texts]."""
+        if getattr(self, "_native", None) is None:
+            import sse_ffi
+            self._native = sse_ffi.NativeTokenizer(self._strings)
+        return self._native.encode_batch(list(raw_texts), max_seq_length, threads)
+
     def decode_list(self, ids: Iterable[int]) -> List[str]:
         return [self._strings[i] if 0 <= i < len(self._strings) else "" for i in ids]
 
