@@ -890,7 +890,16 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   if (n_groups > MAX_GROUPS) { set_error("search_tc: Q=%d too large for one call (max %d rows)", Q, MAX_GROUPS * 2 * TILE_M); return SSE_EINVAL; }
   const int Qp = n_groups * mtg * TILE_M;
   const int gstride = mtg * TILE_M;                 // padded rows per group
-  const int rpg = cdiv(Q, n_groups);                // query rows per group (equal for all groups)
+  // Row packing.  "full": groups of gstride rows, the last one holds the remainder and may need fewer m-tiles (600
+  // rows -> 256 + 256 + 88: five m-tiles of MMA work instead of six); the groups then get work items in proportion to
+  // their per-tile cost.  "equal": every group holds cdiv(Q, n_groups) rows, all groups cost the same and sweep
+  // identical tile ranges in lock-step (index fetched from HBM once; 1.03x measured).  Full packing pays when it
+  // removes >= 10 % of the m-tiles (measured: Q=600 0.383 -> 0.359 ms, Q=257 0.131 -> 0.128; but Q=2400, where it
+  // saves 1 m-tile in 20 and the odd group breaks the lock-step L2 sharing, 0.367 -> 0.426).  SSE_SCAN_PACK=0/1 forces.
+  static const int pack_env = getenv("SSE_SCAN_PACK") ? atoi(getenv("SSE_SCAN_PACK")) : -1;
+  const int mt_last_full = cdiv(Q - (n_groups - 1) * gstride, TILE_M);
+  const bool pack_full = pack_env >= 0 ? pack_env != 0 : (mtg - mt_last_full) * 10 >= n_groups * mtg;
+  const int rpg = pack_full ? gstride : cdiv(Q, n_groups);   // query rows per group (the last group may hold fewer)
   const int n_tiles = (int)cdiv64(N, tn);
   // sample = every 16th tile: tau = k-th largest sampled tile maximum - 2 eps keeps ~16 k candidates per query
   // (measured: 1/32 and 1/64 samples cost more in candidate handling than they save in the sample pass); rows whose
@@ -916,16 +925,28 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   sp.N = N; sp.Qp = Qp; sp.global_offset = global_offset;
   int items = 0;
   {
-    // every group holds rpg query rows (same cost) and gets the same number of work items with IDENTICAL tile
-    // ranges: the CTAs of different groups that share a range run concurrently, so the index is fetched from HBM
-    // about once and the other groups' reads of the same tiles hit L2.
-    const int R = max(1, max(num_sms, n_groups) / n_groups);
+    // groups with the same number of live m-tiles get the same number of work items with IDENTICAL tile ranges: the
+    // CTAs of different groups that share a range run concurrently, so the index is fetched from HBM about once per
+    // distinct item count and the other groups' reads of the same tiles hit L2.  A lighter last group (one live
+    // m-tile) gets fewer items, in proportion to its measured per-tile cost (feed + commit ~400 cycles, ~550 per m-tile).
+    int mt_of[MAX_GROUPS];
+    double cost_sum = 0;
     for (int g = 0; g < n_groups; ++g) {
-      sp.group_first_item[g] = g * R;
-      sp.group_items[g] = R;
-      sp.group_mt[g] = min(mtg, cdiv(min(rpg, Q - g * rpg), TILE_M));
+      mt_of[g] = std::max(1, std::min(mtg, cdiv(std::min(rpg, Q - g * rpg), TILE_M)));
+      cost_sum += 400.0 + 550.0 * mt_of[g];
     }
-    items = n_groups * R;
+    const int budget = std::max(num_sms, n_groups);
+    int first = 0;
+    for (int g = 0; g < n_groups; ++g) {
+      int R = (int)((400.0 + 550.0 * mt_of[g]) / cost_sum * budget);
+      if (mt_of[g] == mtg) R = (int)((400.0 + 550.0 * mtg) / cost_sum * budget);     // identical for all full groups
+      R = std::max(1, std::min(R, n_tiles));
+      sp.group_first_item[g] = first;
+      sp.group_items[g] = R;
+      sp.group_mt[g] = mt_of[g];
+      first += R;
+    }
+    items = first;
   }
 
   // workspace carve
