@@ -8,5 +8,5 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-pipeline --no-cpu-baseline --train-steps 0 > gpurun_out/ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 4 -c 2 -o gpurun_out/prof_scan python bench.py --steps 2 --warmup 3 --no-pipeline --no-cpu-baseline --train-steps 0 > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log | cut -c1-200
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_ptable_kernel -s 2 -c 1 -o gpurun_out/prof_lstm python bench.py --steps 2 --warmup 3 --no-pipeline --no-cpu-baseline --train-steps 0 > gpurun_out/ncu_full2.log 2>&1; tail -1 gpurun_out/ncu_full2.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none -k regex:lstm_tc_kernel -s 1 -c 1 -o gpurun_out/prof_lstm_tc_fullwave python scripts/lstm_debug.py 18944 > gpurun_out/ncu_full3.log 2>&1; tail -2 gpurun_out/ncu_full3.log | cut -c1-200
+timeout 200 python scripts/tsv_bench.py 200000 256 > gpurun_out/tsv_bench.json 2>/dev/null; cut -c1-300 gpurun_out/tsv_bench.json
 ls -la gpurun_out | head -40
