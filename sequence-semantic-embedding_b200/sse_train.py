@@ -87,6 +87,51 @@ def set_up_logging():
     log.addHandler(fh)
 
 
+class WindowStats(object):
+    """Means over the current reporting window of `steps_per_checkpoint` steps (reference sse_train.py:170-174, 215:
+    the reference accumulates x / steps_per_checkpoint per step and zeroes the sums after each report)."""
+
+    def __init__(self, window):
+        self.window = float(window)
+        self.reset()
+
+    def reset(self):
+        self.step_time = self.loss = self.train_acc = 0.0
+
+    def add(self, seconds, loss, acc):
+        self.step_time += seconds / self.window
+        self.loss += loss / self.window
+        self.train_acc += acc / self.window
+
+
+class CheckpointPolicy(object):
+    """What to do at a reporting point, given the window's training accuracy (reference sse_train.py:196-212):
+      * decay the learning rate when more than six reports exist and this one is below the minimum of the last five;
+      * the accuracy joins the history; equal to the best so far -> save `-BestEver`, else report and skip;
+      * `finished` (save `-final`, leave the batch loop) when epoch > 10 and the accuracy is below the minimum of the
+        last five reports -- evaluated AFTER the append, as the reference does, so the window's own value is part of
+        that minimum and the branch cannot fire; kept for parity of behaviour."""
+
+    def __init__(self):
+        self.history = []
+
+    def report(self, acc, epoch):
+        decay = len(self.history) > 6 and acc < min(self.history[-5:])
+        self.history.append(acc)
+        return {"decay_lr": decay, "save_best": acc == max(self.history), "best": max(self.history),
+                "finished": epoch > 10 and acc < min(self.history[-5:])}
+
+
+def _evaluate_epoch(model, data, sess, epoch):
+    """Index the whole target space with the current weights and report top-1/3/10 (reference sse_train.py:221-227)."""
+    model.set_forward_only(True)
+    idx_file = os.path.join(FLAGS.model_dir, FLAGS.encodedIndexFile)
+    sse_index.createIndexFile(model, data.encoder, os.path.join(FLAGS.model_dir, FLAGS.rawfilename), FLAGS.max_seq_length, idx_file,
+                              sess, batchsize=1000)
+    acc1, acc3, acc10 = sse_evaluator.Evaluator(model, data.rawEvalCorpus, idx_file, sess).eval()
+    logging.info("epoc#%d, task specific evaluation: top 1/3/10 accuracies: %f / %f / %f \n\n\n" % (epoch, acc1, acc3, acc10))
+
+
 def train():
     logging.info("Preparing Train & Eval data in %s" % FLAGS.data_dir)
     for d in (FLAGS.data_dir, FLAGS.model_dir):
@@ -94,62 +139,50 @@ def train():
     data = Data(FLAGS.model_dir, FLAGS.data_dir, FLAGS.vocab_size, FLAGS.max_seq_length, seed=FLAGS.seed)
     epoc_steps = len(data.rawTrainPosCorpus) / FLAGS.batch_size
     logging.info("Training Data: %d total positive samples, each epoch need %d steps" % (len(data.rawTrainPosCorpus), epoc_steps))
+    ckpt_prefix = os.path.join(FLAGS.model_dir, "SSE-LSTM.ckpt")
     with sse_model.Session(seed=FLAGS.seed) as sess:
         model = create_model(sess, data.rawnegSetLen, data.vocab_size, False)
         summary_op = model.add_summaries()
-        step_time, loss, train_acc = 0.0, 0.0, 0.0
-        current_step = 0
-        previous_accuracies = []
-        stop = False
+        fetches = [model.train, summary_op, model.loss, model.train_acc]
+        stats, policy = WindowStats(FLAGS.steps_per_checkpoint), CheckpointPolicy()
+        steps_done, out_of_budget = 0, False
         for epoch in range(FLAGS.max_epoc):
-            epoc_start_Time = time.time()
-            for _batchId in range(int(epoc_steps)):
-                start_time = time.time()
-                source_inputs, tgt_inputs, labels = data.get_train_batch(FLAGS.batch_size)
+            t_epoch = time.time()
+            for _ in range(int(epoc_steps)):
+                t0 = time.time()
+                src, tgt, labels = data.get_train_batch(FLAGS.batch_size)
                 model.set_forward_only(False)
-                d = model.get_train_feed_dict(source_inputs, tgt_inputs, labels)
-                _, _summary, step_loss, step_train_acc = sess.run([model.train, summary_op, model.loss, model.train_acc], feed_dict=d)
-                step_time += (time.time() - start_time) / FLAGS.steps_per_checkpoint
-                loss += step_loss / FLAGS.steps_per_checkpoint
-                train_acc += step_train_acc / FLAGS.steps_per_checkpoint
-                current_step += 1
-                if FLAGS.max_steps and current_step >= FLAGS.max_steps:
-                    stop = True
-                if current_step % FLAGS.steps_per_checkpoint == 0:
+                _, _summary, step_loss, step_acc = sess.run(fetches, feed_dict=model.get_train_feed_dict(src, tgt, labels))
+                stats.add(time.time() - t0, step_loss, step_acc)
+                steps_done += 1
+                out_of_budget = bool(FLAGS.max_steps) and steps_done >= FLAGS.max_steps
+                if steps_done % FLAGS.steps_per_checkpoint == 0:
+                    gs = model.global_step.eval()
                     logging.info("global epoc: %.3f, global step %d, learning rate %.4f step-time:%.2f loss:%.4f train_binary_acc:%.4f " %
-                                 (float(model.global_step.eval()) / float(epoc_steps), model.global_step.eval(),
-                                  model.learning_rate.eval(), step_time, step_loss, train_acc))
-                    checkpoint_path = os.path.join(FLAGS.model_dir, "SSE-LSTM.ckpt")
-                    # Decrease learning rate if no improvement was seen over last 5 times.
-                    if len(previous_accuracies) > 6 and train_acc < min(previous_accuracies[-5:]):
+                                 (float(gs) / float(epoc_steps), gs, model.learning_rate.eval(), stats.step_time, step_loss, stats.train_acc))
+                    verdict = policy.report(stats.train_acc, epoch)
+                    if verdict["decay_lr"]:
                         sess.run(model.learning_rate_decay_op)
-                    previous_accuracies.append(train_acc)
-                    if train_acc == max(previous_accuracies):
-                        logging.info("Better Accuracy %.4f found. Saving current best model ..." % train_acc)
-                        model.save(sess, checkpoint_path + "-BestEver")
+                    if verdict["save_best"]:
+                        logging.info("Better Accuracy %.4f found. Saving current best model ..." % stats.train_acc)
+                        model.save(sess, ckpt_prefix + "-BestEver")
                     else:
-                        logging.info("Best Accuracy is: %.4f, while current round is: %.4f" % (max(previous_accuracies), train_acc))
+                        logging.info("Best Accuracy is: %.4f, while current round is: %.4f" % (verdict["best"], stats.train_acc))
                         logging.info("skip saving model ...")
-                    if epoch > 10 and train_acc < min(previous_accuracies[-5:]):
-                        p = model.save(sess, checkpoint_path + "-final")
-                        logging.info("After around %d Epocs no further improvement, Training finished, wrote checkpoint to %s." % (epoch, p))
-                        stop = True
-                    step_time, loss, train_acc = 0.0, 0.0, 0.0
-                if stop:
+                    if verdict["finished"]:
+                        where = model.save(sess, ckpt_prefix + "-final")
+                        logging.info("After around %d Epocs no further improvement, Training finished, wrote checkpoint to %s." % (epoch, where))
+                        break
+                    stats.reset()
+                if out_of_budget:
                     break
-            logging.info("\n\n\nepoch# %d  took %f hours" % (epoch, (time.time() - epoc_start_Time) / 3600.0))
-            if (FLAGS.task_type not in ["ranking", "crosslingual"]) or ((epoch + 1) % 20 == 0) or stop:
-                model.set_forward_only(True)
-                idx_file = os.path.join(FLAGS.model_dir, FLAGS.encodedIndexFile)
-                sse_index.createIndexFile(model, data.encoder, os.path.join(FLAGS.model_dir, FLAGS.rawfilename),
-                                          FLAGS.max_seq_length, idx_file, sess, batchsize=1000)
-                evaluator = sse_evaluator.Evaluator(model, data.rawEvalCorpus, idx_file, sess)
-                acc1, acc3, acc10 = evaluator.eval()
-                logging.info("epoc#%d, task specific evaluation: top 1/3/10 accuracies: %f / %f / %f \n\n\n" % (epoch, acc1, acc3, acc10))
-            model.save(sess, os.path.join(FLAGS.model_dir, "SSE-LSTM.ckpt") + "-epoch-%d" % epoch)
-            if previous_accuracies:
-                logging.info("So far best ever model training binary accuracy is: %.4f " % max(previous_accuracies))
-            if stop:
+            logging.info("\n\n\nepoch# %d  took %f hours" % (epoch, (time.time() - t_epoch) / 3600.0))
+            if FLAGS.task_type not in ("ranking", "crosslingual") or (epoch + 1) % 20 == 0 or out_of_budget:
+                _evaluate_epoch(model, data, sess, epoch)
+            model.save(sess, ckpt_prefix + "-epoch-%d" % epoch)
+            if policy.history:
+                logging.info("So far best ever model training binary accuracy is: %.4f " % max(policy.history))
+            if out_of_budget:
                 break
 
 

@@ -215,3 +215,101 @@ def test_lr_decay_floor():
     assert O.lr_decay(st, 0.5) == pytest.approx(1e-3)
     st.learning_rate = 0.9
     assert O.lr_decay(st, 0.99) == pytest.approx(np.float32(0.9) * np.float32(0.99))
+
+
+def test_train_loop_policy_matches_reference_rules():
+    """Host logic of the training entry point (sse_train.py:196-215 of the reference): lr decay / BestEver / the dead
+    early-stop branch, and the windowed means."""
+    import sse_train
+    pol = sse_train.CheckpointPolicy()
+    accs = [0.5, 0.6, 0.7, 0.65, 0.66, 0.67, 0.68, 0.60, 0.69, 0.9]
+    out = [pol.report(a, epoch=12) for a in accs]
+    assert [o["save_best"] for o in out] == [True, True, True, False, False, False, False, False, False, True]
+    # decay needs more than six earlier reports and a value below the minimum of the last five of them
+    assert [o["decay_lr"] for o in out] == [False] * 7 + [True, False, False]
+    assert not any(o["finished"] for o in out)          # the reference's own early stop can never fire (checked after append)
+    assert out[-1]["best"] == 0.9
+    w = sse_train.WindowStats(4)
+    for s in range(4):
+        w.add(2.0, 1.0 + s, 0.5)
+    assert abs(w.step_time - 2.0) < 1e-12 and abs(w.loss - 2.5) < 1e-12 and abs(w.train_acc - 0.5) < 1e-12
+    w.reset()
+    assert w.loss == 0.0
+
+
+def test_train_entry_point_flow_with_stubbed_compute(tmp_path, monkeypatch):
+    """Drives sse_train.main() end to end on the CPU with the compute (model / session / index / evaluator / data)
+    replaced by recorders: checks the order of operations, checkpoint names and the log lines the reference emits."""
+    import logging
+    import sse_train
+
+    calls = []
+
+    class T(object):
+        def __init__(self, v): self.v = v
+        def eval(self): return self.v
+
+    class FakeModel(object):
+        train, loss, train_acc, learning_rate_decay_op = "train", "loss", "acc", "decay"
+        def __init__(self, params, device=0):
+            self.global_step, self.learning_rate, self.saver = T(0), T(float(params["learning_rate"])), self
+        def add_summaries(self): return "summary"
+        def set_forward_only(self, f): calls.append(("forward_only", f))
+        def get_train_feed_dict(self, s, t, l): return {"s": s}
+        def save(self, sess, path): calls.append(("save", os.path.basename(path))); return path
+        def restore(self, sess, path): calls.append(("restore", path))
+
+    class FakeSession(object):
+        def __init__(self, seed=None): self.n = 0
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+        def run(self, fetches, feed_dict=None):
+            if fetches == "decay": calls.append(("decay",)); return None
+            if not isinstance(fetches, list): calls.append(("init",)); return None
+            self.n += 1
+            model.global_step.v = self.n
+            return [None, None, 1.0 / self.n, min(0.99, 0.5 + 0.01 * self.n)]
+
+    class FakeData(object):
+        def __init__(self, *a, **k):
+            self.rawTrainPosCorpus, self.rawnegSetLen, self.vocab_size, self.encoder, self.rawEvalCorpus = list(range(40)), 7, 100, None, []
+        def get_train_batch(self, bs): return [[0]], [[0]], [1.0]
+
+    model = None
+
+    def make_model(params, device=0):
+        nonlocal model
+        model = FakeModel(params, device)
+        return model
+
+    class FakeEval(object):
+        def __init__(self, *a): calls.append(("evaluator",))
+        def eval(self): return 0.1, 0.3, 0.9
+
+    monkeypatch.setattr(sse_train, "Data", FakeData)
+    monkeypatch.setattr(sse_train.sse_model, "SSEModel", make_model)
+    monkeypatch.setattr(sse_train.sse_model, "Session", FakeSession)
+    monkeypatch.setattr(sse_train.sse_model, "get_checkpoint_state", lambda d: None)
+    monkeypatch.setattr(sse_train.sse_index, "createIndexFile", lambda *a, **k: calls.append(("index", k.get("batchsize"))))
+    monkeypatch.setattr(sse_train.sse_evaluator, "Evaluator", FakeEval)
+    md = str(tmp_path / "m")
+    root = logging.getLogger("")
+    before = list(root.handlers)
+    try:
+        sse_train.main(["--data_dir", str(tmp_path / "d"), "--model_dir", md, "--batch_size", "10", "--steps_per_checkpoint", "2",
+                        "--max_epoc", "2", "--task_type", "classification"])
+    finally:
+        for h in list(root.handlers):
+            if h not in before:
+                root.removeHandler(h); h.close()
+    # 40 positives / batch 10 = 4 steps per epoch, report every 2 steps: 2 reports per epoch, accuracies rise -> BestEver each time
+    saves = [c[1] for c in calls if c[0] == "save"]
+    assert saves == ["SSE-LSTM.ckpt-BestEver", "SSE-LSTM.ckpt-BestEver", "SSE-LSTM.ckpt-epoch-0",
+                     "SSE-LSTM.ckpt-BestEver", "SSE-LSTM.ckpt-BestEver", "SSE-LSTM.ckpt-epoch-1"]
+    assert [c for c in calls if c[0] in ("index", "evaluator")] == [("index", 1000), ("evaluator",)] * 2
+    assert ("init",) in calls and ("decay",) not in calls
+    log = open(os.path.join(md, "TrainingLog.txt")).read()
+    assert "Created model with fresh parameters." in log and "Better Accuracy" in log
+    assert "epoc#1, task specific evaluation: top 1/3/10 accuracies: 0.100000 / 0.300000 / 0.900000" in log
+    assert "global epoc: 0.500, global step 2, learning rate 0.9000" in log
+    assert os.path.exists(os.path.join(md, "modelConfig.param"))
