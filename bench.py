@@ -179,6 +179,7 @@ def init_weights(seed=1234):
 def run_b200(args):
     import torch
     import torch.distributed as dist
+    import sse_dist
     import sse_ffi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,7 +253,7 @@ def run_b200(args):
             if emu:
                 out.view(G, Ql, E).copy_(scratch.unsqueeze(0).expand(G, Ql, E))
             else:
-                dist.all_gather_into_tensor(out, scratch)
+                sse_dist.allgather_rows(scratch, out)
 
     def issue_encode(b, slot):
         with torch.cuda.stream(enc_stream):

@@ -49,6 +49,28 @@ def gather_and_merge(scores: torch.Tensor, ids: torch.Tensor, k: int, merge_fn: 
     return merge_fn(cs, ci, k)
 
 
+def allgather_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
+    """Rank-major concatenation of equally shaped per-rank row blocks: [R, C] on every rank -> [G*R, C] on every rank
+    (rank r's rows land at [r*R, (r+1)*R)).  The throughput-serving flow uses it to hand every rank the query encodings
+    of all ranks before the shard scan (each rank encodes only its own batch); single process: returns x."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        if out is not None:
+            out.copy_(x)
+            return out
+        return x
+    if out is None:
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def rows_of_rank(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """The block of `rank` inside a rank-major concatenation produced by allgather_rows."""
+    r = x.shape[0] // world
+    return x[rank * r:(rank + 1) * r]
+
+
 class ShardedIndex(object):
     """Index rows partitioned over the ranks of the default process group."""
 
@@ -81,6 +103,13 @@ class ShardedIndex(object):
         i = torch.empty(Q, k, device=q_dev.device, dtype=torch.int32)
         self.h.search(q_dev, Q, k, s, i, torch.cuda.current_stream())
         return gather_and_merge(s, i, k, self._merge_cuda)
+
+    def search_distributed_queries(self, q_local_dev: torch.Tensor, k: int):
+        """Every rank brings its OWN [Q_r, E] query vectors (same Q_r on all ranks): all-gather them, scan the local
+        shard for all G*Q_r, all-gather + merge the partial top-k; returns this rank's rows of the merged result."""
+        q_all = allgather_rows(q_local_dev)
+        s, i = self.search(q_all, k)
+        return rows_of_rank(s, self.rank, self.world), rows_of_rank(i, self.rank, self.world)
 
 
 def allreduce_train_step(handle, src, tgt, labels, b_global: int):

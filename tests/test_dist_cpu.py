@@ -81,3 +81,62 @@ def test_pack_unpack_round_trip():
     g = torch.stack([packed, packed + 0])
     cs, ci = sse_dist.unpack_gathered(g, 4)
     assert cs.shape == (3, 8) and torch.equal(cs[:, :4], s) and torch.equal(ci[:, 4:], i)
+
+
+def _body_distributed_queries(rank, world, N, Q, E, k, out):
+    """The throughput-serving flow of bench.py --gpus N: every rank brings its own queries."""
+    rng = np.random.default_rng(11)
+    tgt = rng.standard_normal((N, E)).astype(np.float32)
+    q_all = rng.standard_normal((world * Q, E)).astype(np.float32)
+    q_mine = torch.from_numpy(q_all[rank * Q:(rank + 1) * Q].copy())
+    gathered = sse_dist.allgather_rows(q_mine)
+    assert np.array_equal(gathered.numpy(), q_all)                       # rank-major, bit-exact
+    pre = torch.empty(world * Q, E)
+    assert sse_dist.allgather_rows(q_mine, pre) is pre and np.array_equal(pre.numpy(), q_all)
+    lo, hi = sse_dist.shard_range(N, world, rank)
+    s, i = O.top_k_tf(gathered.numpy() @ tgt[lo:hi].T, k, normalize_scores=False)
+    ms, mi = sse_dist.gather_and_merge(torch.from_numpy(s.astype(np.float32)), torch.from_numpy((i + lo).astype(np.int32)), k, _merge_numpy)
+    my_s, my_i = sse_dist.rows_of_rank(ms, rank, world), sse_dist.rows_of_rank(mi, rank, world)
+    ws, wi = O.top_k_tf(q_mine.numpy() @ tgt.T, k, normalize_scores=False)
+    ok = np.array_equal(my_i.numpy(), wi) and float(np.abs(my_s.numpy() - ws).max()) < 1e-6
+    flags = [torch.zeros(1) for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([1.0 if ok else 0.0]))
+    if rank == 0:
+        out.put((all(f.item() == 1.0 for f in flags), 0.0))
+
+
+def _worker_dq(rank, world, port, N, Q, E, k, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _body_distributed_queries(rank, world, N, Q, E, k, out)
+    except Exception as e:
+        if rank == 0:
+            out.put((False, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_queries_allgather_scan_merge_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker_dq, args=(r, 2, port, 777, 6, 8, 4, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, err = out.get(timeout=90)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok, err
+
+
+def test_allgather_rows_single_process_is_identity():
+    x = torch.arange(6.0).reshape(3, 2)
+    assert sse_dist.allgather_rows(x) is x
+    y = torch.empty(3, 2)
+    assert sse_dist.allgather_rows(x, y) is y and torch.equal(x, y)
+    assert torch.equal(sse_dist.rows_of_rank(torch.arange(8).reshape(4, 2), 1, 2), torch.tensor([[4, 5], [6, 7]]))
