@@ -42,6 +42,17 @@ class DemoSession(object):
         self.model.handle.index_set(encs, global_offset=0)
         self.T = int(self.cfg["max_seq_length"])
 
+    def batcher(self, max_batch=64, max_wait_ms=2.0):
+        """A micro-batcher over this session's device index for concurrent callers (web-server threads): requests
+        arriving within max_wait_ms share one encode + scan (sse_serve.MicroBatcher)."""
+        import sse_serve
+        return sse_serve.MicroBatcher(lambda toks, k, normalize: self.model.handle.query_host(toks, k, normalize=normalize),
+                                      max_batch=max_batch, max_wait_ms=max_wait_ms)
+
+    def tokens(self, sentence):
+        ids = self.encoder.encode(sentence.lower())
+        return np.array(text_encoder.pad_tokens(ids, self.T), dtype=np.int32)
+
     def query(self, sentence, nbest, normalize=False):
         ids = self.encoder.encode(sentence.lower())
         if len(ids) > self.T - 2:
