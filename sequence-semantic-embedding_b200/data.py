@@ -63,6 +63,51 @@ class Data(object):
             labels.append(0.0)
         return source_inputs, tgt_inputs, labels
 
+    # ------------------------------------------------------------------ vectorised sampler (host side)
+    def _build_arrays(self):
+        """Corpus as arrays: source rows [P,T], verified-target lists in CSR form over target ROW numbers, target rows
+        [N,T].  Built once; the python objects stay the source of truth for the reference-shaped API above."""
+        tid_row = {tid: j for j, tid in enumerate(self.fullSetTargetIds)}
+        self._tgt_rows = numpy.array([self.encodedFullTargetSpace[t] for t in self.fullSetTargetIds], dtype=numpy.int32)
+        self._src_rows = numpy.array([src for src, _ in self.rawTrainPosCorpus], dtype=numpy.int32)
+        counts = numpy.array([len(v) for _, v in self.rawTrainPosCorpus], dtype=numpy.int64)
+        self._ver_off = numpy.concatenate([[0], numpy.cumsum(counts)])
+        self._ver_rows = numpy.array([tid_row[t] for _, v in self.rawTrainPosCorpus for t in v], dtype=numpy.int64)
+        # membership test "target row j is verified for positive i" as a sorted key array (i * N + j)
+        owner = numpy.repeat(numpy.arange(len(counts), dtype=numpy.int64), counts)
+        self._ver_keys = numpy.sort(owner * len(self.fullSetTargetIds) + self._ver_rows)
+
+    def get_train_batch_arrays(self, batch_size):
+        """Same sampling rule and row layout as get_train_batch (reference data.py:95-115) -- window of consecutive
+        positives that never starts in the first batch_size samples, one uniformly chosen verified target per positive,
+        one uniformly chosen NON-verified target as the negative (rejection), rows alternating (pos, 1.0), (neg, 0.0)
+        -- drawn with array operations: returns int32 [2B,T], int32 [2B,T], float32 [2B].  The random stream differs
+        from the python loop's (the reference's is unseeded); the distribution is the same."""
+        if not hasattr(self, "_src_rows"):
+            self._build_arrays()
+        rng = self.rng
+        P, N = self._src_rows.shape[0], self._tgt_rows.shape[0]
+        start = int(rng.randint(0, P - batch_size)) + batch_size
+        rows = numpy.arange(start, min(start + batch_size, P), dtype=numpy.int64)
+        B = rows.shape[0]
+        cnt = self._ver_off[rows + 1] - self._ver_off[rows]
+        pos = self._ver_rows[self._ver_off[rows] + (rng.random_sample(B) * cnt).astype(numpy.int64)]
+        neg = rng.randint(0, N, size=B).astype(numpy.int64)
+        keys = self._ver_keys
+        while True:
+            k = rows * N + neg
+            j = numpy.searchsorted(keys, k)
+            clash = (j < keys.shape[0]) & (keys[numpy.minimum(j, keys.shape[0] - 1)] == k)
+            if not clash.any():
+                break
+            neg[clash] = rng.randint(0, N, size=int(clash.sum()))
+        src = numpy.repeat(self._src_rows[rows], 2, axis=0)
+        tgt = numpy.empty((2 * B, self._tgt_rows.shape[1]), numpy.int32)
+        tgt[0::2] = self._tgt_rows[pos]
+        tgt[1::2] = self._tgt_rows[neg]
+        labels = numpy.tile(numpy.array([1.0, 0.0], numpy.float32), B)
+        return src, tgt, labels
+
     def get_test_batch(self, batch_size):
         num_samples = len(self.rawEvalCorpus)
         idx = self.rng.randint(0, num_samples - batch_size) + batch_size
