@@ -195,6 +195,8 @@ int sse_set_option(sse_handle* h, const char* key, int value);
  * Formatting is numpy's str(np.float32) byte for byte; parsing is correctly rounded, so a written index reads
  * back bit-exactly.  Rows are split over `threads` host threads (<= 0: all hardware threads). */
 const char* sse_tsv_last_error(void);
+/* CRC-32C (Castagnoli) of n bytes, continuing from `seed` (0 to start): checksum of TF table blocks / bundle entries. */
+uint32_t sse_crc32c(const void* data, size_t n, uint32_t seed);
 /* n floats -> their decimal strings packed back to back (no separators); ends[i] = end offset of value i. */
 int sse_tsv_format_f32(const float* values, int64_t n, char* out, size_t cap, int64_t* ends);
 int sse_tsv_write_index(const char* path, const char* const* ids, const char* const* texts, const float* rows,

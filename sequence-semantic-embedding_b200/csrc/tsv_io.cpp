@@ -111,6 +111,35 @@ inline bool is_py_space(unsigned char c) {   // str.strip() on the ASCII range
 
 extern "C" {
 
+// CRC-32C (Castagnoli), the checksum of TensorFlow's table blocks and tensor-bundle entries (tf_bundle.py): table-driven,
+// 8 bytes per step (slicing-by-8), no ISA extensions required.
+uint32_t sse_crc32c(const void* data, size_t n, uint32_t seed) {
+  static uint32_t T[8][256];
+  static bool ready = false;
+  if (!ready) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      T[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xFF];
+    ready = true;
+  }
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint32_t crc = ~seed;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4); memcpy(&hi, p + 4, 4);
+    lo ^= crc;
+    crc = T[7][lo & 0xFF] ^ T[6][(lo >> 8) & 0xFF] ^ T[5][(lo >> 16) & 0xFF] ^ T[4][lo >> 24] ^
+          T[3][hi & 0xFF] ^ T[2][(hi >> 8) & 0xFF] ^ T[1][(hi >> 16) & 0xFF] ^ T[0][hi >> 24];
+    p += 8; n -= 8;
+  }
+  while (n--) crc = T[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
+  return ~crc;
+}
+
 const char* sse_tsv_last_error(void) { return g_tsv_error.c_str(); }
 
 int sse_tsv_format_f32(const float* values, int64_t n, char* out, size_t cap, int64_t* ends) {

@@ -88,6 +88,7 @@ _SIGNATURES = {
     "sse_launch_count": (C.c_int64, [_P]),
     "sse_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "sse_tsv_last_error": (C.c_char_p, []),
+    "sse_crc32c": (C.c_uint32, [_P, C.c_size_t, C.c_uint32]),
     "sse_tsv_format_f32": (C.c_int, [_P, C.c_int64, _P, C.c_size_t, _P]),
     "sse_tsv_write_index": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _P, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "sse_tsv_parse_index": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int64, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
@@ -444,3 +445,13 @@ class NativeTokenizer(object):
             self.close()
         except Exception:
             pass
+
+
+def crc32c(data, seed: int = 0) -> int:
+    """CRC-32C of a bytes-like object / numpy array (native, slicing-by-8)."""
+    lib = load_library()
+    if isinstance(data, np.ndarray):
+        a = np.ascontiguousarray(data)
+        return int(lib.sse_crc32c(a.ctypes.data, a.nbytes, seed))
+    b = bytes(data)
+    return int(lib.sse_crc32c(b, len(b), seed))

@@ -84,6 +84,8 @@ class Saver(object):
         return prefix
 
     def restore(self, session, path):
+        if not path.endswith(".npz") and not os.path.exists(path + ".npz") and os.path.exists(path + ".index"):
+            return self._restore_tf_bundle(path)
         fn = path if path.endswith(".npz") else path + ".npz"
         with np.load(fn) as z:
             names = dict(self.model.handle.param_names())
@@ -94,6 +96,32 @@ class Saver(object):
                     raise sse_ffi.SseError("checkpoint variable %s not in model" % name)
                 self.model.handle.set_param(name, z[name])
             self.model.handle.set_scalars(float(z["learning_rate"]), int(z["global_step"]))
+        self.model._initialized = True
+
+
+    def _restore_tf_bundle(self, prefix):
+        """A checkpoint written by the reference's tf.train.Saver (V2 tensor bundle: <prefix>.index + .data-*), read by
+        tf_bundle.py (format-level reader, unpinned against the real library).  Variable names are TensorFlow's
+        (SURVEY A.6); TF <= 1.1 LSTM names (`.../basic_lstm_cell/weights|biases`) map to `kernel|bias`.  Variables the
+        model does not have (summaries, beta powers, ...) are ignored; every model variable must be present."""
+        import tf_bundle
+        tensors = tf_bundle.read_bundle(prefix)
+        names = dict(self.model.handle.param_names())
+        found = set()
+        for name, arr in tensors.items():
+            tgt = name.replace("basic_lstm_cell/weights", "basic_lstm_cell/kernel").replace("basic_lstm_cell/biases", "basic_lstm_cell/bias")
+            if tgt in names:
+                self.model.handle.set_param(tgt, np.asarray(arr, dtype=np.float32))
+                found.add(tgt)
+        missing = [n for n in names if n not in found and not n.endswith("/Adagrad")]
+        if missing:
+            raise sse_ffi.SseError("TF checkpoint %s lacks model variables: %s" % (prefix, ", ".join(sorted(missing)[:6])))
+        lr, gs = self.model.handle.scalars()
+        if "learning_rate" in tensors:
+            lr = float(np.asarray(tensors["learning_rate"]).reshape(-1)[0])
+        if "global_step" in tensors:
+            gs = int(np.asarray(tensors["global_step"]).reshape(-1)[0])
+        self.model.handle.set_scalars(lr, gs)
         self.model._initialized = True
 
 
@@ -111,7 +139,7 @@ def get_checkpoint_state(model_dir):
         if line.startswith("model_checkpoint_path:"):
             name = line.split(":", 1)[1].strip().strip('"')
             p = name if os.path.isabs(name) else os.path.join(model_dir, name)
-            if os.path.exists(p + ".npz"):
+            if os.path.exists(p + ".npz") or os.path.exists(p + ".index"):
                 return CheckpointState(p)
     return None
 
