@@ -1,10 +1,25 @@
 """Index-file I/O measurement (host only): native writer / reader (csrc/tsv_io.cpp) next to the reference's python loops
-(restated in oracle/sse_oracle.py: format_index_row / parse_index_lines).  usage: tsv_bench.py [rows] [E]"""
+(restated inline).  usage: tsv_bench.py [rows] [E]"""
 import json, os, sys, time
 import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(REPO, "sequence-semantic-embedding_b200")); sys.path.insert(0, os.path.join(REPO, "oracle"))
-import sse_ffi, sse_oracle as O
+sys.path.insert(0, os.path.join(REPO, "sequence-semantic-embedding_b200"))
+import sse_ffi
+
+
+def py_format_row(tgt_id, text, enc_row):            # the reference's writer loop body (sse_index.py:93-97)
+    return tgt_id + "\t" + text + "\t" + ",".join([str(n) for n in enc_row]) + "\n"
+
+
+def py_parse_lines(lines):                            # the reference's reader loop (sse_evaluator.py:79-88)
+    ids, encs = [], []
+    for line in lines:
+        info = line.strip().split("\t")
+        if len(info) != 3:
+            continue
+        ids.append(info[0]); encs.append([float(f) for f in info[2].strip().split(",")])
+    return ids, np.array(encs)
+
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 rng = np.random.default_rng(0)
@@ -15,9 +30,9 @@ t = time.perf_counter(); sse_ffi.tsv_write_index(p, ids, texts, enc); tw = time.
 t = time.perf_counter(); gi, gt, ge, _ = sse_ffi.tsv_read_index(p); tr = time.perf_counter() - t
 assert np.array_equal(ge.view(np.uint32), enc.view(np.uint32)) and gi == ids
 n2 = min(N, 5000)
-t = time.perf_counter(); s = "".join(O.format_index_row(i, tx, r) for i, tx, r in zip(ids[:n2], texts[:n2], enc[:n2])); tpw = time.perf_counter() - t
+t = time.perf_counter(); s = "".join(py_format_row(i, tx, r) for i, tx, r in zip(ids[:n2], texts[:n2], enc[:n2])); tpw = time.perf_counter() - t
 lines = s.splitlines(True)
-t = time.perf_counter(); O.parse_index_lines(lines); tpr = time.perf_counter() - t
+t = time.perf_counter(); py_parse_lines(lines); tpr = time.perf_counter() - t
 # batched tokenizer + padder (csrc/subword_tok.cpp) vs the python encoder, product-title-like sentences
 import text_encoder
 enc_tok = text_encoder.SubwordTextEncoder(os.path.join(REPO, "tests", "golden", "subword_vocab.txt"))

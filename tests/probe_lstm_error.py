@@ -1,4 +1,5 @@
-"""Probe (not a test): error of the tcgen05 LSTM kernels against the numpy oracle at the headline shape."""
+"""Probe (not collected by pytest -- no test_ prefix; lives under tests/ because it uses the oracle): error of the
+tcgen05 LSTM kernels against the numpy oracle at the headline shape.  python tests/probe_lstm_error.py"""
 import os, sys
 import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
