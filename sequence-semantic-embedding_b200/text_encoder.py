@@ -121,7 +121,14 @@ class SubwordTextEncoder(object):
         if getattr(self, "_native", None) is None:
             import sse_ffi
             self._native = sse_ffi.NativeTokenizer(self._strings)
-        return self._native.encode_batch(list(raw_texts), max_seq_length, threads)
+        texts = list(raw_texts)
+        rows, lengths = self._native.encode_batch([t if "\x00" not in t else "" for t in texts], max_seq_length, threads)
+        for i, t in enumerate(texts):             # C strings end at NUL: such (pathological) rows take the python path
+            if "\x00" in t:
+                ids = self.encode(t)
+                rows[i] = pad_tokens(ids, max_seq_length)
+                lengths[i] = len(ids)
+        return rows, lengths
 
     def decode_list(self, ids: Iterable[int]) -> List[str]:
         return [self._strings[i] if 0 <= i < len(self._strings) else "" for i in ids]

@@ -46,7 +46,7 @@ def test_adversarial_unicode_and_escapes(enc):
     for _ in range(3000):
         k = int(rng.integers(0, 6))
         texts.append(" ".join(rng.choice(pool, size=k)) if k else "")
-    texts += pool
+    texts += pool + ["nul\x00inside", "\x00"]
     for T in (3, 12):
         rows, lengths = enc.encode_batch(texts, T, threads=4)
         want_rows, want_len = python_rows(enc, texts, T)
