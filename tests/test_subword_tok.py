@@ -62,3 +62,18 @@ def test_bulk_rate_is_reported(enc):
     t = time.perf_counter(); want, _ = python_rows(enc, texts[:2000], 50); dp = time.perf_counter() - t
     assert np.array_equal(rows[:2000], want)
     print("native %.0f sentences/s, python %.0f sentences/s" % (len(texts) / dt, 2000 / dp))
+
+
+def test_property_native_equals_python_on_arbitrary_unicode(enc):
+    """hypothesis: any text (all planes, control characters, mixed scripts) tokenises identically on both paths."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.text(max_size=40), min_size=1, max_size=8), st.integers(min_value=3, max_value=20))
+    def check(texts, T):
+        texts = [t.lower() for t in texts]
+        rows, lengths = enc.encode_batch(texts, T, threads=2)
+        want_rows, want_len = python_rows(enc, texts, T)
+        assert np.array_equal(rows, want_rows) and np.array_equal(lengths, want_len)
+
+    check()

@@ -81,3 +81,20 @@ def test_reader_rejects_a_row_with_a_broken_vector(tmp_path):
     open(p, "w").write("a\tb\t0.1,0.2\nc\td\t0.1\n")
     with pytest.raises(sse_ffi.SseError):
         sse_ffi.tsv_read_index(p)
+
+
+def test_property_format_and_round_trip_for_arbitrary_float32_bits():
+    """hypothesis: every float32 bit pattern prints like numpy prints it and parses back to the same bits."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.integers(min_value=0, max_value=2 ** 32 - 1), min_size=1, max_size=64))
+    def check(bits):
+        v = np.array(bits, np.uint32).view(np.float32)
+        got = sse_ffi.tsv_format_f32(v)
+        assert got == [str(x) for x in v]
+        back = np.array([np.float32(s) for s in got], np.float32)
+        same = (back.view(np.uint32) == v.view(np.uint32)) | (np.isnan(back) & np.isnan(v))
+        assert same.all()
+
+    check()
