@@ -68,7 +68,7 @@ def test_property_native_equals_python_on_arbitrary_unicode(enc):
     """hypothesis: any text (all planes, control characters, mixed scripts) tokenises identically on both paths."""
     from hypothesis import given, settings, strategies as st
 
-    @settings(max_examples=300, deadline=None)
+    @settings(max_examples=300, deadline=None, derandomize=True)
     @given(st.lists(st.text(max_size=40), min_size=1, max_size=8), st.integers(min_value=3, max_value=20))
     def check(texts, T):
         texts = [t.lower() for t in texts]
