@@ -29,6 +29,7 @@
 #ifndef SSE_B200_H_
 #define SSE_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

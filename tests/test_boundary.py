@@ -50,3 +50,24 @@ def test_no_cpu_fallback_without_gpu():
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(sse_ffi.SseError):
         sse_ffi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_header_is_valid_c_and_links_from_a_c_program(tmp_path):
+    """The boundary is a C ABI: include/sse_b200.h must compile as C99 and a plain C program must link against the
+    library and call (host-only) entry points."""
+    import subprocess
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(repo, "include", "sse_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "use.c"
+    src.write_text('#include "sse_b200.h"\n#include <stdio.h>\n#include <string.h>\nint main(void) {\n'
+                   '  float v[3] = {0.1f, 1e-5f, 1234567.0f}; char out[64]; int64_t ends[3];\n'
+                   '  if (sse_tsv_format_f32(v, 3, out, sizeof out, ends) != 0) return 1;\n'
+                   '  printf("%.*s %08x\\n", (int)ends[2], out, sse_crc32c("123456789", 9, 0));\n'
+                   '  return strlen(sse_version()) == 0;\n}\n')
+    libdir = os.path.join(repo, "sequence-semantic-embedding_b200")
+    exe = str(tmp_path / "use_c")
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(repo, "include"), str(src), "-o", exe, "-L", libdir, "-l:libsse_b200.so",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["0.11e-051.234567e+06", "e3069283"]
