@@ -17,7 +17,7 @@
  *   - plain pointers and sizes only.  "dev" pointers are CUDA device pointers
  *     on the handle's device (e.g. torch.Tensor.data_ptr()); "host" pointers are
  *     ordinary (ideally pinned) host memory.  The caller owns every buffer it
- *     passes; the library owns weights, optimizer slots, workspaces, the bf16
+ *     passes; the library owns weights, optimizer slots, workspaces, the fp16
  *     copy of the index.
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls
  *     taking a stream are asynchronous on it; *_host calls synchronise before
@@ -52,7 +52,7 @@ extern "C" {
 
 /* arithmetic of the tensor-core paths (the SIMT fp32 path is always available) */
 #define SSE_PRECISION_FP32  0   /* every kernel in fp32 SIMT (exact mode)              */
-#define SSE_PRECISION_TC    1   /* bf16 tcgen05 scan + exact fp32 re-rank; encoder per tc_encoder */
+#define SSE_PRECISION_TC    1   /* fp16-operand tcgen05 scan + exact fp32 re-rank; fp16-operand tcgen05 encoders */
 
 #define SSE_SIDE_SRC 0
 #define SSE_SIDE_TGT 1
@@ -123,7 +123,7 @@ int sse_encode_host(sse_handle* h, int side, const int32_t* tokens_host, int B, 
 /* ---- index + retrieval --------------------------------------------------- */
 /* replaces Evaluator.__init__'s targetEncodings matrix (sse_evaluator.py:80-92):
  * registers this rank's shard of the target index.  tgt: fp32 [N_local, E],
- * host or device; the library keeps its own fp32 copy (and a bf16 copy for the
+ * host or device; the library keeps its own fp32 copy (and an fp16 copy for the
  * tensor-core scan).  global_offset = global id of local row 0. */
 int sse_index_set(sse_handle* h, const float* tgt, int64_t n_local, int64_t global_offset);
 /* encode this rank's target rows straight into the resident index

@@ -1,0 +1,27 @@
+"""Probe (not a test, not a benchmark): the tcgen05 scan under different work decompositions (environment knobs of
+search_tc.cu), one subprocess per configuration because the knobs are read once per process.
+usage: python scripts/scan_configs.py [QxN ...]"""
+import os, subprocess, sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+shapes = sys.argv[1:] or ["600x1000000", "4800x125000"]
+CONFIGS = [
+    ("auto", {}),
+    ("pack0", {"SSE_SCAN_PACK": "0"}),
+    ("pack1", {"SSE_SCAN_PACK": "1"}),
+    ("tn64", {"SSE_SCAN_ACC1": "0"}),
+    ("mtg1", {"SSE_SCAN_MTG": "1"}),
+    ("cluster", {"SSE_SCAN_CLUSTER": "1"}),
+    ("cluster mtg1", {"SSE_SCAN_CLUSTER": "1", "SSE_SCAN_MTG": "1"}),
+]
+only = os.environ.get("SCAN_CONFIGS")
+for name, env in CONFIGS:
+    if only and name not in only.split(","):
+        continue
+    e = dict(os.environ); e.update(env)
+    print("#### %s %s" % (name, env), flush=True)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "search_probe.py")] + shapes, env=e, capture_output=True, text=True, timeout=180)
+        out = [l for l in r.stdout.splitlines() if "Q=" in l]
+        print("\n".join(out) if out else "FAILED rc=%d: %s" % (r.returncode, (r.stderr or "")[-600:]), flush=True)
+    except subprocess.TimeoutExpired:
+        print("TIMEOUT", flush=True)

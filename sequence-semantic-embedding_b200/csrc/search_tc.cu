@@ -17,8 +17,8 @@
 //                        fp32 index, sort by (score desc, idx asc), emit k
 //   6. fallback          rows whose candidate lists overflowed (pathological ties)
 //                        are recomputed by brute force in fp32
-// Exactness: |approx - exact| <= eps_r = 0.0045*|q_r|*max|t| (fp16 operand rounding,
-// fp32 accumulate).  Every exact top-k element has approx >= A_k - 2 eps >= tau, so it
+// Exactness: |approx - exact| <= eps_r = EPS_REL*|q_r|*max|t|, EPS_REL = 0.0011 (fp16 operand rounding 2*2^-11
+// plus fp32 accumulation slack; derivation next to EPS_REL).  Every exact top-k element has approx >= A_k - 2 eps >= tau, so it
 // survives 4 and 5; the final order/scores come from fp32 arithmetic only.
 //
 // GEMM mapping: queries are the A operand (M = 128 rows per m-tile, 1 or 2 m-tiles
@@ -37,12 +37,21 @@ namespace {
 constexpr int TILE_M = 128;          // query rows per m-tile
 constexpr int KBLK = 64;             // fp16 elements per 128-byte swizzle row
 constexpr int CAND_CAP = 128;        // candidates per (CTA item, row); compacted in-kernel when fewer than 32 slots remain
-constexpr int MAX_GROUPS = 32;
+constexpr int MAX_GROUPS = 64;
 constexpr int DBG_N = 12;            // debug cycle counters per work item
 constexpr int SCAN_THREADS = 384;
 constexpr int FIN_MAXC = 2048;       // candidates per row the finalize kernel can sort
 constexpr int FIN_MAXR = 256;        // candidates per row re-scored exactly
-constexpr float EPS_REL = 0.0011f;   // fp16 x fp16 dot error bound / (|q| |t|): 2*2^-11 + fp32 accumulation slack
+// Bound of |fp16-operand dot - exact dot| / (|q| |t|), valid for every supported E (<= 512):
+//   operand rounding: q_i(1+a_i) t_i(1+b_i), |a_i|,|b_i| <= u = 2^-11  ->  sum |q_i t_i| (2u + u^2) <= (2u + u^2) |q||t|
+//                     = 0.000977 |q||t|                                   (Cauchy-Schwarz);
+//   fp32 accumulation in the tensor core: E/16 k-steps, each adding a 16-term partial sum: <= (E/16 + 16) 2^-23 |q||t|
+//                     = 5.8e-6 at E = 512 (2.0e-6 at 256);
+//   fp16 subnormal index elements (|t_i| < 6.1e-5, absolute rounding error <= 2^-25): <= sqrt(E) 2^-25 |q| = 6.8e-7 |q|
+//                     at E = 512 -- negligible for the normalised index rows the path produces (|t| = 1).  Queries
+//                     are rescaled to max |q_i| in [0.5, 1) (prep_queries_kernel), so they have no subnormal issue.
+// Sum < 0.000985; EPS_REL = 0.0011 leaves > 10 % slack at E = 512.
+constexpr float EPS_REL = 0.0011f;
 
 enum { MODE_TILEMAX = 0, MODE_FILTER = 1 };
 
@@ -57,7 +66,11 @@ struct ScanParams {
   long long* dbg;                  // optional [items][DBG_N] cycle counters (nullptr = off)
   int dbg_flags;                   // timing experiments only: 1 = no TMA loads, 2 = no MMA issue
   int use3d;                       // one 3-D TMA instruction per index tile (else KB 2-D loads)
-  int group_first_item[MAX_GROUPS];
+  int cs;                          // CTAs per thread-block cluster (1 = no cluster): the CTAs of a cluster hold
+                                   // different m-groups and sweep the SAME tile range; every index tile is fetched
+                                   // once by the cluster leader and TMA-multicast into all cs shared memories
+  int R;                           // clusters per super-group (a super-group = cs consecutive m-groups)
+  int group_first_item[MAX_GROUPS];  // cs == 1: items of group g are [first, first + items)
   int group_items[MAX_GROUPS];
   int group_mt[MAX_GROUPS];        // valid m-tiles in the group
   int n_j;                         // tiles visited: tile = tile_base + j * tile_step, j in [0, n_j)
@@ -309,19 +322,91 @@ __device__ __forceinline__ int chunk_filter(const uint32_t (&v)[32], float thr, 
   return cnt;
 }
 
-template <int MODE, int KBT, int TNT>
+// ---- cluster helpers (multicast variant)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar), "r"(rank)
+      : "memory");
+}
+// wait on a local mbarrier whose arrivals come from other CTAs of the cluster
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 32) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (backoff_ns) __nanosleep(backoff_ns);
+    if ((spins & 0xfff) == 0xfff) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+// MODE: tile maxima (sample pass) or threshold filter.  KBT / TNT: compile-time E/64 and tile width (0 = run-time).
+// ACC1: accumulator scheme.  false: one [mt_count x TN] accumulator set per tile, double-buffered over tiles (one commit
+// per tile).  true (two m-tiles, TN = 128): ONE accumulator per m-tile; the MMAs of m-tile 1 run while the epilogue
+// drains m-tile 0 and vice versa (one commit per m-tile), which buys 128-column tiles -- half the MMA instructions and
+// commits per flop -- inside the same 512 TMEM columns.
+template <int MODE, int KBT, int TNT, bool ACC1>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant__ ScanParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- which item
+  // ---- which item: cluster `cid` = (super-group sg, tile range r_in_g); CTA `rank` of the cluster owns m-group sg*cs+rank
   const int item = blockIdx.x;
-  int g = 0;
-  while (g + 1 < P.n_groups && item >= P.group_first_item[g + 1]) ++g;
-  const int r_in_g = item - P.group_first_item[g];
-  const int R = P.group_items[g];
+  const int cs = P.cs;
+  const uint32_t rank = cs > 1 ? cluster_ctarank() : 0u;
+  int g, r_in_g, R;
+  if (cs > 1) {
+    const int cid = item / cs;
+    R = P.R;
+    const int sg = cid / R;
+    r_in_g = cid - sg * R;
+    g = sg * cs + (int)rank;
+  } else {
+    g = 0;
+    while (g + 1 < P.n_groups && item >= P.group_first_item[g + 1]) ++g;
+    r_in_g = item - P.group_first_item[g];
+    R = P.group_items[g];
+  }
   const int mt_count = P.group_mt[g];
   const int j0 = (int)(((int64_t)P.n_j * r_in_g) / R);
   const int j1 = (int)(((int64_t)P.n_j * (r_in_g + 1)) / R);
@@ -332,18 +417,19 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
 
   uint8_t* b_smem = smem;                                // [NG] slots x [KB] sub-tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)NG * slot_bytes);
-  // bars: full[NG], empty[NG], a_full, acc_full[2], acc_empty[2]
+  // bars: full[NG], empty[NG], a_full, acc_full[2], acc_empty[2], cl_empty[NG]
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + NG);
   const uint32_t bar_a = smem_u32(bars + 2 * NG);
   const uint32_t bar_accf = smem_u32(bars + 2 * NG + 1);
   const uint32_t bar_acce = smem_u32(bars + 2 * NG + 3);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NG + 5);
+  const uint32_t bar_cle = smem_u32(bars + 2 * NG + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NG + 5);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < NG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_cle + 8 * s, (uint32_t)cs); }
     mbar_init(bar_a, mt_count * 4);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, mt_count * 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, ACC1 ? 4 : mt_count * 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -353,14 +439,17 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();     // every CTA's barriers exist before a peer arrives on them / multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_col0 = (uint32_t)P.a_cols;          // accumulators sit behind the query columns
 
   if (warp == 9) {
-    // ===== TMA producer: one whole index tile (KB sub-tiles) per ring slot, one barrier per slot =====
+    // ===== TMA producer.  Every CTA arms its own full barrier for the slot once its consumers released it and tells the
+    // cluster leader; the leader issues ONE multicast load per tile when all cs CTAs are ready (cs == 1: plain load).
     if (j1 > j0) {     // whole warp, converged; one elected lane issues
-      long long w_empty = 0, t_begin = clock64();
+      long long w_empty = 0, w_cl = 0, t_begin = clock64();
+      const uint16_t mask = (uint16_t)((1u << cs) - 1u);
       for (int j = j0; j < j1; ++j) {
         const int jj = j - j0;
         const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
@@ -371,21 +460,31 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
             mbar_arrive(bar_full + 8 * s);
           } else {
             mbar_expect_tx(bar_full + 8 * s, slot_bytes);
-            if (P.use3d) {
-              tma_load_3d(smem_u32(b_smem + (size_t)s * slot_bytes), &tmap_idx, bar_full + 8 * s, 0, tile * TN, 0);
-            } else {
-              for (int kb = 0; kb < KB; ++kb)
-                tma_load_2d(smem_u32(b_smem + (size_t)s * slot_bytes + (size_t)kb * kb_bytes), &tmap_idx, bar_full + 8 * s,
-                            kb * KBLK, tile * TN);
-            }
+            if (cs > 1) mbar_arrive_remote(bar_cle + 8 * s, 0);
           }
         }
         __syncwarp();
+        if (!(P.dbg_flags & 1) && rank == 0) {
+          if (cs > 1) { long long t = clock64(); mbar_wait_cluster(bar_cle + 8 * s, ph, 64); w_cl += clock64() - t; }
+          if (elect_one_sync()) {
+            const uint32_t dst = smem_u32(b_smem + (size_t)s * slot_bytes);
+            if (P.use3d) {
+              if (cs > 1) tma_load_3d_mc(dst, &tmap_idx, bar_full + 8 * s, 0, tile * TN, 0, mask);
+              else tma_load_3d(dst, &tmap_idx, bar_full + 8 * s, 0, tile * TN, 0);
+            } else {
+              for (int kb = 0; kb < KB; ++kb) {
+                if (cs > 1) tma_load_2d_mc(dst + (uint32_t)kb * kb_bytes, &tmap_idx, bar_full + 8 * s, kb * KBLK, tile * TN, mask);
+                else tma_load_2d(dst + (uint32_t)kb * kb_bytes, &tmap_idx, bar_full + 8 * s, kb * KBLK, tile * TN);
+              }
+            }
+          }
+          __syncwarp();
+        }
       }
-      if (P.dbg && lane == 0) { P.dbg[item * DBG_N + 0] = w_empty; P.dbg[item * DBG_N + 1] = clock64() - t_begin; }
+      if (P.dbg && lane == 0) { P.dbg[item * DBG_N + 0] = w_empty; P.dbg[item * DBG_N + 1] = clock64() - t_begin; P.dbg[item * DBG_N + 11] = w_cl; }
     }
   } else if (warp == 8) {
-    // ===== MMA issuer (one thread): all MMAs of a tile back to back, ONE tcgen05.commit per tile =====
+    // ===== MMA issuer (one thread): all MMAs of an accumulator back to back, ONE tcgen05.commit per accumulator =====
     if (j1 > j0) {     // whole warp, converged; one elected lane issues
       const uint32_t idesc = make_idesc_f16(TILE_M, TN);
       long long w_full = 0, w_acce = 0, w_a = 0, t_begin = clock64();
@@ -396,39 +495,44 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         const int buf = jj & 1;
         const uint32_t use = (uint32_t)(jj >> 1);
         const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
-        mbar_wait_timed(bar_acce + 8 * buf, (use & 1) ^ 1, w_acce);
+        if (!ACC1) mbar_wait_timed(bar_acce + 8 * buf, (use & 1) ^ 1, w_acce);
         mbar_wait_timed(bar_full + 8 * s, ph, w_full);
-        tc_fence_after();
-        if (elect_one_sync()) {
-         if (!(P.dbg_flags & 2)) {
-          const uint64_t bd0 = make_sw128_desc(smem_u32(b_smem + (size_t)s * slot_bytes));
-          const uint32_t bd_lo = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
-          const uint32_t kb_units = kb_bytes >> 4;           // descriptor address units (16 B) per k-block
+        const uint64_t bd0 = make_sw128_desc(smem_u32(b_smem + (size_t)s * slot_bytes));
+        const uint32_t bd_lo = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
+        const uint32_t kb_units = kb_bytes >> 4;           // descriptor address units (16 B) per k-block
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            if (mt < mt_count) {
-              const uint32_t d = tmem_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
-              const uint32_t a0 = tmem_base + (uint32_t)(mt * (E / 2));
-              if (KBT > 0) {
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt < mt_count) {
+            if (ACC1) mbar_wait_timed(bar_acce + 8 * mt, ((uint32_t)jj & 1) ^ 1, w_acce);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              if (!(P.dbg_flags & 2)) {
+                const uint32_t d = tmem_base + acc_col0 + (uint32_t)(ACC1 ? mt * TN : (buf * P.mtg + mt) * TN);
+                const uint32_t a0 = tmem_base + (uint32_t)(mt * (E / 2));
+                if (KBT > 0) {
 #pragma unroll
-                for (int kb = 0; kb < (KBT > 0 ? KBT : 1); ++kb)
+                  for (int kb = 0; kb < (KBT > 0 ? KBT : 1); ++kb)
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4)   // 4 x (K=16): A advances 8 columns, B 32 bytes (= 2 descriptor units)
-                    tc_mma_f16_ts2(d, a0 + (uint32_t)(kb * (KBLK / 2) + 8 * k4), bd_lo + (uint32_t)kb * kb_units + 2 * k4, bd_hi, idesc,
-                                   (kb | k4) ? 1u : 0u);
-              } else {
-                for (int kb = 0; kb < KB; ++kb)
+                    for (int k4 = 0; k4 < 4; ++k4)   // 4 x (K=16): A advances 8 columns, B 32 bytes (= 2 descriptor units)
+                      tc_mma_f16_ts2(d, a0 + (uint32_t)(kb * (KBLK / 2) + 8 * k4), bd_lo + (uint32_t)kb * kb_units + 2 * k4, bd_hi, idesc,
+                                     (kb | k4) ? 1u : 0u);
+                } else {
+                  for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4)
-                    tc_mma_f16_ts2(d, a0 + (uint32_t)(kb * (KBLK / 2) + 8 * k4), bd_lo + (uint32_t)kb * kb_units + 2 * k4, bd_hi, idesc,
-                                   (kb | k4) ? 1u : 0u);
+                    for (int k4 = 0; k4 < 4; ++k4)
+                      tc_mma_f16_ts2(d, a0 + (uint32_t)(kb * (KBLK / 2) + 8 * k4), bd_lo + (uint32_t)kb * kb_units + 2 * k4, bd_hi, idesc,
+                                     (kb | k4) ? 1u : 0u);
+                }
               }
+              if (ACC1) tc_commit(bar_accf + 8 * mt);
             }
+            __syncwarp();
           }
-         }
-         tc_commit(bar_accf + 8 * buf);      // accumulators complete == this ring slot fully read
         }
-        __syncwarp();
+        if (!ACC1) {
+          if (elect_one_sync()) tc_commit(bar_accf + 8 * buf);      // accumulators complete == this ring slot fully read
+          __syncwarp();
+        }
       }
       if (P.dbg && lane == 0) { P.dbg[item * DBG_N + 2] = w_full; P.dbg[item * DBG_N + 3] = w_acce; P.dbg[item * DBG_N + 4] = clock64() - t_begin; P.dbg[item * DBG_N + 5] = w_a; }
     }
@@ -469,23 +573,25 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         my_i = P.cand_i + base;
       }
       const int n_chunks = TN / 32;
+      // the warp that hands the ring slot back: all MMAs of the tile have retired once the LAST accumulator's commit fired
+      const bool releases_slot = ACC1 ? (e == 4 * (mt_count - 1)) : (e == 0);
       long long w_accf = 0, w_ld = 0, w_cmp = 0, t_begin = clock64();
       for (int j = j0; j < j1; ++j) {
         const int jj = j - j0;
-        const int buf = jj & 1;
-        const uint32_t use = (uint32_t)(jj >> 1);
+        const int buf = ACC1 ? mt : (jj & 1);
+        const uint32_t use = ACC1 ? (uint32_t)jj : (uint32_t)(jj >> 1);
         const int tile = j * P.tile_step;
         const int64_t col0 = (int64_t)tile * TN;
         const bool ragged = col0 + TN > P.N;
         mbar_wait_timed(bar_accf + 8 * buf, use & 1, w_accf);
         tc_fence_after();
         // the MMAs of this tile have retired: hand its ring slot back to the TMA producer
-        if (e == 0 && lane == 0) mbar_arrive(bar_empty + 8 * ((uint32_t)jj % NG));
-        const uint32_t taddr = lane_base + acc_col0 + (uint32_t)((buf * P.mtg + mt) * TN);
+        if (releases_slot && lane == 0) mbar_arrive(bar_empty + 8 * ((uint32_t)jj % NG));
+        const uint32_t taddr = lane_base + acc_col0 + (uint32_t)(ACC1 ? mt * TN : (buf * P.mtg + mt) * TN);
         float tmax = -CUDART_INF_F;
         // 64 accumulator columns per round: both TMEM loads in flight together; after the last round's data has
         // landed in registers the accumulator buffer goes straight back to the MMA warp, and the compares run
-        // from registers while the next-but-one tile's MMAs already overwrite it.
+        // from registers while the next MMAs already overwrite it.
 #pragma unroll 1
         for (int ch = 0; ch < n_chunks; ch += 2) {
           uint32_t va[32], vb[32];
@@ -533,6 +639,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();     // no CTA leaves while a peer may still arrive on its barriers
   if (warp == 10) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -549,16 +656,33 @@ __device__ __forceinline__ int padded_to_query_row(int p, int gstride, int rpg, 
   return (l < rpg && r < Q) ? r : -1;
 }
 
-// q fp32 [Q,E] -> fp16 [Qp,E] in padded row order (unused rows zero), qnorm[Qp]
+// q fp32 [Q,E] -> fp16 [Qp,E] in padded row order (unused rows zero), qnorm[Qp].
+// Every row is scaled by an exact power of two so that its largest element lands in [0.5, 1) before the fp16
+// conversion: un-normalised sources (sse_demo.py:123) whose elements exceed the fp16 range (65504) or sit in its
+// subnormal range keep full fp16 relative precision.  The scan works in the scaled units throughout (qnorm, tau,
+// margin and the candidates' approximate scores all carry the same factor; finalize re-scores in fp32 from the
+// original q), so the scaling never reaches the results.
 __global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, int gstride, int rpg,
                                     __half* __restrict__ qb, float* __restrict__ qnorm) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= Qp) return;
   const int qr = padded_to_query_row(row, gstride, rpg, Q);
+  float mx = 0.f;
+  if (qr >= 0)
+    for (int j = lane; j < E; j += 32) mx = fmaxf(mx, fabsf(q[(size_t)qr * E + j]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float scale = 1.f;
+  if (mx > 0.f && mx < CUDART_INF_F) {
+    int ex;
+    frexpf(mx, &ex);                       // mx = m * 2^ex, m in [0.5, 1)
+    ex = max(-100, min(100, ex));
+    scale = ldexpf(1.f, -ex);
+  }
   float ss = 0.f;
   for (int j = lane; j < E; j += 32) {
-    float v = qr >= 0 ? q[(size_t)qr * E + j] : 0.f;
+    float v = qr >= 0 ? q[(size_t)qr * E + j] * scale : 0.f;
     ss = fmaf(v, v, ss);
     qb[(size_t)row * E + j] = __float2half_rn(v);
   }
@@ -626,7 +750,8 @@ __global__ void select_tau_kernel(const float* __restrict__ tilemax, int n_s, in
 struct FinParams {
   int n_groups, mtg;
   int rpg;                 // query rows per m-group
-  int group_first_item[MAX_GROUPS];
+  int cs, R;               // cluster scan layout: item of (group g, range it) = ((g / cs) * R + it) * cs + g % cs
+  int group_first_item[MAX_GROUPS];   // cs == 1: items of group g are [first, first + items)
   int group_items[MAX_GROUPS];
   const float* cand_s;
   const int32_t* cand_i;
@@ -672,12 +797,13 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   const int tid = threadIdx.x;
   const int rows_per_group = P.mtg * TILE_M;
   const int g = row / P.rpg, lrow = row % P.rpg;
-  const int first = P.group_first_item[g], R = P.group_items[g];
+  const int R = P.cs > 1 ? P.R : P.group_items[g];
+  const int first = P.cs > 1 ? (g / P.cs) * P.R * P.cs + g % P.cs : P.group_first_item[g], istride = P.cs;
   if (tid == 0) { s_total = 0; s_over = 0; }
   __syncthreads();
   // gather candidates (one item at a time per thread; counts are small)
   for (int it = tid; it < R; it += blockDim.x) {
-    size_t slot = (size_t)(first + it) * rows_per_group + lrow;
+    size_t slot = (size_t)(first + it * istride) * rows_per_group + lrow;
     int c = P.cand_cnt[slot];
     if (c > CAND_CAP) { atomicExch(&s_over, 1); c = CAND_CAP; }
     int at = atomicAdd(&s_total, c);
@@ -874,6 +1000,13 @@ void search_tc_release(TcIndex& ti) {
   ti.h16 = nullptr; ti.N = 0; ti.E = 0; ti.tmap_ok = false;
 }
 
+int search_tc_max_rows(int E) { (void)E; return TILE_M * MAX_GROUPS; }   // one m-tile per group in the worst case
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
               float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches) {
   if (Q <= 0) return SSE_OK;
@@ -881,24 +1014,57 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   const int64_t N = ti.N;
   const int KB = E / KBLK;
   const int m_tiles = cdiv(Q, TILE_M);
-  // TMEM budget (512 columns): queries mtg*E/2  +  accumulators mtg * 2 buffers * tn
-  int mtg = (m_tiles >= 2 && E <= 256) ? 2 : 1;
+  const size_t ring_cap = 232448 - 1024 - 512;
+  // ---- work decomposition (knobs for experiments: SSE_SCAN_MTG / _ACC1 / _CLUSTER / _CS / _PACK)
+  // m-tiles per CTA.  TMEM budget (512 columns): queries mtg*E/2 + accumulators.  Two m-tiles per CTA make one index
+  // tile feed 256 query rows (half the shared-memory fill per flop); their accumulators are either 2 x 2 x 64 columns
+  // (64-column tiles, double-buffered over tiles) or -- ACC1, the default -- ONE 128-column accumulator per m-tile,
+  // the two m-tiles double-buffering each other.  Measured at 600 x 1M (whole search, round 2): 64-column tiles 0.379 ms,
+  // ACC1 0.327 ms; one m-tile per CTA with double-buffered 128-column tiles 0.334 ms (0.453 vs 0.342 ms at 2400 x 250k).
+  static const int env_mtg = env_int("SSE_SCAN_MTG", 0), env_cs = env_int("SSE_SCAN_CS", 0), env_acc1 = env_int("SSE_SCAN_ACC1", -1);
+  // Thread-block clusters (SSE_SCAN_CLUSTER=1): cs CTAs holding consecutive m-groups sweep the same tile range and share
+  // ONE multicast TMA load per index tile.  Correct and tested, but measured SLOWER than unicast loads with L2 sharing
+  // (600 x 1M: 0.338 vs 0.327 ms with ACC1, 0.421 vs 0.334 ms with one m-tile per CTA and cs = 5): the per-tile handshake
+  // (all CTAs release the slot -> leader issues -> data lands) adds latency a 3-slot ring cannot hide, the L2->SM fabric
+  // was not the limiter (7.7 TB/s measured in the unicast one-m-tile configuration), and GPC granularity leaves SMs idle.
+  static const bool env_cluster = env_int("SSE_SCAN_CLUSTER", 0) != 0;
+  int mtg = (E > 256 || m_tiles == 1) ? 1 : (env_mtg ? std::min(env_mtg, 2) : ((m_tiles == 2 || m_tiles >= 4) ? 2 : 1));
+  bool acc1 = false;
+  int tn;
+  if (mtg == 2) {
+    acc1 = env_acc1 != 0 && E + 2 * 128 <= 512 && (size_t)3 * 128 * E * 2 <= ring_cap;
+    tn = acc1 ? 128 : 64;
+  } else {
+    tn = (E / 2 + 2 * 128 <= 512 && (size_t)3 * 128 * E * 2 <= ring_cap) ? 128 : 64;
+  }
   const int a_cols = mtg * E / 2;
-  // tile width: 128 index rows when TMEM (512 columns) and a >=3-deep ring allow it, else 64
-  const int tn = (a_cols + mtg * 2 * 128 <= 512 && 3 * 128 * E * 2 <= 232448 - 2048) ? 128 : 64;
-  const int n_groups = cdiv(m_tiles, mtg);
-  if (n_groups > MAX_GROUPS) { set_error("search_tc: Q=%d too large for one call (max %d rows)", Q, MAX_GROUPS * 2 * TILE_M); return SSE_EINVAL; }
+  const int n_groups0 = cdiv(m_tiles, mtg);
+  int cs = 1, nsg = n_groups0;
+  if (env_cluster && n_groups0 > 1) {
+    if (n_groups0 <= 8) { cs = n_groups0; nsg = 1; }
+    else {
+      int best_pad = 1 << 30;
+      for (int c = 8; c >= 4; --c) {
+        int pad = cdiv(n_groups0, c) * c - n_groups0;
+        if (pad < best_pad) { best_pad = pad; cs = c; }
+      }
+      nsg = cdiv(n_groups0, cs);
+    }
+    if (env_cs > 0 && env_cs <= 8) { cs = env_cs; nsg = cdiv(n_groups0, cs); }
+  }
+  const int n_groups = nsg * cs;
+  if (n_groups > MAX_GROUPS) { set_error("search_tc: Q=%d too large for one call (max %d rows)", Q, search_tc_max_rows(E)); return SSE_EINVAL; }
   const int Qp = n_groups * mtg * TILE_M;
   const int gstride = mtg * TILE_M;                 // padded rows per group
   // Row packing.  "full": groups of gstride rows, the last one holds the remainder and may need fewer m-tiles (600
   // rows -> 256 + 256 + 88: five m-tiles of MMA work instead of six); the groups then get work items in proportion to
   // their per-tile cost.  "equal": every group holds cdiv(Q, n_groups) rows, all groups cost the same and sweep
-  // identical tile ranges in lock-step (index fetched from HBM once; 1.03x measured).  Full packing pays when it
-  // removes >= 10 % of the m-tiles (measured: Q=600 0.383 -> 0.359 ms, Q=257 0.131 -> 0.128; but Q=2400, where it
-  // saves 1 m-tile in 20 and the odd group breaks the lock-step L2 sharing, 0.367 -> 0.426).  SSE_SCAN_PACK=0/1 forces.
-  static const int pack_env = getenv("SSE_SCAN_PACK") ? atoi(getenv("SSE_SCAN_PACK")) : -1;
+  // identical tile ranges in lock-step (their re-reads of a tile hit L2).  Full packing pays when it removes >= 10 % of
+  // the m-tiles (round 1: Q=600 0.383 -> 0.359 ms; but Q=2400, where it saves 1 m-tile in 20 and the odd group breaks
+  // the lock-step L2 sharing, 0.367 -> 0.426).  SSE_SCAN_PACK=0/1 forces.  Clusters always pack equally.
+  static const int pack_env = env_int("SSE_SCAN_PACK", -1);
   const int mt_last_full = cdiv(Q - (n_groups - 1) * gstride, TILE_M);
-  const bool pack_full = pack_env >= 0 ? pack_env != 0 : (mtg - mt_last_full) * 10 >= n_groups * mtg;
+  const bool pack_full = cs == 1 && (pack_env >= 0 ? pack_env != 0 : (mtg - mt_last_full) * 10 >= n_groups * mtg);
   const int rpg = pack_full ? gstride : cdiv(Q, n_groups);   // query rows per group (the last group may hold fewer)
   const int n_tiles = (int)cdiv64(N, tn);
   // sample = every 16th tile: tau = k-th largest sampled tile maximum - 2 eps keeps ~16 k candidates per query
@@ -907,47 +1073,88 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   static const int sample_div = getenv("SSE_SCAN_SAMPLE_DIV") ? std::max(1, atoi(getenv("SSE_SCAN_SAMPLE_DIV"))) : 16;
   int n_s = (int)(N / sample_div / tn);
   if (n_s < 64) n_s = 64;
+  if (n_s < 2 * k) n_s = 2 * k;
   if (n_s > 1024) n_s = 1024;
   if (n_s > n_tiles) n_s = n_tiles;
   const int s_step = n_tiles / n_s;
 
   // shared memory = the TMA ring only: NS slots of one whole [tn x E] fp16 index tile each
   const size_t stage_bytes = (size_t)tn * E * 2;
-  int NS = (int)((232448 - 1024 - 512) / stage_bytes);
+  int NS = (int)(ring_cap / stage_bytes);
   if (NS > 16) NS = 16;
   if (NS < 2) { set_error("search_tc: E=%d does not fit the shared-memory ring", E); return SSE_EINVAL; }
   const size_t smem = 1024 + (size_t)NS * stage_bytes + 512;
 
-  // items: split ~num_sms CTAs over groups in proportion to their m-tile count
+  // specialised instances for the common E = 256 (fully unrolled MMA issue), generic otherwise
+  typedef void (*scan_fn)(const CUtensorMap, const ScanParams);
+  scan_fn fn_tilemax, fn_filter;
+  if (KB == 4 && tn == 64) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 64, false>; fn_filter = scan_kernel<MODE_FILTER, 4, 64, false>; }
+  else if (KB == 4 && tn == 128 && !acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 128, false>; fn_filter = scan_kernel<MODE_FILTER, 4, 128, false>; }
+  else if (KB == 4 && tn == 128 && acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 128, true>; fn_filter = scan_kernel<MODE_FILTER, 4, 128, true>; }
+  else if (acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0, true>; fn_filter = scan_kernel<MODE_FILTER, 0, 0, true>; }
+  else { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0, false>; fn_filter = scan_kernel<MODE_FILTER, 0, 0, false>; }
+  SSE_CUDA_OK(cudaFuncSetAttribute(fn_tilemax, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  SSE_CUDA_OK(cudaFuncSetAttribute(fn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+
+  // clusters per super-group: fill the SM budget, but never more clusters than can be co-resident (one CTA per SM and
+  // the CTAs of a cluster share a GPC, so fewer than num_sms / cs clusters may fit)
+  cudaLaunchAttribute lattr[1];
+  cudaLaunchConfig_t lcfg;
+  memset(&lcfg, 0, sizeof(lcfg));
+  lcfg.blockDim = dim3(SCAN_THREADS, 1, 1);
+  lcfg.dynamicSmemBytes = smem;
+  lcfg.stream = st;
+  lcfg.numAttrs = 0;
+  if (cs > 1) {
+    lattr[0].id = cudaLaunchAttributeClusterDimension;
+    lattr[0].val.clusterDim.x = cs; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
+    lcfg.attrs = lattr;
+    lcfg.numAttrs = 1;
+  }
   ScanParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.n_groups = n_groups; sp.mtg = mtg; sp.kb = KB; sp.n_stages = NS; sp.tn = tn; sp.a_cols = a_cols;
   sp.N = N; sp.Qp = Qp; sp.global_offset = global_offset;
+  for (int g = 0; g < n_groups; ++g)
+    sp.group_mt[g] = std::max(1, std::min(mtg, cdiv(std::max(0, std::min(rpg, Q - g * rpg)), TILE_M)));
+  const int budget = std::max(num_sms, n_groups);
+  int R = std::max(1, budget / n_groups);
   int items = 0;
-  {
+  if (cs > 1) {
+    static std::map<std::pair<const void*, int>, int> max_clusters_cache;
+    auto key = std::make_pair((const void*)fn_filter, cs);
+    auto it = max_clusters_cache.find(key);
+    int max_cl = 0;
+    if (it != max_clusters_cache.end()) max_cl = it->second;
+    else {
+      lcfg.gridDim = dim3(cs * 32, 1, 1);
+      if (cudaOccupancyMaxActiveClusters(&max_cl, fn_filter, &lcfg) != cudaSuccess) { cudaGetLastError(); max_cl = 0; }
+      max_clusters_cache[key] = max_cl;
+    }
+    if (max_cl > 0) R = std::max(1, std::min(R, max_cl / nsg));
+    R = std::min(R, n_tiles);
+    items = nsg * R * cs;
+  } else {
     // groups with the same number of live m-tiles get the same number of work items with IDENTICAL tile ranges: the
     // CTAs of different groups that share a range run concurrently, so the index is fetched from HBM about once per
     // distinct item count and the other groups' reads of the same tiles hit L2.  A lighter last group (one live
-    // m-tile) gets fewer items, in proportion to its measured per-tile cost (feed + commit ~400 cycles, ~550 per m-tile).
-    int mt_of[MAX_GROUPS];
+    // m-tile) gets fewer items, in proportion to its per-tile cost (per m-tile MMA time + a small per-tile constant).
+    const double c_tile = acc1 ? 100.0 : 400.0, c_mt = acc1 ? 1100.0 : 550.0;
     double cost_sum = 0;
-    for (int g = 0; g < n_groups; ++g) {
-      mt_of[g] = std::max(1, std::min(mtg, cdiv(std::min(rpg, Q - g * rpg), TILE_M)));
-      cost_sum += 400.0 + 550.0 * mt_of[g];
-    }
-    const int budget = std::max(num_sms, n_groups);
+    for (int g = 0; g < n_groups; ++g) cost_sum += c_tile + c_mt * sp.group_mt[g];
     int first = 0;
     for (int g = 0; g < n_groups; ++g) {
-      int R = (int)((400.0 + 550.0 * mt_of[g]) / cost_sum * budget);
-      if (mt_of[g] == mtg) R = (int)((400.0 + 550.0 * mtg) / cost_sum * budget);     // identical for all full groups
-      R = std::max(1, std::min(R, n_tiles));
+      int Rg = (int)((c_tile + c_mt * sp.group_mt[g]) / cost_sum * budget);
+      Rg = std::max(1, std::min(Rg, n_tiles));
       sp.group_first_item[g] = first;
-      sp.group_items[g] = R;
-      sp.group_mt[g] = mt_of[g];
-      first += R;
+      sp.group_items[g] = Rg;
+      first += Rg;
     }
     items = first;
+    R = sp.group_items[0];
   }
+  sp.cs = cs; sp.R = R;
+  lcfg.gridDim = dim3(items, 1, 1);
 
   // workspace carve
   size_t off = 0;
@@ -980,18 +1187,9 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   sp.qb = qb;
   sp.use3d = ti.use3d ? 1 : 0;
 
-  // specialised instances for the common E = 256 (fully unrolled MMA issue), generic otherwise
-  typedef void (*scan_fn)(const CUtensorMap, const ScanParams);
-  scan_fn fn_tilemax, fn_filter;
-  if (KB == 4 && tn == 64) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 64>; fn_filter = scan_kernel<MODE_FILTER, 4, 64>; }
-  else if (KB == 4 && tn == 128) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 128>; fn_filter = scan_kernel<MODE_FILTER, 4, 128>; }
-  else { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0>; fn_filter = scan_kernel<MODE_FILTER, 0, 0>; }
-  SSE_CUDA_OK(cudaFuncSetAttribute(fn_tilemax, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  SSE_CUDA_OK(cudaFuncSetAttribute(fn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-
   // pass A: tile maxima over the strided sample
   sp.n_j = n_s; sp.tile_step = s_step; sp.tilemax = tm; sp.tau = nullptr;
-  fn_tilemax<<<items, SCAN_THREADS, smem, st>>>(tmi, sp);
+  SSE_CUDA_OK(cudaLaunchKernelEx(&lcfg, fn_tilemax, tmi, sp));
   if (launches) ++*launches;
   select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, gstride, rpg, qn, tnorm, tau, mg);
   if (launches) ++*launches;
@@ -1003,12 +1201,12 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   sp.cand_s = reinterpret_cast<float*>(w + o_cs);
   sp.cand_i = reinterpret_cast<int32_t*>(w + o_ci);
   sp.cand_cnt = reinterpret_cast<int32_t*>(w + o_cc);
-  fn_filter<<<items, SCAN_THREADS, smem, st>>>(tmi, sp);
+  SSE_CUDA_OK(cudaLaunchKernelEx(&lcfg, fn_filter, tmi, sp));
   if (launches) ++*launches;
 
   FinParams fp;
   memset(&fp, 0, sizeof(fp));
-  fp.n_groups = n_groups; fp.mtg = mtg; fp.rpg = rpg;
+  fp.n_groups = n_groups; fp.mtg = mtg; fp.rpg = rpg; fp.cs = cs; fp.R = R;
   for (int g = 0; g < n_groups; ++g) { fp.group_first_item[g] = sp.group_first_item[g]; fp.group_items[g] = sp.group_items[g]; }
   fp.cand_s = sp.cand_s; fp.cand_i = sp.cand_i; fp.cand_cnt = sp.cand_cnt; fp.margin = mg;
   fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E; fp.k = k;
@@ -1018,11 +1216,12 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
     cudaStreamSynchronize(st);
     cudaMemcpy(hd.data(), w + o_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
     const char* nm[DBG_N] = {"prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_acce", "mma_total", "mma_wait_a", "epi_wait_accf", "epi_total",
-                             "epi_tmem_ld", "epi_compare", "epi_cand_lane0", "-"};
-    for (int c = 0; c < 11; ++c) {
+                             "epi_tmem_ld", "epi_compare", "epi_cand_lane0", "lead_wait_peers"};
+    for (int c = 0; c < DBG_N; ++c) {
       long long mn = 1LL << 62, mx = 0, sm = 0;
       for (int i = 0; i < items; ++i) { long long v = hd[(size_t)i * DBG_N + c]; mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
-      fprintf(stderr, "[scan dbg] %-16s min %10lld avg %10lld max %10lld  (items %d, tiles/item ~%d, tn %d, NS %d)\n", nm[c], mn, sm / items, mx, items, n_tiles / items * n_groups, tn, NS);
+      fprintf(stderr, "[scan dbg] %-16s min %10lld avg %10lld max %10lld  (items %d = %d sg x %d clusters x cs %d, mtg %d acc1 %d, tiles/cluster ~%d, tn %d, NS %d)\n",
+              nm[c], mn, sm / items, mx, items, nsg, R, cs, mtg, (int)acc1, n_tiles / R, tn, NS);
     }
   }
   finalize_kernel<<<Q, 128, 0, st>>>(fp);

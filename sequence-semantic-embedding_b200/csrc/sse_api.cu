@@ -218,7 +218,7 @@ int search_device(sse_handle* h, const float* q, int Q, int k, float* scores, in
   }
   if (use_tc) {
     if (!h->tc.tmap_ok) SSE_TRY(search_tc_prepare(h->tc, h->index_f32, h->index_n, E, st, &h->launches));
-    const int maxq = 32 * 2 * 128;
+    const int maxq = search_tc_max_rows(E);
     for (int q0 = 0; q0 < Q; q0 += maxq) {
       int nq = std::min(maxq, Q - q0);
       SSE_TRY(search_tc(q + (size_t)q0 * E, nq, E, h->index_f32, h->tc, h->index_off, k, scores + (size_t)q0 * k,

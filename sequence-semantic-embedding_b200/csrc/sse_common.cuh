@@ -109,6 +109,7 @@ struct TcIndex {
   bool tmap_ok = false;
 };
 bool search_tc_supported(int E, int64_t N, int k);
+int search_tc_max_rows(int E);   // query rows one search_tc call accepts
 int search_tc_prepare(TcIndex& ti, const float* index_f32, int64_t N, int E, cudaStream_t st, int64_t* launches);
 void search_tc_release(TcIndex& ti);
 int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,

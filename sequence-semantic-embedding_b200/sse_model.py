@@ -72,11 +72,18 @@ class Saver(object):
         arrays["global_step"] = np.int64(gs)
         np.savez(prefix + ".npz", **arrays)
         d = os.path.dirname(prefix) or "."
+        # tf.train.Saver keeps ONE entry per checkpoint name: re-saving `...-BestEver` moves it to the newest
+        # position instead of filling the max_to_keep window with duplicates (which would later delete a file
+        # that newer entries still name)
+        if prefix in self._kept:
+            self._kept.remove(prefix)
         self._kept.append(prefix)
         while len(self._kept) > self.max_to_keep:
             old = self._kept.pop(0)
-            if os.path.exists(old + ".npz") and old != prefix:
-                os.remove(old + ".npz")
+            if old not in self._kept and old != prefix:
+                for ext in (".npz", ".index", ".data-00000-of-00001"):
+                    if os.path.exists(old + ext):
+                        os.remove(old + ext)
         with open(os.path.join(d, "checkpoint"), "w") as f:
             f.write('model_checkpoint_path: "%s"\n' % os.path.basename(prefix))
             for k in self._kept:

@@ -147,7 +147,7 @@ def test_tc_lstm_encode_within_tolerance(We, H, E, T, B, kern):
         want = O.encode(p, mode, name, tok, True)
         err = np.abs(got - want).max()
         assert err < TOL_TC, (name, err)
-        assert err > 0          # it really is the bf16 path, not the fp32 one
+        assert err > 0          # it really is the fp16-operand tensor-core path, not the fp32 one
         raw = h.encode_host(side, tok, False)
         wraw = O.encode(p, mode, name, tok, False)
         assert np.abs(raw - wraw).max() < 2e-2 * np.abs(wraw).max()
