@@ -150,6 +150,13 @@ int sse_merge_topk(sse_handle* h, const float* cand_scores_dev, const int32_t* c
  * classify route, 0 for demo/search/qna/crosslingual (sse_demo.py:123). */
 int sse_query_host(sse_handle* h, const int32_t* tokens_host, int Q, int k, int normalize,
                    float* scores_host, int32_t* idx_host);
+/* replaces model.predicted_tgts_score / model.predicted_labels (sse_model.py:286,344-350):
+ * tf.nn.top_k(similarity, TOP_N, sorted=True) of q [Q,E] against the BATCH's own target encodings tgt [n_tgt,E]
+ * (device pointers; nothing is registered, the resident index is untouched), ids = row numbers of tgt, ties -> lower
+ * index; normalize_scores = 1 applies l2_normalize(scores, 1) as :350 does.  n_tgt < k is TF's "input must have at
+ * least k columns" error. */
+int sse_topk_batch(sse_handle* h, const float* q_dev, int Q, const float* tgt_dev, int64_t n_tgt, int k,
+                   int normalize_scores, float* scores_dev, int32_t* idx_dev, void* stream);
 /* x * rsqrt(max(sum x^2, 1e-12)) over each row, in place (tf.nn.l2_normalize,
  * sse_model.py:282-283,350). */
 int sse_l2_normalize_rows(sse_handle* h, float* x_dev, int rows, int cols, void* stream);
@@ -177,6 +184,12 @@ int sse_lr_decay(sse_handle* h);
 int sse_get_scalars(sse_handle* h, float* learning_rate, int64_t* global_step);
 int sse_set_scalars(sse_handle* h, float learning_rate, int64_t global_step);
 
+/* Token ids outside [0, vocab_size) (TensorFlow's embedding_lookup raises InvalidArgument, sse_model.py:163-164):
+ * every encoder / train entry point checks the ids on the device; offenders are read as PAD_ID and counted.  Entry
+ * points that synchronise anyway (*_host, sse_index_build, train calls that return scalars) fail with SSE_EINVAL;
+ * after asynchronous calls this returns (and resets) the count seen so far -- it synchronises `stream`. */
+int sse_token_errors(sse_handle* h, int64_t* count_out, void* stream);
+
 /* ---- introspection for benchmarks / tests -------------------------------- */
 /* number of kernels this library launched on the handle since creation */
 int64_t sse_launch_count(sse_handle* h);
@@ -185,7 +198,8 @@ int64_t sse_launch_count(sse_handle* h);
  * lstm_kernel (tcgen05 encoder only): 0 auto, 1 weight-streaming kernel, 2 cluster kernel (weights resident in
  * the shared memory of a thread-block cluster), 3 cluster kernel with the input projection tabulated per
  * vocabulary entry (V x 4H fp32 table, rebuilt when parameters change; the default when it fits in 2 GiB);
- * pad_skip: 0 off, 1 on (host-token entry points only);  search_ctas: cap on the scan grid (0 = all SMs),
+ * pad_skip: 1 (default) rows are bucketed by their number of leading PADs on the device and every kernel tile starts
+ * from the tabulated pad-prefix state instead of running the PAD steps (all entry points), 0 off;  search_ctas: cap on the scan grid (0 = all SMs),
  * so that an encoder launched on another stream can run concurrently on the remaining SMs. */
 int sse_set_option(sse_handle* h, const char* key, int value);
 /* names + durations of the last timed kernels are not kept here: time with CUDA events on `stream`. */

@@ -45,6 +45,9 @@ struct LstmClParams {
   const float* bias_r;        // [4H] chunk-major, pre-scaled for the ex2 gate math (lstm_tc.cu prep_weights_kernel)
   const float* init_h;        // optional [H] broadcast initial state (pad-prefix table row)
   const float* init_c;
+  const int32_t* lead_sorted; // optional [B]: leading PADs of each (sorted) row -> per-tile start step (tok_prep.cu)
+  const float* pad_h;         // with lead_sorted: pad-prefix state table [T][H] (entry t = state after t+1 PADs)
+  const float* pad_c;
   float* h_out;               // [B, H] fp32 (last step)
   int B, T, t_start, We, H;
   long long* dbg;             // optional [grid][8] cycle counters
@@ -233,9 +236,18 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_c
   const int CL = P.H / 32;
   const uint32_t rank = cluster_ctarank();
   const int row0 = (blockIdx.x / CL) * CL_ROWS;
-  const int t0 = P.t_start;
+  // per-tile pad-prefix start (tok_prep.cu): rows are sorted by descending number of leading PADs, so the tile's LAST row
+  // has the shortest prefix; the tile starts at t0 from the tabulated state after t0 PADs
+  int t0 = P.t_start;
+  const float* init_h = P.init_h;
+  const float* init_c = P.init_c;
+  if (P.lead_sorted) {
+    t0 = min(__ldg(P.lead_sorted + min(row0 + CL_ROWS - 1, P.B - 1)), P.T - 1);
+    init_h = t0 > 0 ? P.pad_h + (size_t)(t0 - 1) * P.H : nullptr;
+    init_c = t0 > 0 ? P.pad_c + (size_t)(t0 - 1) * P.H : nullptr;
+  }
+  const bool has_init = init_h != nullptr;
   const int nsteps = P.T - t0;
-  const bool has_init = P.init_h != nullptr;
 
   // The A tiles hold 64 rows; every MMA still reads 128 rows per k-block, i.e. 8 KB past the tile: those bytes are
   // the next tile / the weight slices (finite fp16 bit patterns) and only feed accumulator lanes 64..127 nobody reads.
@@ -403,7 +415,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_c
     const int ub = half * 16;                      // first of this thread's units within the CTA slice
     float c[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) c[u] = has_init ? __ldg(P.init_c + rank * 32 + ub + u) : 0.f;
+    for (int u = 0; u < 16; ++u) c[u] = has_init ? __ldg(init_c + rank * 32 + ub + u) : 0.f;
     // row r of a slice: 64 bytes at r*64, 16-byte chunk c stored at c ^ ((r >> 1) & 3)  (SWIZZLE_64B)
     const uint32_t row_off64 = (uint32_t)(r * 64);
     const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
@@ -414,7 +426,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_c
         for (int j = 0; j < 4; ++j) {
           uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(P.init_h + q * 32 + j * 8 + 2 * e), __ldg(P.init_h + q * 32 + j * 8 + 2 * e + 1));
+          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(init_h + q * 32 + j * 8 + 2 * e), __ldg(init_h + q * 32 + j * 8 + 2 * e + 1));
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t1 + (uint32_t)q * SLICE_BYTES + (((uint32_t)j ^ sw64) * 16)),
                        "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
@@ -529,6 +541,11 @@ struct LstmP2Params {
   const float* ptable;        // [V, 4H] fp32, chunk-major, scaled, bias folded in
   const float* init_h;
   const float* init_c;
+  const int32_t* lead_sorted; // optional [B]: leading PADs of each (sorted) row -> per-tile start step (tok_prep.cu)
+  const float* pad_h;         // with lead_sorted: pad-prefix state table [T][H] (entry t = state after t+1 PADs)
+  const float* pad_c;
+  float* dump_h;              // optional [T][H]: row 0's state after every step (h as the fp16 value the recurrence carries, c fp32):
+  float* dump_c;              // run on one all-PAD row this IS the pad-prefix table of this kernel's own arithmetic
   float* h_out;               // [B, H]
   int B, T, t_start, H;
   int gate_math;              // 0: ex2/rcp form (8 MUFU per unit); 1: tanh.approx form (5 MUFU per unit) -- same accuracy on the
@@ -545,9 +562,18 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   const int CL = P.H / 32;
   const uint32_t rank = cluster_ctarank();
   const int row0 = (blockIdx.x / CL) * P2_ROWS;
-  const int t0 = P.t_start;
+  // per-tile pad-prefix start (tok_prep.cu): rows are sorted by descending number of leading PADs, so the tile's LAST row
+  // has the shortest prefix; the tile starts at t0 from the tabulated state after t0 PADs
+  int t0 = P.t_start;
+  const float* init_h = P.init_h;
+  const float* init_c = P.init_c;
+  if (P.lead_sorted) {
+    t0 = min(__ldg(P.lead_sorted + min(row0 + P2_ROWS - 1, P.B - 1)), P.T - 1);
+    init_h = t0 > 0 ? P.pad_h + (size_t)(t0 - 1) * P.H : nullptr;
+    init_c = t0 > 0 ? P.pad_c + (size_t)(t0 - 1) * P.H : nullptr;
+  }
+  const bool has_init = init_h != nullptr;
   const int nsteps = P.T - t0;
-  const bool has_init = P.init_h != nullptr;
 
   // h tile = 2*CL sub-slices of 16 hidden units: sub-slice m = units [16 m, 16 m + 16) = CTA m/2's pass m%2,
   // [128 rows x 32 B] fp16, SWIZZLE_32B K-major -- exactly the A operand of k-step m.
@@ -651,7 +677,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
     const uint32_t sw32 = (uint32_t)((r >> 2) & 1);            // SWIZZLE_32B: 16-byte chunk c of row r sits at c ^ ((r >> 2) & 1)
     float c[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) c[u] = has_init ? __ldg(P.init_c + rank * 32 + (u >> 3) * 16 + half * 8 + (u & 7)) : 0.f;
+    for (int u = 0; u < 16; ++u) c[u] = has_init ? __ldg(init_c + rank * 32 + (u >> 3) * 16 + half * 8 + (u & 7)) : 0.f;
     if (has_init) {
       // the broadcast initial state is the same for every row: each CTA fills its own tile 1 (= "step -1"), all sub-slices
       const uint32_t t1 = smem_u32(h_smem) + (uint32_t)(2 * CL * P2_SUB_BYTES) + row_off32;
@@ -659,7 +685,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
         for (int j = 0; j < 2; ++j) {
           uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(P.init_h + m * 16 + j * 8 + 2 * e), __ldg(P.init_h + m * 16 + j * 8 + 2 * e + 1));
+          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(init_h + m * 16 + j * 8 + 2 * e), __ldg(init_h + m * 16 + j * 8 + 2 * e + 1));
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t1 + (uint32_t)m * P2_SUB_BYTES + (((uint32_t)j ^ sw32) * 16)),
                        "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
@@ -730,6 +756,12 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
           const float ec = ex2_approx(fminf(c[u] * (2.f * NL2E), 57.f));
           hv[i] = (1.f - ec) * rcp_approx((1.f + ec) * (1.f + eo));
         }
+        if (P.dump_h && grow == 0) {        // pad-prefix table generation: the state this kernel itself carries past step t0 + s
+          float* dh = P.dump_h + (size_t)(t0 + s) * P.H + rank * 32 + p * 16 + half * 8;
+          float* dc = P.dump_c + (size_t)(t0 + s) * P.H + rank * 32 + p * 16 + half * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { dh[i] = __half2float(__float2half_rn(hv[i])); dc[i] = c[p * 8 + i]; }
+        }
         if (!last) {
           const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]), p2 = pack_f16x2(hv[4], hv[5]), p3 = pack_f16x2(hv[6], hv[7]);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_sub + (uint32_t)(p * P2_SUB_BYTES)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
@@ -793,11 +825,12 @@ __global__ void ptable_bias_kernel(const float* __restrict__ bias_r, int64_t V, 
 bool lstm_cluster_supported(int We, int H) { return We % 64 == 0 && We >= 64 && We <= 256 && (H == 64 || H == 128 || H == 256); }
 
 int lstm_forward_cluster(const int32_t* tokens, int B, int T, int t_start, const __half* emb_f16, int We, int H,
-                         const TcTower& tt, const float* init_h, const float* init_c, float* h_out, cudaStream_t st,
+                         const TcTower& tt, const float* init_h, const float* init_c, const PadSkip& ps, float* h_out, cudaStream_t st,
                          int64_t* launches) {
   if (B <= 0 || T - t_start <= 0) return SSE_OK;
   LstmClParams p;
   p.tokens = tokens; p.emb = emb_f16; p.bias_r = tt.bias_r; p.init_h = init_h; p.init_c = init_c; p.h_out = h_out;
+  p.lead_sorted = ps.lead_sorted; p.pad_h = ps.pad_h; p.pad_c = ps.pad_c;
   p.B = B; p.T = T; p.t_start = t_start; p.We = We; p.H = H; p.dbg = nullptr;
   p.dbg_flags = getenv("SSE_LSTM_CL_FLAGS") ? atoi(getenv("SSE_LSTM_CL_FLAGS")) : 0;
   const int CL = H / 32, KBx = We / KBLK, KBh = H / KBLK;
@@ -877,11 +910,12 @@ int lstm_ptable_prepare(TcTower& tt, const float* emb, int64_t V, const float* K
 }
 
 int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We, int H, const TcTower& tt, const float* init_h,
-                        const float* init_c, float* h_out, cudaStream_t st, int64_t* launches) {
+                        const float* init_c, const PadSkip& ps, float* h_out, cudaStream_t st, int64_t* launches) {
   if (B <= 0 || T - t_start <= 0) return SSE_OK;
   if (!tt.ptable_valid) { set_error("lstm_forward_ptable: table not prepared"); return SSE_ESTATE; }
   LstmP2Params p;
   p.tokens = tokens; p.ptable = tt.ptable; p.init_h = init_h; p.init_c = init_c; p.h_out = h_out;
+  p.lead_sorted = ps.lead_sorted; p.pad_h = ps.pad_h; p.pad_c = ps.pad_c; p.dump_h = ps.dump_h; p.dump_c = ps.dump_c;
   p.B = B; p.T = T; p.t_start = t_start; p.H = H; p.dbg = nullptr;
   p.gate_math = tt.ptable_mode;
   const int CL = H / 32, KBh = H / KBLK;

@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(
     const float* __restrict__ h_prev,   // nullptr => zero state (h = c = 0)
     float* __restrict__ h_next, float* __restrict__ c,
     const float* __restrict__ init_h, const float* __restrict__ init_c,  // optional [H] broadcast state used instead of h_prev/c
+    const int32_t* __restrict__ lead,                                    // optional [B]: per-row pad-prefix start (row r joins at step lead[r]
+    const float* __restrict__ pad_h, const float* __restrict__ pad_c,    //   from the tabulated state pad_*[lead[r]-1]; earlier steps skip it)
     int B, int H,
     float* __restrict__ save_h, float* __restrict__ save_c, float* __restrict__ save_g) {
   constexpr int BM = 16 * RPT;
@@ -48,12 +50,14 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(
   float wreg[4];
   int arow[RPT];
   int atok[RPT];
+  bool afirst[RPT];             // this is the row's first live step: its h_{t-1} comes from the pad-prefix table
 #pragma unroll
   for (int e = 0; e < RPT; ++e) {
     int idx = tid + e * 256;
     int r = row0 + (idx >> 4);
     arow[e] = r < B ? r : B - 1;
     atok[e] = tokens[(size_t)arow[e] * T + t];
+    afirst[e] = lead != nullptr && t > 0 && min(lead[arow[e]], T - 1) == t;
   }
   const int akk = tid & 15;
   const int wkk = tid >> 4;       // W-tile loader: row kk = tid/16, unit = tid%16, 4 gates
@@ -65,7 +69,8 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(
     for (int e = 0; e < RPT; ++e) {
       float v = 0.f;
       if (k < We) v = __ldg(emb + (size_t)atok[e] * We + k);
-      else if (k < Ktot) v = init_h ? __ldg(init_h + (k - We)) : h_prev[(size_t)arow[e] * H + (k - We)];
+      else if (k < Ktot) v = afirst[e] ? __ldg(pad_h + (size_t)(t - 1) * H + (k - We))
+                                       : (init_h ? __ldg(init_h + (k - We)) : h_prev[(size_t)arow[e] * H + (k - We)]);
       areg[e] = v;
     }
     int kw = kt * BK + wkk;
@@ -127,7 +132,10 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(
     if (r >= B) continue;
     size_t off = (size_t)r * H + u;
     float c_old = 0.f;
-    if (init_c) c_old = __ldg(init_c + u);
+    const int lr = lead ? min(lead[r], T - 1) : 0;
+    if (lead && t < lr) continue;                       // still inside this row's pad prefix: it joins at step lr
+    if (lead && t == lr && t > 0) c_old = __ldg(pad_c + (size_t)(t - 1) * H + u);
+    else if (init_c) c_old = __ldg(init_c + u);
     else if (h_prev) c_old = c[off];
     float si = sigmoidf_(acc[i][0] + bi);
     float tj = tanhf(acc[i][1] + bj);
@@ -227,7 +235,7 @@ __global__ void l2norm_rows_kernel(const float* __restrict__ x, float* __restric
 int lstm_forward_simt(const int32_t* tokens, int B, int T, int t_start, const float* emb, int We,
                       const LstmTower& tw, float* h0, float* h1, float* c, const float* init_h,
                       const float* init_c, float* save_h, float* save_c, float* save_g, float** h_final,
-                      cudaStream_t st, int64_t* launches) {
+                      cudaStream_t st, int64_t* launches, const int32_t* lead, const float* pad_h, const float* pad_c) {
   const int H = tw.H;
   float* hp = nullptr;   // h_{t-1}
   float* hn = h0;
@@ -237,11 +245,11 @@ int lstm_forward_simt(const int32_t* tokens, int B, int T, int t_start, const fl
     const float* ic = (t == t_start) ? init_c : nullptr;
     if (big) {
       dim3 grid(cdiv(B, 128), cdiv(H, 16));
-      lstm_step_kernel<8><<<grid, 256, 0, st>>>(tokens, T, t, emb, We, tw.K, tw.b, hp, hn, c, ih, ic, B, H,
+      lstm_step_kernel<8><<<grid, 256, 0, st>>>(tokens, T, t, emb, We, tw.K, tw.b, hp, hn, c, ih, ic, lead, pad_h, pad_c, B, H,
                                                 save_h, save_c, save_g);
     } else {
       dim3 grid(cdiv(B, 64), cdiv(H, 16));
-      lstm_step_kernel<4><<<grid, 256, 0, st>>>(tokens, T, t, emb, We, tw.K, tw.b, hp, hn, c, ih, ic, B, H,
+      lstm_step_kernel<4><<<grid, 256, 0, st>>>(tokens, T, t, emb, We, tw.K, tw.b, hp, hn, c, ih, ic, lead, pad_h, pad_c, B, H,
                                                 save_h, save_c, save_g);
     }
     if (launches) ++*launches;

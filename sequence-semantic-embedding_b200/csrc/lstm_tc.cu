@@ -36,6 +36,9 @@ struct LstmTcParams {
   const float* bias_r;        // [4H] chunk-major, +1 folded into the forget gate
   const float* init_h;        // optional [H] broadcast initial state (pad-prefix table row)
   const float* init_c;
+  const int32_t* lead_sorted; // optional [B]: leading PADs of each (sorted) row -> per-tile start step (tok_prep.cu)
+  const float* pad_h;         // with lead_sorted: pad-prefix state table [T][H] (entry t = state after t+1 PADs)
+  const float* pad_c;
   float* c_scratch;           // [Bpad, H] fp32
   float* h_out;               // [B, H] fp32 (last step)
   int B, T, t_start, We, H, n_stages;
@@ -242,8 +245,17 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w3, const __grid_constan
   const int RPC = P.rows_per_cta;
   const int n_act = RPC / 32;                                 // active TMEM lane quarters
   const int row0 = blockIdx.x * RPC;
-  const int t0 = P.t_start;
-  const bool has_init = P.init_h != nullptr;
+  // per-tile pad-prefix start (tok_prep.cu): rows are sorted by descending number of leading PADs, so the tile's LAST row
+  // has the shortest prefix; the tile starts at t0 from the tabulated state after t0 PADs
+  int t0 = P.t_start;
+  const float* init_h = P.init_h;
+  const float* init_c = P.init_c;
+  if (P.lead_sorted) {
+    t0 = min(__ldg(P.lead_sorted + min(row0 + RPC - 1, P.B - 1)), P.T - 1);
+    init_h = t0 > 0 ? P.pad_h + (size_t)(t0 - 1) * P.H : nullptr;
+    init_c = t0 > 0 ? P.pad_c + (size_t)(t0 - 1) * P.H : nullptr;
+  }
+  const bool has_init = init_h != nullptr;
   const uint32_t slot_bytes = (uint32_t)SKB * TILE_BYTES;
 
   const int XB = P.xbufs;
@@ -456,10 +468,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w3, const __grid_constan
       for (int u0 = half * 16; u0 < P.H; u0 += 32) {
         uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack_f16x2(__ldg(P.init_h + u0 + 2 * i), __ldg(P.init_h + u0 + 2 * i + 1));
+        for (int i = 0; i < 8; ++i) pk[i] = pack_f16x2(__ldg(init_h + u0 + 2 * i), __ldg(init_h + u0 + 2 * i + 1));
         TMEM_ST_8(hdst + u0 / 2, pk);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) crow[u0 + i] = __ldg(P.init_c + u0 + i);
+        for (int i = 0; i < 16; ++i) crow[u0 + i] = __ldg(init_c + u0 + i);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -659,11 +671,12 @@ int lstm_tc_prepare(TcTower& tt, const float* K, const float* b, int We, int H, 
 }
 
 int lstm_forward_tc(const int32_t* tokens, int B, int T, int t_start, const __half* emb_f16, int We, int H,
-                    const TcTower& tt, const float* init_h, const float* init_c, float* c_scratch, float* h_out,
+                    const TcTower& tt, const float* init_h, const float* init_c, const PadSkip& ps, float* c_scratch, float* h_out,
                     cudaStream_t st, int64_t* launches) {
   if (B <= 0) return SSE_OK;
   LstmTcParams p;
   p.tokens = tokens; p.emb = emb_f16; p.bias_r = tt.bias_r; p.init_h = init_h; p.init_c = init_c;
+  p.lead_sorted = ps.lead_sorted; p.pad_h = ps.pad_h; p.pad_c = ps.pad_c;
   p.c_scratch = c_scratch; p.h_out = h_out; p.B = B; p.T = T; p.t_start = t_start; p.We = We; p.H = H;
   // small batches: 64- / 32-row tiles spread the rows over more SMs (the step latency, not the MMA rate, bounds them)
   const int rpc_auto = (cdiv(B, 128) * 2 >= 148) ? 128 : ((cdiv(B, 64) * 2 >= 148) ? 64 : 32);

@@ -69,6 +69,7 @@ void refresh_pointers(sse_handle* h) {
 
 void invalidate_derived(sse_handle* h) {
   h->pad[0].valid = h->pad[1].valid = false;
+  h->pad_tc[0].valid = h->pad_tc[1].valid = false;
   h->tct[0].valid = h->tct[1].valid = false;
   h->tct[0].ptable_valid = h->tct[1].ptable_valid = false;
   h->emb_f16_valid = false;
@@ -101,18 +102,80 @@ static int ensure_pad_table(sse_handle* h, int side, cudaStream_t st) {
   return SSE_OK;
 }
 
+// the same table in the arithmetic of the tabulated-projection tensor-core kernel (lstm_ptable_kernel run on one all-PAD
+// row, dumping the state it carries past every step: h as the fp16 value of the recurrence, c in fp32), so that a tile
+// started from S[t0] continues bit-identically to a tile that ran the t0 PAD steps itself
+static int ensure_pad_table_tc(sse_handle* h, int side, cudaStream_t st) {
+  PadTable& pt = h->pad_tc[side];
+  if (pt.valid) return SSE_OK;
+  const LstmTower& tw = h->lstm[side];
+  const int T = h->cfg.max_seq_length, H = tw.H;
+  SSE_TRY(pt.buf.ensure((size_t)T * 2 * H * 4 + (size_t)T * 4 + (size_t)H * 4));
+  float* tab_h = pt.buf.as<float>();
+  float* tab_c = tab_h + (size_t)T * H;
+  float* hout = tab_c + (size_t)T * H;
+  int32_t* toks = reinterpret_cast<int32_t*>(hout + H);
+  SSE_CUDA_OK(cudaMemsetAsync(toks, 0, (size_t)T * 4, st));
+  PadSkip ps;
+  ps.dump_h = tab_h; ps.dump_c = tab_c;
+  SSE_TRY(lstm_forward_ptable(toks, 1, T, 0, h->cfg.embedding_size, H, h->tct[side], nullptr, nullptr, ps, hout, st, &h->launches));
+  pt.h = tab_h; pt.c = tab_c; pt.valid = true;
+  return SSE_OK;
+}
+
+// sticky count of out-of-range token ids seen by the device pre-pass: read + reset (synchronises `st`)
+int take_token_errors(sse_handle* h, cudaStream_t st, int* count) {
+  int bad = 0;
+  SSE_CUDA_OK(cudaMemcpyAsync(&bad, h->tok_bad, 4, cudaMemcpyDeviceToHost, st));
+  SSE_CUDA_OK(cudaStreamSynchronize(st));
+  if (bad) SSE_CUDA_OK(cudaMemsetAsync(h->tok_bad, 0, 4, st));
+  *count = bad;
+  return SSE_OK;
+}
+static int fail_on_token_errors(sse_handle* h, cudaStream_t st, const char* who) {
+  int bad = 0;
+  SSE_TRY(take_token_errors(h, st, &bad));
+  if (bad) {
+    set_error("%s: %d token id(s) outside [0, vocab_size=%d) (TensorFlow's gather raises InvalidArgument here; they were read as PAD_ID)",
+              who, bad, h->cfg.vocab_size);
+    return SSE_EINVAL;
+  }
+  return SSE_OK;
+}
+
 // encode B rows of one side into out [B,E]
-int encode_device(sse_handle* h, int side, const int32_t* tokens, int B, float* out, int normalize, int t_start,
-                  cudaStream_t st) {
+int encode_device(sse_handle* h, int side, const int32_t* tokens_in, int B, float* out, int normalize, cudaStream_t st) {
   const sse_config& c = h->cfg;
   const int T = c.max_seq_length, We = c.embedding_size, E = c.encoding_size;
   if (B <= 0) return SSE_OK;
   const float* emb = h->params[h->emb_param].dev;
-  if (side_is_cnn(h, side)) {
-    if (c.network_mode == SSE_MODE_SOURCE_ONLY_CNN && side != SSE_SIDE_SRC) {
-      set_error("target side of source_only_cnn is a table (target_embedding/tgt_seq_embedding), not an encoder");
-      return SSE_ESTATE;
-    }
+  const bool is_cnn = side_is_cnn(h, side);
+  if (is_cnn && c.network_mode == SSE_MODE_SOURCE_ONLY_CNN && side != SSE_SIDE_SRC) {
+    set_error("target side of source_only_cnn is a table (target_embedding/tgt_seq_embedding), not an encoder");
+    return SSE_ESTATE;
+  }
+  if (!is_cnn && c.network_mode == SSE_MODE_SOURCE_ENCODER_ONLY && side != SSE_SIDE_SRC) {
+    set_error("target side of source-encoder-only is a table (target_embedding/tgt_seq_embedding), not an encoder");
+    return SSE_ESTATE;
+  }
+  // device pre-pass: range check (+ pad-prefix bucketing for the LSTM towers)
+  const bool sort_rows = !is_cnn && h->opt_pad_skip;
+  TokPrep tp;
+  SSE_TRY(h->tok_ws.ensure(tok_prep_ws_bytes(B, T)));
+  SSE_TRY(tok_prep(tokens_in, B, T, c.vocab_size, sort_rows, h->tok_ws.p, &tp, h->tok_bad, st, &h->launches));
+  const int32_t* tokens = tp.stok;
+  // rows leave the tower in sorted order: project into a scratch [B,E], then un-permute (+ l2-normalise) into `out`
+  float* proj = out;
+  if (tp.sorted) {
+    SSE_TRY(h->proj_ws.ensure((size_t)B * E * 4));
+    proj = h->proj_ws.as<float>();
+  }
+  auto finish = [&]() -> int {
+    if (tp.sorted) return unpermute_rows(proj, out, tp.perm, B, E, normalize, st, &h->launches);
+    if (normalize) return l2norm_rows(out, B, E, st, &h->launches);
+    return SSE_OK;
+  };
+  if (is_cnn) {
     const CnnTower& tw = h->cnn[side];
     int maxF = 0;
     for (int i = 0; i < tw.nf; ++i) maxF = std::max(maxF, tw.nfilt[i]);
@@ -126,25 +189,13 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens, int B, float* 
     for (int b0 = 0; b0 < B; b0 += slab) {
       int nb = std::min(slab, B - b0);
       SSE_TRY(cnn_forward_ws(tokens + (size_t)b0 * T, nb, T, emb, We, tw, xg, conv, pool, nullptr, st, &h->launches));
-      SSE_TRY(sgemm(false, false, nb, E, tw.sumF, 1.f, pool, tw.sumF, tw.M, E, 0.f, out + (size_t)b0 * E, E, st,
+      SSE_TRY(sgemm(false, false, nb, E, tw.sumF, 1.f, pool, tw.sumF, tw.M, E, 0.f, proj + (size_t)b0 * E, E, st,
                     &h->launches));
     }
-    if (normalize) SSE_TRY(l2norm_rows(out, B, E, st, &h->launches));
-    return SSE_OK;
-  }
-  if (c.network_mode == SSE_MODE_SOURCE_ENCODER_ONLY && side != SSE_SIDE_SRC) {
-    set_error("target side of source-encoder-only is a table (target_embedding/tgt_seq_embedding), not an encoder");
-    return SSE_ESTATE;
+    return finish();
   }
   const LstmTower& tw = h->lstm[side];
   const int H = tw.H;
-  const float *ih = nullptr, *ic = nullptr;
-  if (t_start > 0) {
-    if (t_start >= T) t_start = T - 1;
-    SSE_TRY(ensure_pad_table(h, side, st));
-    ih = h->pad[side].h + (size_t)(t_start - 1) * H;
-    ic = h->pad[side].c + (size_t)(t_start - 1) * H;
-  }
   const bool want_tc = h->opt_encoder == 2 || (h->opt_encoder == 0 && c.precision == SSE_PRECISION_TC);
   if (want_tc && lstm_tc_supported(We, H)) {
     if (!h->emb_f16_valid) {
@@ -168,17 +219,24 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens, int B, float* 
     // measured (We=H=256, T=50): table kernel 0.22 ms at 600 rows, 0.67 ms at 4800; the weight-streaming kernel is
     // flat ~0.8 ms up to ~5k rows and wins once every SM holds a full 128-row tile (1.44 vs 2.2 ms at 18944 rows)
     if (kern == 0) kern = (ptable_ok && B <= 8192) ? 3 : ((cluster_ok && B <= 1024) ? 2 : 1);
-    if (kern == 3) {
-      if (!tt.ptable_valid) SSE_TRY(lstm_ptable_prepare(tt, emb, c.vocab_size, tw.K, We, H, st, &h->launches));
-      SSE_TRY(lstm_forward_ptable(tokens, B, T, t_start, We, H, tt, ih, ic, hout, st, &h->launches));
-    } else if (kern == 2) {
-      SSE_TRY(lstm_forward_cluster(tokens, B, T, t_start, h->emb_f16, We, H, tt, ih, ic, hout, st, &h->launches));
-    } else {
-      SSE_TRY(lstm_forward_tc(tokens, B, T, t_start, h->emb_f16, We, H, tt, ih, ic, cs, hout, st, &h->launches));
+    if (kern == 3 && !tt.ptable_valid) SSE_TRY(lstm_ptable_prepare(tt, emb, c.vocab_size, tw.K, We, H, st, &h->launches));
+    PadSkip ps;
+    if (tp.sorted) {
+      // kernel 3 continues bit-identically from a table in its own arithmetic; the other two start from the fp32 table
+      // (equal within the tensor-core tolerance)
+      if (kern == 3) { SSE_TRY(ensure_pad_table_tc(h, side, st)); ps.pad_h = h->pad_tc[side].h; ps.pad_c = h->pad_tc[side].c; }
+      else { SSE_TRY(ensure_pad_table(h, side, st)); ps.pad_h = h->pad[side].h; ps.pad_c = h->pad[side].c; }
+      ps.lead_sorted = tp.lead_sorted;
     }
-    SSE_TRY(sgemm(false, false, B, E, H, 1.f, hout, H, tw.M, E, 0.f, out, E, st, &h->launches));
-    if (normalize) SSE_TRY(l2norm_rows(out, B, E, st, &h->launches));
-    return SSE_OK;
+    if (kern == 3) {
+      SSE_TRY(lstm_forward_ptable(tokens, B, T, 0, We, H, tt, nullptr, nullptr, ps, hout, st, &h->launches));
+    } else if (kern == 2) {
+      SSE_TRY(lstm_forward_cluster(tokens, B, T, 0, h->emb_f16, We, H, tt, nullptr, nullptr, ps, hout, st, &h->launches));
+    } else {
+      SSE_TRY(lstm_forward_tc(tokens, B, T, 0, h->emb_f16, We, H, tt, nullptr, nullptr, ps, cs, hout, st, &h->launches));
+    }
+    SSE_TRY(sgemm(false, false, B, E, H, 1.f, hout, H, tw.M, E, 0.f, proj, E, st, &h->launches));
+    return finish();
   } else if (h->opt_encoder == 2) {
     set_error("tcgen05 encoder needs We%%64==0, H%%64==0, We,H<=256 (We=%d H=%d)", We, H);
     return SSE_EINVAL;
@@ -188,23 +246,16 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens, int B, float* 
   float* h1 = h0 + (size_t)B * H;
   float* cc = h1 + (size_t)B * H;
   float* hf = nullptr;
-  SSE_TRY(lstm_forward_simt(tokens, B, T, t_start, emb, We, tw, h0, h1, cc, ih, ic, nullptr, nullptr, nullptr, &hf, st,
-                            &h->launches));
-  SSE_TRY(sgemm(false, false, B, E, H, 1.f, hf, H, tw.M, E, 0.f, out, E, st, &h->launches));
-  if (normalize) SSE_TRY(l2norm_rows(out, B, E, st, &h->launches));
-  return SSE_OK;
-}
-
-// smallest number of leading PAD tokens over the batch (host tokens)
-static int min_lead_pads(const int32_t* tok, int B, int T) {
-  int best = T;
-  for (int r = 0; r < B && best > 0; ++r) {
-    const int32_t* p = tok + (size_t)r * T;
-    int n = 0;
-    while (n < best && p[n] == 0) ++n;
-    best = std::min(best, n);
+  const int32_t* lead = nullptr;
+  const float *ph = nullptr, *pc = nullptr;
+  if (tp.sorted) {
+    SSE_TRY(ensure_pad_table(h, side, st));
+    lead = tp.lead_sorted; ph = h->pad[side].h; pc = h->pad[side].c;
   }
-  return best;
+  SSE_TRY(lstm_forward_simt(tokens, B, T, 0, emb, We, tw, h0, h1, cc, nullptr, nullptr, nullptr, nullptr, nullptr, &hf, st,
+                            &h->launches, lead, ph, pc));
+  SSE_TRY(sgemm(false, false, B, E, H, 1.f, hf, H, tw.M, E, 0.f, proj, E, st, &h->launches));
+  return finish();
 }
 
 int search_device(sse_handle* h, const float* q, int Q, int k, float* scores, int32_t* idx, cudaStream_t st) {
@@ -321,6 +372,7 @@ int sse_create(const sse_config* cfg_in, sse_handle** out) {
     }
     h->n_vars = (int)nvar;
   }
+  if (rc == SSE_OK && (cudaMalloc(&h->tok_bad, 4) != cudaSuccess || cudaMemset(h->tok_bad, 0, 4) != cudaSuccess)) rc = SSE_ENOMEM;
   if (rc != SSE_OK) { sse_destroy(h); return rc; }
   refresh_pointers(h);
   cudaDeviceSynchronize();
@@ -335,6 +387,9 @@ int sse_destroy(sse_handle* h) {
   for (auto& p : h->params) if (p.dev) cudaFree(p.dev);
   h->enc_ws.release(); h->search_ws.release(); h->io_ws.release(); h->train_ws.release();
   h->pad[0].buf.release(); h->pad[1].buf.release();
+  h->pad_tc[0].buf.release(); h->pad_tc[1].buf.release();
+  h->tok_ws.release(); h->proj_ws.release();
+  if (h->tok_bad) cudaFree(h->tok_bad);
   if (h->index_f32 && h->index_owned) cudaFree(h->index_f32);
   if (h->grad_arena) cudaFree(h->grad_arena);
   search_tc_release(h->tc);
@@ -386,7 +441,7 @@ int sse_get_param(sse_handle* h, const char* name, void* host_dst, int64_t nbyte
 int sse_encode(sse_handle* h, int side, const int32_t* tokens_dev, int B, float* out_dev, int normalize, void* stream) {
   if (!h || !tokens_dev || !out_dev || B < 0 || (side != 0 && side != 1)) { set_error("sse_encode: bad argument"); return SSE_EINVAL; }
   SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
-  return encode_device(h, side, tokens_dev, B, out_dev, normalize, 0, (cudaStream_t)stream);
+  return encode_device(h, side, tokens_dev, B, out_dev, normalize, (cudaStream_t)stream);
 }
 
 int sse_encode_host(sse_handle* h, int side, const int32_t* tokens_host, int B, float* out_host, int normalize) {
@@ -400,12 +455,9 @@ int sse_encode_host(sse_handle* h, int side, const int32_t* tokens_host, int B, 
   float* dout = reinterpret_cast<float*>(h->io_ws.as<uint8_t>() + tb);
   cudaStream_t st = 0;
   SSE_CUDA_OK(cudaMemcpyAsync(dt, tokens_host, (size_t)B * T * 4, cudaMemcpyHostToDevice, st));
-  int t_start = 0;
-  if (h->opt_pad_skip && !side_is_cnn(h, side)) t_start = min_lead_pads(tokens_host, B, T);
-  SSE_TRY(encode_device(h, side, dt, B, dout, normalize, t_start, st));
+  SSE_TRY(encode_device(h, side, dt, B, dout, normalize, st));
   SSE_CUDA_OK(cudaMemcpyAsync(out_host, dout, (size_t)B * E * 4, cudaMemcpyDeviceToHost, st));
-  SSE_CUDA_OK(cudaStreamSynchronize(st));
-  return SSE_OK;
+  return fail_on_token_errors(h, st, "sse_encode_host");
 }
 
 int sse_index_set(sse_handle* h, const float* tgt, int64_t n_local, int64_t global_offset) {
@@ -443,11 +495,10 @@ int sse_index_build(sse_handle* h, const int32_t* tgt_tokens, int64_t n_local, i
   for (int64_t r0 = 0; r0 < n_local; r0 += batch) {
     int nb = (int)std::min<int64_t>(batch, n_local - r0);
     SSE_CUDA_OK(cudaMemcpyAsync(h->io_ws.p, tgt_tokens + (size_t)r0 * T, (size_t)nb * T * 4, cudaMemcpyDefault, st));
-    SSE_TRY(encode_device(h, SSE_SIDE_TGT, h->io_ws.as<int32_t>(), nb, h->index_f32 + (size_t)r0 * E, 1, 0, st));
+    SSE_TRY(encode_device(h, SSE_SIDE_TGT, h->io_ws.as<int32_t>(), nb, h->index_f32 + (size_t)r0 * E, 1, st));
   }
-  SSE_CUDA_OK(cudaStreamSynchronize(st));
   h->index_n = n_local; h->index_off = global_offset;
-  return SSE_OK;
+  return fail_on_token_errors(h, st, "sse_index_build");
 }
 
 int sse_index_get(sse_handle* h, int64_t row0, int64_t n, float* host_dst) {
@@ -486,13 +537,32 @@ int sse_query_host(sse_handle* h, const int32_t* tokens_host, int Q, int k, int 
   int32_t* di = reinterpret_cast<int32_t*>(w + o_i);
   cudaStream_t st = 0;
   SSE_CUDA_OK(cudaMemcpyAsync(dt, tokens_host, (size_t)Q * T * 4, cudaMemcpyHostToDevice, st));
-  int t_start = 0;
-  if (h->opt_pad_skip && !side_is_cnn(h, SSE_SIDE_SRC)) t_start = min_lead_pads(tokens_host, Q, T);
-  SSE_TRY(encode_device(h, SSE_SIDE_SRC, dt, Q, enc, normalize, t_start, st));
+  SSE_TRY(encode_device(h, SSE_SIDE_SRC, dt, Q, enc, normalize, st));
   SSE_TRY(search_device(h, enc, Q, k, ds, di, st));
   SSE_CUDA_OK(cudaMemcpyAsync(scores_host, ds, (size_t)Q * k * 4, cudaMemcpyDeviceToHost, st));
   SSE_CUDA_OK(cudaMemcpyAsync(idx_host, di, (size_t)Q * k * 4, cudaMemcpyDeviceToHost, st));
-  SSE_CUDA_OK(cudaStreamSynchronize(st));
+  return fail_on_token_errors(h, st, "sse_query_host");
+}
+
+int sse_topk_batch(sse_handle* h, const float* q_dev, int Q, const float* tgt_dev, int64_t n_tgt, int k, int normalize_scores,
+                   float* scores_dev, int32_t* idx_dev, void* stream) {
+  if (!h || !q_dev || !tgt_dev || !scores_dev || !idx_dev || Q < 0 || n_tgt < 0) { set_error("sse_topk_batch: bad argument"); return SSE_EINVAL; }
+  if (k < 1 || k > SSE_MAX_TOPK) { set_error("k=%d out of range [1,%d]", k, SSE_MAX_TOPK); return SSE_EINVAL; }
+  if (n_tgt < k) { set_error("input must have at least k columns (k=%d, %lld targets)", k, (long long)n_tgt); return SSE_EINVAL; }   // TF top_k's error
+  if (Q == 0) return SSE_OK;
+  SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  SSE_TRY(search_simt(q_dev, Q, h->cfg.encoding_size, tgt_dev, n_tgt, 0, k, scores_dev, idx_dev, h->search_ws, h->num_sms, st, &h->launches));
+  if (normalize_scores) SSE_TRY(l2norm_rows(scores_dev, Q, k, st, &h->launches));
+  return SSE_OK;
+}
+
+int sse_token_errors(sse_handle* h, int64_t* count_out, void* stream) {
+  if (!h || !count_out) { set_error("sse_token_errors: null argument"); return SSE_EINVAL; }
+  SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
+  int bad = 0;
+  SSE_TRY(take_token_errors(h, (cudaStream_t)stream, &bad));
+  *count_out = bad;
   return SSE_OK;
 }
 

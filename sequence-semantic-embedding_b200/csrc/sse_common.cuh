@@ -79,7 +79,8 @@ int lstm_forward_simt(const int32_t* tokens, int B, int T, int t_start, const fl
                       const LstmTower& tw, float* h0, float* h1, float* c,      // [B,H] each
                       const float* init_h, const float* init_c,                // optional [H] broadcast initial state (pad-prefix table row)
                       float* save_h, float* save_c, float* save_g,             // optional training stash: [T,B,H],[T,B,H],[T,B,5H]
-                      float** h_final, cudaStream_t st, int64_t* launches);
+                      float** h_final, cudaStream_t st, int64_t* launches,
+                      const int32_t* lead = nullptr, const float* pad_h = nullptr, const float* pad_c = nullptr);   // per-row pad-prefix start
 int sgemm(bool ta, bool tb, int M, int N, int Kd, float alpha, const float* A, int lda, const float* Bm, int ldb,
           float beta, float* C, int ldc, cudaStream_t st, int64_t* launches);
 int l2norm_rows(float* x, int rows, int cols, cudaStream_t st, int64_t* launches);
@@ -115,6 +116,27 @@ void search_tc_release(TcIndex& ti);
 int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
               float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches);
 
+// tok_prep.cu: token range check + pad-prefix bucketing (device pre-pass of the LSTM encoders)
+struct TokPrep {
+  int32_t* stok = nullptr;          // [B,T] sanitised tokens, rows in SORTED order
+  int32_t* perm = nullptr;          // [B] original row of sorted position
+  int32_t* lead_sorted = nullptr;   // [B] leading PADs (<= T-1) of each sorted row, descending when `sorted`
+  bool sorted = false;
+};
+size_t tok_prep_ws_bytes(int B, int T);
+int tok_prep(const int32_t* tokens, int B, int T, int V, bool sort, void* ws, TokPrep* out, int* bad_total, cudaStream_t st,
+             int64_t* launches);
+int sanitize_tokens_inplace(int32_t* tokens, int64_t n, int V, int* bad_total, cudaStream_t st, int64_t* launches);
+int unpermute_rows(const float* x, float* y, const int32_t* perm, int rows, int cols, int normalize, cudaStream_t st, int64_t* launches);
+// per-tile pad-prefix start of the tensor-core LSTM kernels (all null = off)
+struct PadSkip {
+  const int32_t* lead_sorted = nullptr;
+  const float* pad_h = nullptr;     // [T][H], entry t = state after t+1 leading PADs
+  const float* pad_c = nullptr;
+  float* dump_h = nullptr;          // table generation (lstm_ptable_kernel only)
+  float* dump_c = nullptr;
+};
+
 // lstm_tc.cu (tcgen05 LSTM tower, fp16 operands / fp32 accumulate and state)
 struct TcTower {
   __half* wt = nullptr;     // [4H, We+H] chunk-major transposed weights
@@ -134,13 +156,13 @@ bool lstm_tc_supported(int We, int H);
 int lstm_tc_prepare(TcTower& tt, const float* K, const float* b, int We, int H, cudaStream_t st, int64_t* launches);
 void lstm_tc_release(TcTower& tt);
 int lstm_forward_tc(const int32_t* tokens, int B, int T, int t_start, const __half* emb_f16, int We, int H,
-                    const TcTower& tt, const float* init_h, const float* init_c, float* c_scratch, float* h_out,
+                    const TcTower& tt, const float* init_h, const float* init_c, const PadSkip& ps, float* c_scratch, float* h_out,
                     cudaStream_t st, int64_t* launches);
 
 // cluster variant for small / medium batches (lstm_cluster.cu): weights resident in the shared memory of a cluster
 bool lstm_cluster_supported(int We, int H);
 int lstm_forward_cluster(const int32_t* tokens, int B, int T, int t_start, const __half* emb_f16, int We, int H,
-                         const TcTower& tt, const float* init_h, const float* init_c, float* h_out, cudaStream_t st,
+                         const TcTower& tt, const float* init_h, const float* init_c, const PadSkip& ps, float* h_out, cudaStream_t st,
                          int64_t* launches);
 
 // variant 2 (lstm_cluster.cu): input projection tabulated per vocabulary entry, 128 rows per cluster
@@ -148,7 +170,7 @@ bool lstm_ptable_supported(int64_t V, int We, int H);
 int lstm_ptable_prepare(TcTower& tt, const float* emb, int64_t V, const float* K, int We, int H, cudaStream_t st, int64_t* launches);
 void lstm_ptable_release(TcTower& tt);
 int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We, int H, const TcTower& tt, const float* init_h,
-                        const float* init_c, float* h_out, cudaStream_t st, int64_t* launches);
+                        const float* init_c, const PadSkip& ps, float* h_out, cudaStream_t st, int64_t* launches);
 
 // small utilities (util.cu)
 int fill_f32(float* p, int64_t n, float v, cudaStream_t st, int64_t* launches);

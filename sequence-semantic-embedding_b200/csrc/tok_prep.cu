@@ -1,0 +1,198 @@
+// Token pre-pass of the LSTM encoders (device side, one or three tiny launches per batch):
+//   1. range check -- ids outside [0, V) would index past the embedding / input-projection tables (and, in training,
+//      scatter gradients out of bounds).  TensorFlow's gather raises InvalidArgument there (reference
+//      sse_model.py:163-164); here such ids are replaced by PAD_ID and COUNTED in a sticky device counter that the
+//      host entry points turn into SSE_EINVAL (device entry points: sse_token_errors()).
+//   2. pad-prefix bucketing -- rows are left-padded with PAD_ID=0 (reference data_utils.py:149-155,
+//      sse_index.py:79-85) and every row starts from the zero state, so the state after p leading PADs is the same
+//      for every row.  Rows are counting-sorted by their number of leading PADs (descending), so that
+//      the rows of one kernel tile share (almost) the same prefix length; a tile then starts at
+//      t0 = lead_sorted[last row of the tile] from the tabulated state S[t0] instead of running the PAD steps.
+// Outputs: stok [B,T] sanitised tokens in SORTED order, perm[pos] = original row, lead_sorted[pos] = leading PADs.
+#include "sse_common.cuh"
+
+namespace sse {
+
+namespace {
+
+constexpr int TP_THREADS = 1024;
+constexpr int TP_MAX_T = 2048;        // histogram bins held in shared memory
+
+// warp per row: number of leading PADs (clamped to T-1) and number of out-of-range ids
+__device__ __forceinline__ void scan_row(const int32_t* __restrict__ row, int T, int V, int lane, int& lead, int& bad) {
+  lead = T;
+  bad = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const int v = t < T ? __ldg(row + t) : 1;
+    const bool oob = t < T && (v < 0 || v >= V);
+    bad += __popc(__ballot_sync(0xffffffffu, oob));
+    const unsigned nz = __ballot_sync(0xffffffffu, t < T && v != 0 && !oob);     // an out-of-range id becomes PAD
+    if (lead == T && nz) lead = t0 + __ffs(nz) - 1;
+  }
+  if (lead > T - 1) lead = T - 1;
+}
+
+__device__ __forceinline__ void copy_row(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int T, int V, int lane) {
+  for (int t = lane; t < T; t += 32) {
+    const int v = __ldg(src + t);
+    dst[t] = (v < 0 || v >= V) ? 0 : v;
+  }
+}
+
+// B <= one block's worth of work: everything in ONE launch
+__global__ void __launch_bounds__(TP_THREADS) tok_prep_fused_kernel(const int32_t* __restrict__ tok, int B, int T, int V, int sort,
+                                                                    int32_t* __restrict__ stok, int32_t* __restrict__ perm,
+                                                                    int32_t* __restrict__ lead_sorted, int* __restrict__ bad_total) {
+  __shared__ int hist[TP_MAX_T];
+  __shared__ int s_bad;
+  extern __shared__ int16_t lead_s[];      // [B]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = TP_THREADS / 32;
+  for (int i = threadIdx.x; i < T; i += TP_THREADS) hist[i] = 0;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  int bad_w = 0;
+  for (int r = warp; r < B; r += nw) {
+    int lead, bad;
+    scan_row(tok + (size_t)r * T, T, V, lane, lead, bad);
+    bad_w += bad;
+    if (lane == 0) { lead_s[r] = (int16_t)lead; if (sort) atomicAdd(&hist[lead], 1); }
+  }
+  if (lane == 0 && bad_w) atomicAdd(&s_bad, bad_w);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_bad) atomicAdd(bad_total, s_bad);
+    if (sort) {           // descending prefix length: bin T-1 first
+      int run = 0;
+      for (int p = T - 1; p >= 0; --p) { const int c = hist[p]; hist[p] = run; run += c; }
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < B; r += nw) {
+    int pos = r;
+    const int lead = lead_s[r];
+    if (sort) {
+      if (lane == 0) pos = atomicAdd(&hist[lead], 1);
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+    }
+    copy_row(tok + (size_t)r * T, stok + (size_t)pos * T, T, V, lane);
+    if (lane == 0) { perm[pos] = r; lead_sorted[pos] = lead; }
+  }
+}
+
+// large batches: three launches with global histogram / cursors (hist: [T] ints, zeroed by the caller)
+__global__ void tok_count_kernel(const int32_t* __restrict__ tok, int B, int T, int V, int32_t* __restrict__ lead_of, int* __restrict__ hist,
+                                 int* __restrict__ bad_total) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  int bad_w = 0;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < B; r += gridDim.x * wpb) {
+    int lead, bad;
+    scan_row(tok + (size_t)r * T, T, V, lane, lead, bad);
+    bad_w += bad;
+    if (lane == 0) { lead_of[r] = lead; atomicAdd(&hist[lead], 1); }
+  }
+  if (lane == 0 && bad_w) atomicAdd(bad_total, bad_w);
+}
+__global__ void tok_scan_kernel(int* __restrict__ hist, int T) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int run = 0;
+    for (int p = T - 1; p >= 0; --p) { const int c = hist[p]; hist[p] = run; run += c; }
+  }
+}
+__global__ void tok_scatter_kernel(const int32_t* __restrict__ tok, int B, int T, int V, const int32_t* __restrict__ lead_of, int* __restrict__ cursor,
+                                   int sort, int32_t* __restrict__ stok, int32_t* __restrict__ perm, int32_t* __restrict__ lead_sorted) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < B; r += gridDim.x * wpb) {
+    const int lead = lead_of[r];
+    int pos = r;
+    if (sort) {
+      if (lane == 0) pos = atomicAdd(&cursor[lead], 1);
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+    }
+    copy_row(tok + (size_t)r * T, stok + (size_t)pos * T, T, V, lane);
+    if (lane == 0) { perm[pos] = r; lead_sorted[pos] = lead; }
+  }
+}
+
+// y[perm[r]] = x[r] * rsqrt(max(sum x[r]^2, 1e-12)) (normalize) or x[r]; warp per row
+__global__ void unpermute_rows_kernel(const float* __restrict__ x, float* __restrict__ y, const int32_t* __restrict__ perm, int rows, int cols,
+                                      int normalize) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * cols;
+  float inv = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int j = lane; j < cols; j += 32) { float v = xr[j]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    inv = rsqrtf(fmaxf(ss, 1e-12f));
+    inv = inv * (1.5f - 0.5f * fmaxf(ss, 1e-12f) * inv * inv);      // same Newton step as l2norm_rows_kernel: bit-identical results
+  }
+  float* yr = y + (size_t)(perm ? perm[row] : row) * cols;
+  for (int j = lane; j < cols; j += 32) yr[j] = normalize ? xr[j] * inv : xr[j];
+}
+
+__global__ void sanitize_inplace_kernel(int32_t* __restrict__ tok, int64_t n, int V, int* __restrict__ bad_total) {
+  int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = tok[i];
+    if (v < 0 || v >= V) { tok[i] = 0; ++bad; }
+  }
+  if (bad) atomicAdd(bad_total, bad);
+}
+
+}  // namespace
+
+// training path: the step works on its own copy of the batch, so ids are checked / replaced in place
+int sanitize_tokens_inplace(int32_t* tokens, int64_t n, int V, int* bad_total, cudaStream_t st, int64_t* launches) {
+  if (n <= 0) return SSE_OK;
+  sanitize_inplace_kernel<<<(int)std::min<int64_t>(cdiv64(n, 256), 148 * 4), 256, 0, st>>>(tokens, n, V, bad_total);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
+size_t tok_prep_ws_bytes(int B, int T) {
+  return ((size_t)B * T * 4 + 255) / 256 * 256 + 3 * (((size_t)B * 4 + 255) / 256 * 256) + (((size_t)T * 4 + 255) / 256 * 256);
+}
+
+// ws layout: stok [B,T] | perm [B] | lead_sorted [B] | lead_of [B] | hist [T]
+int tok_prep(const int32_t* tokens, int B, int T, int V, bool sort, void* ws, TokPrep* out, int* bad_total, cudaStream_t st,
+             int64_t* launches) {
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  out->stok = reinterpret_cast<int32_t*>(w);
+  out->perm = reinterpret_cast<int32_t*>(w + al((size_t)B * T * 4));
+  out->lead_sorted = out->perm + al((size_t)B * 4) / 4;
+  int32_t* lead_of = out->lead_sorted + al((size_t)B * 4) / 4;
+  int* hist = reinterpret_cast<int*>(lead_of + al((size_t)B * 4) / 4);
+  out->sorted = sort;
+  if (B <= 0) return SSE_OK;
+  if (B <= 8192 && T <= TP_MAX_T) {
+    tok_prep_fused_kernel<<<1, TP_THREADS, (size_t)B * 2, st>>>(tokens, B, T, V, sort ? 1 : 0, out->stok, out->perm, out->lead_sorted, bad_total);
+    if (launches) ++*launches;
+  } else {
+    SSE_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)T * 4, st));
+    const int blocks = std::min(cdiv(B, 8), 148 * 8);
+    tok_count_kernel<<<blocks, 256, 0, st>>>(tokens, B, T, V, lead_of, hist, bad_total);
+    tok_scan_kernel<<<1, 32, 0, st>>>(hist, T);
+    tok_scatter_kernel<<<blocks, 256, 0, st>>>(tokens, B, T, V, lead_of, hist, sort ? 1 : 0, out->stok, out->perm, out->lead_sorted);
+    if (launches) *launches += 3;
+  }
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
+int unpermute_rows(const float* x, float* y, const int32_t* perm, int rows, int cols, int normalize, cudaStream_t st, int64_t* launches) {
+  if (rows <= 0) return SSE_OK;
+  unpermute_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, y, perm, rows, cols, normalize);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
+}  // namespace sse

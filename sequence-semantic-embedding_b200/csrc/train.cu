@@ -220,9 +220,9 @@ int sse_pair_score(sse_handle* h, const int32_t* src_dev, const int32_t* tgt_dev
   SSE_TRY(h->train_ws.ensure((size_t)2 * B * E * 4));
   float* uS = h->train_ws.as<float>();
   float* uT = uS + (size_t)B * E;
-  SSE_TRY(encode_device(h, SSE_SIDE_SRC, src_dev, B, uS, 0, 0, st));
+  SSE_TRY(encode_device(h, SSE_SIDE_SRC, src_dev, B, uS, 0, st));
   if (h->tgt_table_param >= 0) { set_error("sse_pair_score: target side is a table in this mode"); return SSE_ESTATE; }
-  SSE_TRY(encode_device(h, SSE_SIDE_TGT, tgt_dev, B, uT, 0, 0, st));
+  SSE_TRY(encode_device(h, SSE_SIDE_TGT, tgt_dev, B, uT, 0, st));
   pair_loss_kernel<<<cdiv(B, 8), 256, 0, st>>>(uS, uT, nullptr, B, E, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr, cos_dev);
   ++h->launches;
   SSE_CUDA_OK(cudaGetLastError());
@@ -274,6 +274,9 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
   SSE_CUDA_OK(cudaMemcpyAsync(d_src, src, (size_t)B * T * 4, cudaMemcpyDefault, st));
   SSE_CUDA_OK(cudaMemcpyAsync(d_tgt, tgt, (size_t)B * T * 4, cudaMemcpyDefault, st));
   SSE_CUDA_OK(cudaMemcpyAsync(d_lab, labels, (size_t)B * 4, cudaMemcpyDefault, st));
+  // ids outside [0, V) would gather past the embedding table and scatter gradients out of bounds (TF raises
+  // InvalidArgument): replaced by PAD and counted; reported when the step hands scalars back / by sse_token_errors
+  SSE_TRY(sanitize_tokens_inplace(d_src, (int64_t)2 * B * T, V, h->tok_bad, st, &h->launches));
   const float* emb = h->params[h->emb_param].dev;
 
   // ---- forward with stash
@@ -343,6 +346,9 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
     SSE_CUDA_OK(cudaStreamSynchronize(st));
     if (loss_host) *loss_host = sc[1];
     if (acc_host) *acc_host = sc[2] + sc[3];
+    int bad = 0;
+    SSE_TRY(take_token_errors(h, st, &bad));
+    if (bad) { set_error("train step: %d token id(s) outside [0, vocab_size=%d)", bad, V); return SSE_EINVAL; }
   }
   return SSE_OK;
 }

@@ -119,7 +119,11 @@ def allreduce_train_step(handle, src, tgt, labels, b_global: int):
 
     class _Raw:
         __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-    arena = torch.as_tensor(_Raw(), device="cuda")
+    # wrap the arena on the HANDLE's device: with device="cuda" (torch's current device) a handle living on another GPU
+    # would be silently copied, the all-reduce would run on the copy and the apply would use un-reduced gradients
+    arena = torch.as_tensor(_Raw(), device=torch.device("cuda", int(handle.cfg.device)))
+    if arena.data_ptr() != ptr:
+        raise RuntimeError("gradient arena was copied instead of wrapped (device mismatch?)")
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(arena)
     return handle.train_apply(stream=torch.cuda.current_stream())

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "sse_merge_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "sse_query_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "sse_l2_normalize_rows": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "sse_topk_batch": (C.c_int, [_P, _P, C.c_int, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P]),
+    "sse_token_errors": (C.c_int, [_P, C.POINTER(C.c_int64), _P]),
     "sse_pair_score": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "sse_train_step": (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float), _P]),
@@ -252,6 +254,9 @@ class Handle:
     def index_set(self, tgt, n_local: Optional[int] = None, global_offset: int = 0):
         if isinstance(tgt, np.ndarray):
             tgt = np.ascontiguousarray(tgt, dtype=np.float32)
+        if len(tgt.shape) != 2 or int(tgt.shape[1]) != self.E:
+            # a stale targetEncodingIndex.tsv written with another encoding_size would be read as n * E_model floats
+            raise SseError("index rows must be [N, %d] (encoding_size of this model), got %s" % (self.E, tuple(tgt.shape)))
         n = int(tgt.shape[0]) if n_local is None else n_local
         self._check(self.lib.sse_index_set(self._h, _ptr(tgt), n, global_offset))
 
@@ -284,6 +289,17 @@ class Handle:
             idx_out = np.empty((Q, k), dtype=np.int32)
         self._check(self.lib.sse_query_host(self._h, _ptr(tokens), Q, k, int(normalize), _ptr(scores_out), _ptr(idx_out)))
         return scores_out, idx_out
+
+    def topk_batch(self, q_dev, Q: int, tgt_dev, n_tgt: int, k: int, scores_dev, idx_dev, normalize_scores: bool = True, stream=None):
+        """tf.nn.top_k over the batch's own target encodings (sse_model.py:344-350); the resident index is untouched."""
+        self._check(self.lib.sse_topk_batch(self._h, _ptr(q_dev), Q, _ptr(tgt_dev), n_tgt, k, int(normalize_scores),
+                                            _ptr(scores_dev), _ptr(idx_dev), _stream_ptr(stream)))
+
+    def token_errors(self, stream=None) -> int:
+        """out-of-range token ids seen since the last check (synchronises the stream, resets the counter)"""
+        n = C.c_int64()
+        self._check(self.lib.sse_token_errors(self._h, C.byref(n), _stream_ptr(stream)))
+        return int(n.value)
 
     def l2_normalize_rows(self, x_dev, rows: int, cols: int, stream=None):
         self._check(self.lib.sse_l2_normalize_rows(self._h, _ptr(x_dev), rows, cols, _stream_ptr(stream)))

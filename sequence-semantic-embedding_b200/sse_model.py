@@ -417,11 +417,11 @@ class SSEModel(object):
             k = self.TOP_N
             if tgt.shape[0] < k:
                 raise ValueError("input must have at least k columns")          # TF's error for top_k
-            h.index_set(tgt, tgt.shape[0], 0)
             s = torch.empty(q.shape[0], k, device=dev)
             i = torch.empty(q.shape[0], k, device=dev, dtype=torch.int32)
-            h.search(q, q.shape[0], k, s, i)
-            h.l2_normalize_rows(s, q.shape[0], k)
+            # scored against the batch's own targets without registering them: the index an Evaluator / DemoSession
+            # keeps resident on this handle is left alone
+            h.topk_batch(q, q.shape[0], tgt.contiguous(), tgt.shape[0], k, s, i, normalize_scores=True)
             torch.cuda.synchronize(dev)
             cache["predicted_tgts_score"], cache["predicted_labels"] = s.cpu().numpy(), i.cpu().numpy()
             return cache[name]

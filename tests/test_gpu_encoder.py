@@ -64,6 +64,7 @@ def test_pad_prefix_skip_is_bit_identical():
     h, p = make(mode, V, We, E, H, H, T)
     rng = np.random.default_rng(5)
     tok = O.synth_tokens(rng, 90, T, V, "real", 3.0)          # queries: ~3 real tokens of 50
+    h.set_option("pad_skip", 0)
     full = h.encode_host(sse_ffi.SIDE_SRC, tok, True)
     h.set_option("pad_skip", 1)
     skipped = h.encode_host(sse_ffi.SIDE_SRC, tok, True)
@@ -163,6 +164,7 @@ def test_tc_lstm_pad_skip_and_exact_mode_switch(kern):
     want = O.encode(p, mode, "src", tok, True)
     h.set_option("encoder", 2)
     h.set_option("lstm_kernel", kern)
+    h.set_option("pad_skip", 0)
     a = h.encode_host(0, tok, True)
     h.set_option("pad_skip", 1)
     b = h.encode_host(0, tok, True)           # starts every row from the pad-prefix state table
