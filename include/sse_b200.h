@@ -141,6 +141,14 @@ int sse_index_get(sse_handle* h, int64_t row0, int64_t n, float* host_dst);
  * than k targets are padded with (-inf, -1). */
 int sse_search(sse_handle* h, const float* q_dev, int Q, int k, float* scores_dev, int32_t* idx_dev,
                void* stream);
+/* Multi-GPU form of sse_search: the local shard's top-k of every row as ONE packed block
+ * packed [Q, 2k] fp32 -- columns [0,k) scores, columns [k,2k) the int32 GLOBAL ids bit-cast -- i.e. exactly the
+ * message a rank contributes to the NCCL exchange (all-gather, or all-to-all of the row blocks each peer owns). */
+int sse_search_packed(sse_handle* h, const float* q_dev, int Q, int k, float* packed_dev, void* stream);
+/* ... and the step after the exchange: gathered [G, Q, 2k] = the packed blocks of G shards for the same Q rows
+ * (as NCCL lays them out, rank-major) -> the k best of the G*k candidates per row, (score desc, id asc). */
+int sse_merge_packed(sse_handle* h, const float* gathered_dev, int G, int Q, int k, float* scores_dev,
+                     int32_t* idx_dev, void* stream);
 /* merge C candidates per row (e.g. the all-gathered per-shard top-k) into the
  * k best: the cross-shard step after the NCCL all-gather. */
 int sse_merge_topk(sse_handle* h, const float* cand_scores_dev, const int32_t* cand_idx_dev, int Q, int C,
@@ -191,6 +199,9 @@ int sse_set_scalars(sse_handle* h, float learning_rate, int64_t global_step);
 int sse_token_errors(sse_handle* h, int64_t* count_out, void* stream);
 
 /* ---- introspection for benchmarks / tests -------------------------------- */
+/* bookkeeping of the LAST tcgen05 search on this handle (synchronises the device): candidates that passed the sampled
+ * threshold summed over all rows, rows searched, rows that overflowed into the brute-force fallback, scan work items */
+int sse_search_stats(sse_handle* h, int64_t* candidates, int* rows, int* fallback_rows, int* items);
 /* number of kernels this library launched on the handle since creation */
 int64_t sse_launch_count(sse_handle* h);
 /* select kernel variants at run time: key in {"search", "encoder", "lstm_kernel", "pad_skip", "search_ctas"};

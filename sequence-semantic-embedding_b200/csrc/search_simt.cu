@@ -99,20 +99,26 @@ __global__ void __launch_bounds__(256) search_simt_kernel(const float* __restric
   }
 }
 
-// warp per query row: k rounds of arg-best over C candidates, order (score desc, idx asc).
+// warp per query row: k rounds of arg-best over C = n_groups * k_in candidates, order (score desc, idx asc).
+// Candidate x of group g of row r sits at cand[g * group_stride + r * row_stride + x] (scores and ids in separate or
+// in one bit-cast array): [Q, C] lists (n_groups = 1) and the all-gathered per-shard packed [G, Q, 2k] blocks alike.
 // Entries with idx < 0 are padding.  dynamic smem: per warp C floats + C ints
-__global__ void merge_topk_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i, int Q, int C,
-                                  int k, float* __restrict__ out_s, int32_t* __restrict__ out_i) {
+__global__ void merge_topk_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i, int Q, int n_groups,
+                                  long long group_stride, int row_stride, int k_in, int k, float* __restrict__ out_s,
+                                  int32_t* __restrict__ out_i, int out_stride) {
   extern __shared__ float dyn[];
   const int wpb = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * wpb + w;
+  const int C = n_groups * k_in;
   float* s = dyn + (size_t)w * C * 2;
   int32_t* id = reinterpret_cast<int32_t*>(s + C);
   if (row >= Q) return;
   for (int j = lane; j < C; j += 32) {
-    s[j] = cand_s[(size_t)row * C + j];
-    id[j] = cand_i[(size_t)row * C + j];
+    const int g = j / k_in, x = j - g * k_in;
+    const size_t at = (size_t)g * group_stride + (size_t)row * row_stride + x;
+    s[j] = cand_s[at];
+    id[j] = cand_i[at];
   }
   __syncwarp();
   for (int r = 0; r < k; ++r) {
@@ -133,8 +139,8 @@ __global__ void merge_topk_kernel(const float* __restrict__ cand_s, const int32_
       if (op >= 0 && (bp < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; bp = op; }
     }
     if (lane == 0) {
-      out_s[(size_t)row * k + r] = bp >= 0 ? bs : -CUDART_INF_F;
-      out_i[(size_t)row * k + r] = bp >= 0 ? bi : -1;
+      out_s[(size_t)row * out_stride + r] = bp >= 0 ? bs : -CUDART_INF_F;
+      out_i[(size_t)row * out_stride + r] = bp >= 0 ? bi : -1;
     }
     if (bp >= 0 && lane == (bp & 31)) id[bp] = -1;   // consumed (owner lane wrote it originally)
     __syncwarp();
@@ -143,24 +149,32 @@ __global__ void merge_topk_kernel(const float* __restrict__ cand_s, const int32_
 
 }  // namespace
 
-int merge_topk(const float* cand_s, const int32_t* cand_i, int Q, int C, int k, float* out_s, int32_t* out_i,
-               cudaStream_t st, int64_t* launches) {
+int merge_topk_strided(const float* cand_s, const int32_t* cand_i, int Q, int n_groups, int64_t group_stride, int row_stride,
+                       int k_in, int k, float* out_s, int32_t* out_i, int out_stride, cudaStream_t st, int64_t* launches) {
   if (Q <= 0) return SSE_OK;
+  const int C = n_groups * k_in;
   int wpb = 4;
   size_t smem = (size_t)wpb * C * 8;
   while (wpb > 1 && smem > 96 * 1024) { wpb >>= 1; smem = (size_t)wpb * C * 8; }
   if (smem > 200 * 1024) { set_error("merge_topk: C=%d too large", C); return SSE_EINVAL; }
   if (smem > 48 * 1024)
     SSE_CUDA_OK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<cdiv(Q, wpb), wpb * 32, smem, st>>>(cand_s, cand_i, Q, C, k, out_s, out_i);
+  merge_topk_kernel<<<cdiv(Q, wpb), wpb * 32, smem, st>>>(cand_s, cand_i, Q, n_groups, (long long)group_stride, row_stride, k_in, k,
+                                                          out_s, out_i, out_stride);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
   return SSE_OK;
 }
 
+int merge_topk(const float* cand_s, const int32_t* cand_i, int Q, int C, int k, float* out_s, int32_t* out_i,
+               cudaStream_t st, int64_t* launches) {
+  return merge_topk_strided(cand_s, cand_i, Q, 1, 0, C, C, k, out_s, out_i, k, st, launches);
+}
+
 int search_simt(const float* q, int Q, int E, const float* index, int64_t N, int64_t global_offset, int k,
                 float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st,
-                int64_t* launches) {
+                int64_t* launches, int out_stride) {
+  if (out_stride <= 0) out_stride = k;
   if (Q <= 0) return SSE_OK;
   const int q_tiles = cdiv(Q, BQ);
   // enough column ranges to fill the machine ~2x, each a multiple of BN columns
@@ -182,7 +196,7 @@ int search_simt(const float* q, int Q, int E, const float* index, int64_t N, int
                                               part_s, part_i);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
-  return merge_topk(part_s, part_i, Q, n_chunks * k, k, out_scores, out_idx, st, launches);
+  return merge_topk_strided(part_s, part_i, Q, 1, 0, n_chunks * k, n_chunks * k, k, out_scores, out_idx, out_stride, st, launches);
 }
 
 }  // namespace sse

@@ -762,6 +762,7 @@ struct FinParams {
   int64_t global_offset;
   int64_t N;
   int Q, E, k;
+  int out_stride;          // row stride of out_s / out_i in elements (k, or 2k when both live in one packed [Q,2k] block)
   float* out_s;
   int32_t* out_i;
   int32_t* overflow;       // [Q]
@@ -861,8 +862,8 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   bitonic_sort_pairs(cs, ci, m2);
   for (int x = tid; x < k; x += blockDim.x) {
     bool ok = x < m;
-    P.out_s[(size_t)row * k + x] = ok ? cs[x] : -CUDART_INF_F;
-    P.out_i[(size_t)row * k + x] = ok ? ci[x] : -1;
+    P.out_s[(size_t)row * P.out_stride + x] = ok ? cs[x] : -CUDART_INF_F;
+    P.out_i[(size_t)row * P.out_stride + x] = ok ? ci[x] : -1;
   }
 }
 
@@ -911,9 +912,9 @@ __global__ void __launch_bounds__(256) fallback_kernel(const __grid_constant__ F
         int32_t bi = reinterpret_cast<int32_t*>(dyn + (size_t)bw * k * 2 + k)[head[bw]];
         if (pair_before(s, i, bs, bi)) bw = w;
       }
-      if (bw < 0) { P.out_s[(size_t)row * k + x] = -CUDART_INF_F; P.out_i[(size_t)row * k + x] = -1; continue; }
-      P.out_s[(size_t)row * k + x] = dyn[(size_t)bw * k * 2 + head[bw]];
-      P.out_i[(size_t)row * k + x] = reinterpret_cast<int32_t*>(dyn + (size_t)bw * k * 2 + k)[head[bw]];
+      if (bw < 0) { P.out_s[(size_t)row * P.out_stride + x] = -CUDART_INF_F; P.out_i[(size_t)row * P.out_stride + x] = -1; continue; }
+      P.out_s[(size_t)row * P.out_stride + x] = dyn[(size_t)bw * k * 2 + head[bw]];
+      P.out_i[(size_t)row * P.out_stride + x] = reinterpret_cast<int32_t*>(dyn + (size_t)bw * k * 2 + k)[head[bw]];
       ++head[bw];
     }
   }
@@ -1008,8 +1009,9 @@ static int env_int(const char* name, int dflt) {
 }
 
 int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
-              float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches) {
+              float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches, int out_stride) {
   if (Q <= 0) return SSE_OK;
+  if (out_stride <= 0) out_stride = k;
   if (!ti.tmap_ok || ti.E != E) { set_error("search_tc: index not prepared"); return SSE_ESTATE; }
   const int64_t N = ti.N;
   const int KB = E / KBLK;
@@ -1210,7 +1212,8 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   for (int g = 0; g < n_groups; ++g) { fp.group_first_item[g] = sp.group_first_item[g]; fp.group_items[g] = sp.group_items[g]; }
   fp.cand_s = sp.cand_s; fp.cand_i = sp.cand_i; fp.cand_cnt = sp.cand_cnt; fp.margin = mg;
   fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E; fp.k = k;
-  fp.out_s = out_scores; fp.out_i = out_idx; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov);
+  fp.out_s = out_scores; fp.out_i = out_idx; fp.out_stride = out_stride; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov);
+  ti.last_cnt = sp.cand_cnt; ti.last_cnt_n = (int64_t)items * mtg * TILE_M; ti.last_overflow = fp.overflow; ti.last_Q = Q; ti.last_items = items;
   if (want_dbg) {
     std::vector<long long> hd((size_t)items * DBG_N);
     cudaStreamSynchronize(st);
@@ -1229,6 +1232,19 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   fallback_kernel<<<Q, 256, (size_t)8 * k * 8, st>>>(fp);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
+int search_tc_stats(const TcIndex& ti, SearchStats* out) {
+  *out = SearchStats();
+  if (!ti.last_cnt || ti.last_Q <= 0) return SSE_OK;
+  std::vector<int32_t> cnt((size_t)ti.last_cnt_n), ov((size_t)ti.last_Q);
+  SSE_CUDA_OK(cudaDeviceSynchronize());
+  SSE_CUDA_OK(cudaMemcpy(cnt.data(), ti.last_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost));
+  SSE_CUDA_OK(cudaMemcpy(ov.data(), ti.last_overflow, ov.size() * 4, cudaMemcpyDeviceToHost));
+  for (int32_t c : cnt) out->candidates += std::min<int32_t>(std::max<int32_t>(c, 0), CAND_CAP);
+  for (int32_t o : ov) out->fallback_rows += o != 0;
+  out->rows = ti.last_Q; out->items = ti.last_items;
   return SSE_OK;
 }
 

@@ -258,7 +258,8 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens_in, int B, floa
   return finish();
 }
 
-int search_device(sse_handle* h, const float* q, int Q, int k, float* scores, int32_t* idx, cudaStream_t st) {
+int search_device(sse_handle* h, const float* q, int Q, int k, float* scores, int32_t* idx, cudaStream_t st, int out_stride = 0) {
+  if (out_stride <= 0) out_stride = k;
   if (!h->index_f32) { set_error("no target index registered (call sse_index_set / sse_index_build first)"); return SSE_ESTATE; }
   if (k < 1 || k > SSE_MAX_TOPK) { set_error("k=%d out of range [1,%d]", k, SSE_MAX_TOPK); return SSE_EINVAL; }
   const int E = h->cfg.encoding_size;
@@ -272,14 +273,14 @@ int search_device(sse_handle* h, const float* q, int Q, int k, float* scores, in
     const int maxq = search_tc_max_rows(E);
     for (int q0 = 0; q0 < Q; q0 += maxq) {
       int nq = std::min(maxq, Q - q0);
-      SSE_TRY(search_tc(q + (size_t)q0 * E, nq, E, h->index_f32, h->tc, h->index_off, k, scores + (size_t)q0 * k,
-                        idx + (size_t)q0 * k, h->search_ws,
-                        h->opt_search_ctas > 0 ? std::min(h->opt_search_ctas, h->num_sms) : h->num_sms, st, &h->launches));
+      SSE_TRY(search_tc(q + (size_t)q0 * E, nq, E, h->index_f32, h->tc, h->index_off, k, scores + (size_t)q0 * out_stride,
+                        idx + (size_t)q0 * out_stride, h->search_ws,
+                        h->opt_search_ctas > 0 ? std::min(h->opt_search_ctas, h->num_sms) : h->num_sms, st, &h->launches, out_stride));
     }
     return SSE_OK;
   }
   return search_simt(q, Q, E, h->index_f32, h->index_n, h->index_off, k, scores, idx, h->search_ws, h->num_sms, st,
-                     &h->launches);
+                     &h->launches, out_stride);
 }
 
 }  // namespace sse
@@ -512,6 +513,31 @@ int sse_search(sse_handle* h, const float* q_dev, int Q, int k, float* scores_de
   if (!h || !q_dev || !scores_dev || !idx_dev || Q < 0) { set_error("sse_search: bad argument"); return SSE_EINVAL; }
   SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
   return search_device(h, q_dev, Q, k, scores_dev, idx_dev, (cudaStream_t)stream);
+}
+
+int sse_search_packed(sse_handle* h, const float* q_dev, int Q, int k, float* packed_dev, void* stream) {
+  if (!h || !q_dev || !packed_dev || Q < 0) { set_error("sse_search_packed: bad argument"); return SSE_EINVAL; }
+  SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
+  return search_device(h, q_dev, Q, k, packed_dev, reinterpret_cast<int32_t*>(packed_dev) + k, (cudaStream_t)stream, 2 * k);
+}
+
+int sse_merge_packed(sse_handle* h, const float* gathered_dev, int G, int Q, int k, float* scores_dev, int32_t* idx_dev, void* stream) {
+  if (!h || !gathered_dev || !scores_dev || !idx_dev || G < 1 || Q < 0 || k < 1) { set_error("sse_merge_packed: bad argument"); return SSE_EINVAL; }
+  SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
+  return merge_topk_strided(gathered_dev, reinterpret_cast<const int32_t*>(gathered_dev) + k, Q, G, (int64_t)Q * 2 * k, 2 * k, k, k,
+                            scores_dev, idx_dev, k, (cudaStream_t)stream, &h->launches);
+}
+
+int sse_search_stats(sse_handle* h, int64_t* candidates, int* rows, int* fallback_rows, int* items) {
+  if (!h) return SSE_EINVAL;
+  SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
+  SearchStats ss;
+  SSE_TRY(search_tc_stats(h->tc, &ss));
+  if (candidates) *candidates = ss.candidates;
+  if (rows) *rows = ss.rows;
+  if (fallback_rows) *fallback_rows = ss.fallback_rows;
+  if (items) *items = ss.items;
+  return SSE_OK;
 }
 
 int sse_merge_topk(sse_handle* h, const float* cand_scores_dev, const int32_t* cand_idx_dev, int Q, int C, int k,

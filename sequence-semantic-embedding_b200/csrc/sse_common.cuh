@@ -93,7 +93,10 @@ int cnn_forward_ws(const int32_t* tokens, int B, int T, const float* emb, int We
 
 // search_simt.cu
 int search_simt(const float* q, int Q, int E, const float* index, int64_t N, int64_t global_offset, int k,
-                float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches);
+                float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches,
+                int out_stride = 0);   // row stride of out_scores / out_idx in elements (0 = k)
+int merge_topk_strided(const float* cand_s, const int32_t* cand_i, int Q, int n_groups, int64_t group_stride, int row_stride,
+                       int k_in, int k, float* out_s, int32_t* out_i, int out_stride, cudaStream_t st, int64_t* launches);
 int merge_topk(const float* cand_s, const int32_t* cand_i, int Q, int C, int k, float* out_s, int32_t* out_i,
                cudaStream_t st, int64_t* launches);
 
@@ -108,13 +111,19 @@ struct TcIndex {
   alignas(64) unsigned char tmap3d64[128]; // 3-D, box = whole [64 x E] tile
   bool use3d = false;
   bool tmap_ok = false;
+  // layout of the last search_tc call's candidate bookkeeping (search_tc_stats)
+  const int32_t* last_cnt = nullptr; int64_t last_cnt_n = 0; const int32_t* last_overflow = nullptr; int last_Q = 0, last_items = 0;
 };
 bool search_tc_supported(int E, int64_t N, int k);
 int search_tc_max_rows(int E);   // query rows one search_tc call accepts
 int search_tc_prepare(TcIndex& ti, const float* index_f32, int64_t N, int E, cudaStream_t st, int64_t* launches);
 void search_tc_release(TcIndex& ti);
 int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
-              float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches);
+              float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches,
+              int out_stride = 0);
+// candidates / fallback rows of the LAST search_tc call on this index (synchronises; for benchmarks and tests)
+struct SearchStats { long long candidates = 0; int rows = 0, fallback_rows = 0, items = 0; };
+int search_tc_stats(const TcIndex& ti, SearchStats* out);
 
 // tok_prep.cu: token range check + pad-prefix bucketing (device pre-pass of the LSTM encoders)
 struct TokPrep {

@@ -49,6 +49,35 @@ def gather_and_merge(scores: torch.Tensor, ids: torch.Tensor, k: int, merge_fn: 
     return merge_fn(cs, ci, k)
 
 
+def exchange_own_rows(packed: torch.Tensor, out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
+    """The exchange step when every rank only needs the results of ITS OWN queries.  `packed` [G*R, 2k] holds this rank's
+    per-shard top-k of ALL G*R query rows, rank-major (rows [r*R, (r+1)*R) are rank r's queries).  One all-to-all sends
+    block r to rank r; the result [G*R, 2k] holds, for this rank's R queries, the packed top-k found in shard 0..G-1
+    (block g = from rank g) -- the layout sse_merge_packed / merge_packed_numpy consume.  Per rank G*R*2k*4 bytes in and
+    out and a merge over R rows, instead of an all-gather of G such blocks and a merge over G*R rows."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        if out is not None:
+            out.copy_(packed)
+            return out
+        return packed
+    if out is None:
+        out = torch.empty_like(packed)
+    dist.all_to_all_single(out, packed.contiguous(), group=group)
+    return out
+
+
+def merge_packed_numpy(recv: torch.Tensor, G: int, k: int):
+    """CPU stand-in of sse_merge_packed for the gloo tests: recv [G, R, 2k] -> (scores [R,k], ids [R,k]), (score desc, id asc)."""
+    r3 = recv.view(G, -1, 2 * k)
+    cs, ci = unpack_gathered(r3, k)
+    cs, ci = cs.numpy(), ci.numpy()
+    import numpy as _np
+    key_s = _np.where(ci < 0, -_np.inf, cs)
+    order = _np.lexsort((ci, -key_s), axis=1)[:, :k]
+    return torch.from_numpy(_np.take_along_axis(cs, order, 1)), torch.from_numpy(_np.take_along_axis(ci, order, 1))
+
+
 def allgather_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
     """Rank-major concatenation of equally shaped per-rank row blocks: [R, C] on every rank -> [G*R, C] on every rank
     (rank r's rows land at [r*R, (r+1)*R)).  The throughput-serving flow uses it to hand every rank the query encodings
@@ -106,10 +135,19 @@ class ShardedIndex(object):
 
     def search_distributed_queries(self, q_local_dev: torch.Tensor, k: int):
         """Every rank brings its OWN [Q_r, E] query vectors (same Q_r on all ranks): all-gather them, scan the local
-        shard for all G*Q_r, all-gather + merge the partial top-k; returns this rank's rows of the merged result."""
+        shard for all G*Q_r straight into one packed [G*Q_r, 2k] block (sse_search_packed), all-to-all so that every
+        rank receives the G per-shard blocks of its own rows, merge G*k -> k for those rows (sse_merge_packed).
+        Returns (scores [Q_r,k], ids [Q_r,k]) of this rank's queries."""
+        Qr = q_local_dev.shape[0]
         q_all = allgather_rows(q_local_dev)
-        s, i = self.search(q_all, k)
-        return rows_of_rank(s, self.rank, self.world), rows_of_rank(i, self.rank, self.world)
+        Q = q_all.shape[0]
+        packed = torch.empty(Q, 2 * k, device=q_all.device)
+        self.h.search_packed(q_all, Q, k, packed, torch.cuda.current_stream())
+        recv = exchange_own_rows(packed)
+        s = torch.empty(Qr, k, device=q_all.device)
+        i = torch.empty(Qr, k, device=q_all.device, dtype=torch.int32)
+        self.h.merge_packed(recv, self.world, Qr, k, s, i, torch.cuda.current_stream())
+        return s, i
 
 
 def allreduce_train_step(handle, src, tgt, labels, b_global: int):

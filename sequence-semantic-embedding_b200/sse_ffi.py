@@ -73,6 +73,9 @@ _SIGNATURES = {
     "sse_index_build": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int]),
     "sse_index_get": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "sse_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "sse_search_packed": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "sse_merge_packed": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "sse_search_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sse_merge_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "sse_query_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "sse_l2_normalize_rows": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
@@ -273,6 +276,19 @@ class Handle:
 
     def search(self, q_dev, Q: int, k: int, scores_dev, idx_dev, stream=None):
         self._check(self.lib.sse_search(self._h, _ptr(q_dev), Q, k, _ptr(scores_dev), _ptr(idx_dev), _stream_ptr(stream)))
+
+    def search_packed(self, q_dev, Q: int, k: int, packed_dev, stream=None):
+        """local top-k as one packed [Q,2k] fp32 block (scores | int32 global ids bit-cast): the NCCL message"""
+        self._check(self.lib.sse_search_packed(self._h, _ptr(q_dev), Q, k, _ptr(packed_dev), _stream_ptr(stream)))
+
+    def merge_packed(self, gathered_dev, G: int, Q: int, k: int, scores_dev, idx_dev, stream=None):
+        """gathered [G,Q,2k] packed blocks of G shards -> k best per row"""
+        self._check(self.lib.sse_merge_packed(self._h, _ptr(gathered_dev), G, Q, k, _ptr(scores_dev), _ptr(idx_dev), _stream_ptr(stream)))
+
+    def search_stats(self) -> Dict[str, int]:
+        c, r, f, it = C.c_int64(), C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.sse_search_stats(self._h, C.byref(c), C.byref(r), C.byref(f), C.byref(it)))
+        return {"candidates": int(c.value), "rows": int(r.value), "fallback_rows": int(f.value), "scan_items": int(it.value)}
 
     def merge_topk(self, cand_s_dev, cand_i_dev, Q: int, Cn: int, k: int, scores_dev, idx_dev, stream=None):
         self._check(self.lib.sse_merge_topk(self._h, _ptr(cand_s_dev), _ptr(cand_i_dev), Q, Cn, k, _ptr(scores_dev),

@@ -140,3 +140,58 @@ def test_allgather_rows_single_process_is_identity():
     y = torch.empty(3, 2)
     assert sse_dist.allgather_rows(x, y) is y and torch.equal(x, y)
     assert torch.equal(sse_dist.rows_of_rank(torch.arange(8).reshape(4, 2), 1, 2), torch.tensor([[4, 5], [6, 7]]))
+
+
+def _body_own_rows(rank, world, N, Q, E, k, out):
+    """bench.py --gpus N flow: packed per-shard top-k of all G*Q rows -> all-to-all of the per-owner row blocks -> merge for the own rows."""
+    rng = np.random.default_rng(21)
+    tgt = rng.standard_normal((N, E)).astype(np.float32)
+    tgt[3] = tgt[N - 2]                                                   # a tie across shards: the lower global id must win
+    q_all = rng.standard_normal((world * Q, E)).astype(np.float32)
+    lo, hi = sse_dist.shard_range(N, world, rank)
+    s, i = O.top_k_tf(q_all @ tgt[lo:hi].T, k, normalize_scores=False)   # this shard's top-k for ALL rows (stands in for sse_search_packed)
+    packed = sse_dist.pack_topk(torch.from_numpy(s.astype(np.float32)), torch.from_numpy((i + lo).astype(np.int32)))
+    recv = sse_dist.exchange_own_rows(packed)
+    ms, mi = sse_dist.merge_packed_numpy(recv, world, k)
+    ws, wi = O.top_k_tf(q_all[rank * Q:(rank + 1) * Q] @ tgt.T, k, normalize_scores=False)
+    ok = np.array_equal(mi.numpy(), wi) and float(np.abs(ms.numpy() - ws).max()) < 1e-6
+    flags = [torch.zeros(1) for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([1.0 if ok else 0.0]))
+    if rank == 0:
+        out.put((all(f.item() == 1.0 for f in flags), 0.0))
+
+
+def _worker_own(rank, world, port, N, Q, E, k, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _body_own_rows(rank, world, N, Q, E, k, out)
+    except Exception as e:
+        if rank == 0:
+            out.put((False, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_own_rows_all_to_all_then_merge_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker_own, args=(r, 2, port, 901, 7, 8, 4, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, err = out.get(timeout=90)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok, err
+
+
+def test_exchange_own_rows_single_process_is_identity():
+    x = torch.arange(12.0).reshape(3, 4)
+    assert sse_dist.exchange_own_rows(x) is x
+    s, i = sse_dist.merge_packed_numpy(sse_dist.pack_topk(torch.tensor([[0.5, 0.1]]), torch.tensor([[4, 9]], dtype=torch.int32)), 1, 2)
+    assert s.tolist() == [[0.5, 0.10000000149011612]] and i.tolist() == [[4, 9]]

@@ -38,6 +38,15 @@ def _worker(rank, world, port, out):
         s, i = sh.search(torch.from_numpy(q).cuda(), k)
         torch.cuda.synchronize()
         res = {"idx": i.cpu().numpy(), "sc": s.cpu().numpy()}
+        # throughput flow: every rank brings its own 150 queries; packed scan + all-to-all of the per-owner blocks + merge
+        Qr = Q // world
+        s2, i2 = sh.search_distributed_queries(torch.from_numpy(q[rank * Qr:(rank + 1) * Qr]).cuda(), k)
+        torch.cuda.synchronize()
+        own_ok = bool(np.array_equal(i2.cpu().numpy(), res["idx"][rank * Qr:(rank + 1) * Qr]) and
+                      np.abs(s2.cpu().numpy() - res["sc"][rank * Qr:(rank + 1) * Qr]).max() < 1e-6)
+        flags = [torch.zeros(1, device="cuda") for _ in range(world)]
+        dist.all_gather(flags, torch.tensor([1.0 if own_ok else 0.0], device="cuda"))
+        res["ok_own_rows"] = all(f.item() == 1.0 for f in flags)
         if rank == 0:
             h.index_set(tgt, global_offset=0)
             s1 = torch.empty(Q, k, device="cuda"); i1 = torch.empty(Q, k, device="cuda", dtype=torch.int32)
@@ -82,4 +91,5 @@ def test_two_gpu_sharded_search_and_dp_train():
     for p in procs:
         p.join(timeout=60)
     assert res["ok_search"], "sharded search differs from single-GPU search"
+    assert res["ok_own_rows"], "own-rows exchange (all-to-all + merge_packed) differs from the all-gather path"
     assert res["ok_train"], "data-parallel train step differs from single-GPU step"
