@@ -202,16 +202,23 @@ int sse_token_errors(sse_handle* h, int64_t* count_out, void* stream);
 /* bookkeeping of the LAST tcgen05 search on this handle (synchronises the device): candidates that passed the sampled
  * threshold summed over all rows, rows searched, rows that overflowed into the brute-force fallback, scan work items */
 int sse_search_stats(sse_handle* h, int64_t* candidates, int* rows, int* fallback_rows, int* items);
+/* test hook of the internal tcgen05 GEMM (csrc/gemm_tc.cu) behind the tensor-core train step and the CNN tower:
+ * D[M,N] = alpha * A[M,K] B[N,K]^T (+ beta D) with the fp32 inputs rounded to fp16 (fmt 0) or bf16 (fmt 1), fp32
+ * accumulation; split_k > 1 adds the partial sums atomically into D (beta must be 1 or D pre-zeroed). */
+int sse_debug_gemm_tc(sse_handle* h, const float* a_dev, const float* b_dev, int M, int N, int K, int fmt, int split_k,
+                      float alpha, float beta, float* d_dev, void* stream);
 /* number of kernels this library launched on the handle since creation */
 int64_t sse_launch_count(sse_handle* h);
-/* select kernel variants at run time: key in {"search", "encoder", "lstm_kernel", "pad_skip", "search_ctas"};
+/* select kernel variants at run time: key in {"search", "encoder", "lstm_kernel", "pad_skip", "search_ctas", "train"};
  * search: 0 auto, 1 simt-fp32, 2 tcgen05-fp16;  encoder: 0 auto, 1 simt-fp32, 2 tcgen05;
  * lstm_kernel (tcgen05 encoder only): 0 auto, 1 weight-streaming kernel, 2 cluster kernel (weights resident in
  * the shared memory of a thread-block cluster), 3 cluster kernel with the input projection tabulated per
  * vocabulary entry (V x 4H fp32 table, rebuilt when parameters change; the default when it fits in 2 GiB);
  * pad_skip: 1 (default) rows are bucketed by their number of leading PADs on the device and every kernel tile starts
  * from the tabulated pad-prefix state instead of running the PAD steps (all entry points), 0 off;  search_ctas: cap on the scan grid (0 = all SMs),
- * so that an encoder launched on another stream can run concurrently on the remaining SMs. */
+ * so that an encoder launched on another stream can run concurrently on the remaining SMs;
+ * train: 0 auto (tensor cores when the handle was created with SSE_PRECISION_TC and the shapes allow), 1 fp32 SIMT
+ * (parity mode), 2 tensor cores (bf16 operands, fp32 accumulation / state / optimizer; error if unsupported). */
 int sse_set_option(sse_handle* h, const char* key, int value);
 /* names + durations of the last timed kernels are not kept here: time with CUDA events on `stream`. */
 

@@ -69,4 +69,56 @@ int cnn_forward_ws(const int32_t* tokens, int B, int T, const float* emb, int We
   return SSE_OK;
 }
 
+// ---- tensor-core path (gemm_tc.cu): fp16 operands / fp32 accumulate; the [B*T, F] convolution output never exists
+void cnn_tc_release(CnnTc& ct) {
+  for (int i = 0; i < SSE_MAX_CNN_FILTERS; ++i) { if (ct.wt[i]) cudaFree(ct.wt[i]); ct.wt[i] = nullptr; }
+  if (ct.mt) cudaFree(ct.mt);
+  ct.mt = nullptr; ct.valid = false;
+}
+
+bool cnn_tc_supported(int We, int T, const CnnTower& tw) {
+  if (We % 8 != 0 || tw.sumF % 8 != 0) return false;
+  for (int i = 0; i < tw.nf; ++i)
+    if (T - tw.ksize[i] + 1 > 128 || T - tw.ksize[i] + 1 <= 0) return false;
+  return true;
+}
+
+// 16-bit K-major copies of the filters ([F, k*We]) and of the projection ([E, sumF]); rebuilt when the weights change
+int cnn_tc_prepare(CnnTc& ct, const CnnTower& tw, int We, int E, cudaStream_t st, int64_t* launches) {
+  for (int i = 0; i < tw.nf; ++i) {
+    const int K = tw.ksize[i] * We, F = tw.nfilt[i];
+    if (!ct.wt[i]) SSE_CUDA_OK(cudaMalloc(&ct.wt[i], (size_t)F * K * 2));
+    SSE_TRY(transpose_to_16(tw.W[i], K, F, F, ct.wt[i], K, 0, st, launches));       // W [k*We, F] -> [F, k*We]
+  }
+  if (!ct.mt) SSE_CUDA_OK(cudaMalloc(&ct.mt, (size_t)E * tw.sumF * 2));
+  SSE_TRY(transpose_to_16(tw.M, tw.sumF, E, E, ct.mt, tw.sumF, 0, st, launches));   // M [sumF, E] -> [E, sumF]
+  ct.valid = true;
+  return SSE_OK;
+}
+
+size_t cnn_tc_ws_bytes(int nb, int T, int We, const CnnTower& tw) {
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  return al((size_t)nb * T * We * 2) + al((size_t)nb * tw.sumF * 4) + al((size_t)nb * tw.sumF * 2);
+}
+
+// tokens [nb,T] -> proj [nb,E] (un-normalised encodings): gather (fp16) -> per filter width fused conv+bias+ReLU+max-pool
+// GEMM -> fp16 copy of the pooled features -> projection GEMM
+int cnn_forward_tc(const int32_t* tokens, int nb, int T, const float* emb, int We, int E, const CnnTower& tw, const CnnTc& ct, void* ws,
+                   float* proj, cudaStream_t st, int64_t* launches) {
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  uint16_t* x16 = reinterpret_cast<uint16_t*>(w);
+  float* pool = reinterpret_cast<float*>(w + al((size_t)nb * T * We * 2));
+  uint16_t* pool16 = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(pool) + al((size_t)nb * tw.sumF * 4));
+  SSE_TRY(gather_rows_16(tokens, (int64_t)nb * T, emb, We, We, x16, 0, st, launches));
+  SSE_CUDA_OK(cudaMemsetAsync(pool, 0, (size_t)nb * tw.sumF * 4, st));
+  int off = 0;
+  for (int i = 0; i < tw.nf; ++i) {
+    SSE_TRY(cnn_conv_pool_tc(x16, nb, T, We, tw.ksize[i], ct.wt[i], tw.nfilt[i], tw.b[i], pool, tw.sumF, off, 0, st, launches));
+    off += tw.nfilt[i];
+  }
+  SSE_TRY(convert_to_16(pool, nb, tw.sumF, tw.sumF, pool16, tw.sumF, 0, st, launches));
+  return gemm_tc(pool16, tw.sumF, ct.mt, tw.sumF, nb, E, tw.sumF, 1.f, 0.f, proj, E, 0, 1, nullptr, 0, st, launches);
+}
+
 }  // namespace sse

@@ -73,6 +73,7 @@ void invalidate_derived(sse_handle* h) {
   h->tct[0].valid = h->tct[1].valid = false;
   h->tct[0].ptable_valid = h->tct[1].ptable_valid = false;
   h->emb_f16_valid = false;
+  h->cnn_tc[0].valid = h->cnn_tc[1].valid = false;
 }
 
 bool side_is_cnn(const sse_handle* h, int side) {
@@ -177,6 +178,19 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens_in, int B, floa
   };
   if (is_cnn) {
     const CnnTower& tw = h->cnn[side];
+    const bool cnn_tc = (h->opt_encoder == 2 || (h->opt_encoder == 0 && c.precision == SSE_PRECISION_TC)) && cnn_tc_supported(We, T, tw);
+    if (h->opt_encoder == 2 && !cnn_tc) { set_error("tcgen05 CNN tower needs We%%8==0, sum(filters)%%8==0, T-k+1 <= 128"); return SSE_EINVAL; }
+    if (cnn_tc) {
+      CnnTc& ct = h->cnn_tc[side];
+      if (!ct.valid) SSE_TRY(cnn_tc_prepare(ct, tw, We, E, st, &h->launches));
+      const int slab = std::min(B, 8192);
+      SSE_TRY(h->enc_ws.ensure(cnn_tc_ws_bytes(slab, T, We, tw)));
+      for (int b0 = 0; b0 < B; b0 += slab) {
+        const int nb = std::min(slab, B - b0);
+        SSE_TRY(cnn_forward_tc(tokens + (size_t)b0 * T, nb, T, emb, We, E, tw, ct, h->enc_ws.p, proj + (size_t)b0 * E, st, &h->launches));
+      }
+      return finish();
+    }
     int maxF = 0;
     for (int i = 0; i < tw.nf; ++i) maxF = std::max(maxF, tw.nfilt[i]);
     // process in slabs so the conv scratch stays bounded
@@ -389,13 +403,14 @@ int sse_destroy(sse_handle* h) {
   h->enc_ws.release(); h->search_ws.release(); h->io_ws.release(); h->train_ws.release();
   h->pad[0].buf.release(); h->pad[1].buf.release();
   h->pad_tc[0].buf.release(); h->pad_tc[1].buf.release();
-  h->tok_ws.release(); h->proj_ws.release();
+  h->tok_ws.release(); h->proj_ws.release(); h->train_tc_ws.release();
   if (h->tok_bad) cudaFree(h->tok_bad);
   if (h->index_f32 && h->index_owned) cudaFree(h->index_f32);
   if (h->grad_arena) cudaFree(h->grad_arena);
   search_tc_release(h->tc);
   lstm_tc_release(h->tct[0]); lstm_tc_release(h->tct[1]);
   lstm_ptable_release(h->tct[0]); lstm_ptable_release(h->tct[1]);
+  cnn_tc_release(h->cnn_tc[0]); cnn_tc_release(h->cnn_tc[1]);
   if (h->emb_f16) cudaFree(h->emb_f16);
   delete h;
   return SSE_OK;
@@ -592,6 +607,20 @@ int sse_token_errors(sse_handle* h, int64_t* count_out, void* stream) {
   return SSE_OK;
 }
 
+int sse_debug_gemm_tc(sse_handle* h, const float* a_dev, const float* b_dev, int M, int N, int K, int fmt, int split_k, float alpha, float beta,
+                      float* d_dev, void* stream) {
+  if (!h || !a_dev || !b_dev || !d_dev || M < 1 || N < 1 || K < 1 || (fmt != 0 && fmt != 1)) { set_error("sse_debug_gemm_tc: bad argument"); return SSE_EINVAL; }
+  SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ldk = (K + 7) / 8 * 8;
+  SSE_TRY(h->io_ws.ensure(((size_t)M + N) * ldk * 2 + 512));
+  uint16_t* a16 = h->io_ws.as<uint16_t>();
+  uint16_t* b16 = a16 + ((size_t)M * ldk + 127) / 128 * 128;
+  SSE_TRY(convert_to_16(a_dev, M, K, K, a16, ldk, fmt, st, &h->launches));
+  SSE_TRY(convert_to_16(b_dev, N, K, K, b16, ldk, fmt, st, &h->launches));
+  return gemm_tc(a16, ldk, b16, ldk, M, N, K, alpha, beta, d_dev, N, fmt, split_k, nullptr, 0, st, &h->launches);
+}
+
 int sse_l2_normalize_rows(sse_handle* h, float* x_dev, int rows, int cols, void* stream) {
   if (!h || !x_dev || rows < 0 || cols < 1) { set_error("sse_l2_normalize_rows: bad argument"); return SSE_EINVAL; }
   SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
@@ -623,6 +652,7 @@ int sse_set_option(sse_handle* h, const char* key, int value) {
   if (!h || !key) return SSE_EINVAL;
   if (!strcmp(key, "search")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_search = value; return SSE_OK; }
   if (!strcmp(key, "encoder")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_encoder = value; return SSE_OK; }
+  if (!strcmp(key, "train")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_train = value; return SSE_OK; }
   if (!strcmp(key, "pad_skip")) { h->opt_pad_skip = value != 0; return SSE_OK; }
   if (!strcmp(key, "lstm_kernel")) { if (value < 0 || value > 3) return SSE_EINVAL; h->opt_lstm_kernel = value; return SSE_OK; }
   if (!strcmp(key, "search_ctas")) { if (value < 0) return SSE_EINVAL; h->opt_search_ctas = value; return SSE_OK; }

@@ -91,6 +91,27 @@ int cnn_forward_ws(const int32_t* tokens, int B, int T, const float* emb, int We
                    float* conv, float* pool /*[B,sumF]*/, int32_t* argmax /*optional [B,sumF]*/, cudaStream_t st,
                    int64_t* launches);
 
+// gemm_tc.cu: tcgen05 GEMM  D[M,N] = alpha A[M,K] B[N,K]^T (+ beta D), 16-bit K-major operands (fmt 0 fp16, 1 bf16)
+int gemm_tc(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int M, int N, int K, float alpha, float beta, float* D, int64_t ldd,
+            int fmt, int split_k, uint16_t* D16, int64_t ldd16, cudaStream_t st, int64_t* launches);
+int convert_to_16(const float* src, int64_t rows, int cols, int64_t lds, uint16_t* dst, int64_t ldd, int fmt, cudaStream_t st, int64_t* launches);
+int transpose_to_16(const float* src, int rows, int cols, int64_t lds, uint16_t* dst, int64_t ldd, int fmt, cudaStream_t st, int64_t* launches);
+int gather_rows_16(const int32_t* tokens, int64_t n_tok, const float* emb, int We, int ld, uint16_t* out, int fmt, cudaStream_t st, int64_t* launches);
+int cnn_conv_pool_tc(const uint16_t* X, int n_seq, int T, int ldx, int kf, const uint16_t* Wt, int F, const float* bias, float* pool, int pool_ld,
+                     int pool_off, int fmt, cudaStream_t st, int64_t* launches);
+// cnn.cu, tensor-core path
+struct CnnTc {
+  uint16_t* wt[SSE_MAX_CNN_FILTERS] = {};   // [F, k*We] fp16
+  uint16_t* mt = nullptr;                   // [E, sumF] fp16
+  bool valid = false;
+};
+bool cnn_tc_supported(int We, int T, const CnnTower& tw);
+int cnn_tc_prepare(CnnTc& ct, const CnnTower& tw, int We, int E, cudaStream_t st, int64_t* launches);
+void cnn_tc_release(CnnTc& ct);
+size_t cnn_tc_ws_bytes(int nb, int T, int We, const CnnTower& tw);
+int cnn_forward_tc(const int32_t* tokens, int nb, int T, const float* emb, int We, int E, const CnnTower& tw, const CnnTc& ct, void* ws,
+                   float* proj, cudaStream_t st, int64_t* launches);
+
 // search_simt.cu
 int search_simt(const float* q, int Q, int E, const float* index, int64_t N, int64_t global_offset, int k,
                 float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches,

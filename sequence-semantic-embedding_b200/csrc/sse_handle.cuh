@@ -21,6 +21,7 @@ struct sse_handle {
   int tgt_table_param = -1;
   sse::LstmTower lstm[2];           // [SSE_SIDE_SRC], [SSE_SIDE_TGT]
   sse::CnnTower cnn[2];
+  sse::CnnTc cnn_tc[2];             // fp16 K-major copies of the CNN filters / projection (lazy, invalidated with the weights)
   sse::PadTable pad[2];             // pad-prefix state tables, fp32 SIMT arithmetic
   sse::PadTable pad_tc[2];          // the same in the arithmetic of lstm_ptable_kernel
   sse::TcTower tct[2];              // tensor-core copies of the LSTM weights (lazy, invalidated with the weights)
@@ -36,13 +37,14 @@ struct sse_handle {
   sse::TcIndex tc;
 
   // workspaces
-  sse::Scratch enc_ws, search_ws, io_ws, train_ws, tok_ws, proj_ws;
+  sse::Scratch enc_ws, search_ws, io_ws, train_ws, train_tc_ws, tok_ws, proj_ws;
   int* tok_bad = nullptr;           // device counter: out-of-range token ids seen by the pre-pass (sticky until read)
   float* grad_arena = nullptr;      // dense gradients, laid out by Param::grad_off, then the dense embedding gradient
   int64_t grad_floats = 0;          // dense (non-embedding) part
   int64_t arena_floats = 0;
 
   int opt_search = 0, opt_encoder = 0;
+  int opt_train = 0;                // 0 = auto (tensor cores with SSE_PRECISION_TC), 1 = fp32 SIMT (parity mode), 2 = tensor cores (bf16 operands)
   int opt_lstm_kernel = 0;          // 0 = auto by batch size; 1 = weight-streaming kernel (lstm_tc.cu); 2 = cluster kernel (lstm_cluster.cu)
   int opt_search_ctas = 0;          // 0 = all SMs; else cap on the scan grid (leaves SMs to a concurrent encoder)
   bool opt_pad_skip = true;         // per-tile pad-prefix start of the LSTM towers (tok_prep.cu)

@@ -14,6 +14,7 @@
 #include "sse_common.cuh"
 #include "sse_handle.cuh"
 #include <math_constants.h>
+#include <cuda_bf16.h>
 
 using namespace sse;
 
@@ -207,6 +208,226 @@ bool trainable_mode(const sse_handle* h) {
   return h->cfg.network_mode == SSE_MODE_DUAL_ENCODER || h->cfg.network_mode == SSE_MODE_SHARED_ENCODER;
 }
 
+// ======================================================================================================================
+// Tensor-core training path (bf16 operands, fp32 accumulate / state / stash; BASELINE config 4).  Same graph as the fp32
+// path; every contraction is a gemm_tc.cu GEMM over TIME-MAJOR 16-bit operand copies:
+//   forward   ZX = X Wx^T (one GEMM over all T*B rows), then per step z_t = ZX[t] += h_{t-1} Wh^T and a gate kernel;
+//   backward  per step dz_t (gate kernel, written as bf16) and dh_{t-1} = dz_t K[We:]^T; after the loop
+//             dX = dZ K[:We]^T (one GEMM), dK[:We] += X^T dZ and dK[We:] += Hprev^T dZ (split-K GEMMs over T*B rows with
+//             atomic fp32 accumulation into the gradient arena), db = column sums of dZ.
+struct TcTrainBufs {
+  uint16_t *x16, *h16, *dz16, *xT, *hT, *dzT, *kT16, *k16;
+  float *zx, *dx, *dh, *dc, *c_zero;
+  int32_t* tok_tm;
+};
+
+__global__ void tokens_time_major_kernel(const int32_t* __restrict__ tok, int B, int T, int32_t* __restrict__ out) {
+  const int64_t total = (int64_t)B * T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i / B), b = (int)(i - (int64_t)t * B);
+    out[i] = tok[(size_t)b * T + t];
+  }
+}
+
+__device__ __forceinline__ uint16_t bf16_bits(float v) {
+  __nv_bfloat16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&b);
+}
+
+// z [B,4H] (pre-activations without bias, TF gate order i,j,f,o) -> gates stash, c, h (bf16 operand copy + optional fp32)
+__global__ void lstm_fwd_gates_kernel(const float* __restrict__ z, const float* __restrict__ bias, const float* __restrict__ c_prev, int B, int H,
+                                      float* __restrict__ sg /*[B,5H]*/, float* __restrict__ c_out /*[B,H]*/, uint16_t* __restrict__ h16 /*[B,H]*/,
+                                      float* __restrict__ h32 /*optional [B,H]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, u = i - b * H;
+  const float* zr = z + (size_t)b * 4 * H + u;
+  const float si = sigmoidf_(zr[0] + __ldg(bias + u));
+  const float tj = tanhf(zr[H] + __ldg(bias + H + u));
+  const float sf = sigmoidf_(zr[2 * H] + __ldg(bias + 2 * H + u) + 1.0f);      // forget_bias = 1.0 added at run time
+  const float so = sigmoidf_(zr[3 * H] + __ldg(bias + 3 * H + u));
+  const float cn = (c_prev ? c_prev[i] : 0.f) * sf + si * tj;
+  const float tc = tanhf(cn);
+  const float hn = tc * so;
+  float* g = sg + (size_t)b * 5 * H + u;
+  g[0] = si; g[H] = tj; g[2 * H] = sf; g[3 * H] = so; g[4 * H] = tc;
+  c_out[i] = cn;
+  h16[i] = bf16_bits(hn);
+  if (h32) h32[i] = hn;
+}
+
+// backward gate step writing dz as the bf16 operand of the three gradient GEMMs
+__global__ void lstm_bwd_gates16_kernel(const float* __restrict__ dh, int ldh, float* __restrict__ dc, const float* __restrict__ g,
+                                        const float* __restrict__ c_prev, int B, int H, uint16_t* __restrict__ dz16 /*[B,4H]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, u = i - b * H;
+  const float* gr = g + (size_t)b * 5 * H + u;
+  const float si = gr[0], tj = gr[H], sf = gr[2 * H], so = gr[3 * H], tc = gr[4 * H];
+  const float dhv = dh[(size_t)b * ldh + u];
+  const float dcv = dc[i] + dhv * so * (1.f - tc * tc);
+  const float cp = c_prev ? c_prev[i] : 0.f;
+  uint16_t* zr = dz16 + (size_t)b * 4 * H + u;
+  zr[0] = bf16_bits(dcv * tj * si * (1.f - si));
+  zr[H] = bf16_bits(dcv * si * (1.f - tj * tj));
+  zr[2 * H] = bf16_bits(dcv * cp * sf * (1.f - sf));
+  zr[3 * H] = bf16_bits(dhv * tc * so * (1.f - so));
+  dc[i] = dcv * sf;
+}
+
+// 16-bit tiled transpose: dst[c][r] = src[r][c], dst leading dimension ldd >= rows (pad zeroed)
+__global__ void transpose_16_kernel(const uint16_t* __restrict__ s, int64_t rows, int cols, int64_t lds, uint16_t* __restrict__ d, int64_t ldd) {
+  __shared__ uint16_t tile[32][34];
+  const int64_t r0 = (int64_t)blockIdx.y * 32;
+  const int c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? s[(size_t)r * lds + c] : (uint16_t)0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t r = r0 + threadIdx.x;
+    if (c < cols && r < ldd) d[(size_t)c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
+// out[j] += sum_r x[r][j] over bf16 rows (db = column sums of dZ)
+__global__ void colsum16_kernel(const uint16_t* __restrict__ x, int64_t rows, int cols, float* __restrict__ out) {
+  __shared__ float sh[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  float s = 0.f;
+  if (col < cols)
+    for (int64_t r = rl; r < rows; r += 8) {
+      const uint32_t bits = (uint32_t)x[(size_t)r * cols + col] << 16;
+      s += __uint_as_float(bits);
+    }
+  sh[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x & 31];
+    out[col] += t;
+  }
+}
+
+bool train_tc_supported(const sse_handle* h, int B) {
+  const int We = h->cfg.embedding_size;
+  return We % 8 == 0 && h->lstm[0].H % 8 == 0 && h->lstm[1].H % 8 == 0 && B % 8 == 0;
+}
+
+static int transpose16(const uint16_t* s, int64_t rows, int cols, int64_t lds, uint16_t* d, int64_t ldd, cudaStream_t st, int64_t* launches) {
+  dim3 grid(cdiv(cols, 32), (unsigned)cdiv64(ldd, 32)), block(32, 8);
+  transpose_16_kernel<<<grid, block, 0, st>>>(s, rows, cols, lds, d, ldd);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
+// forward + backward of ONE tower on the tensor cores.  u [B,E] out (forward), then du -> grads into the arena.
+// Split in two calls because the pair loss needs both towers' forward results first.
+struct TcTowerState {
+  float *sg, *sc, *u, *hlast;      // stash [T,B,5H], [T,B,H]; projection; fp32 h_T
+  uint16_t* h16;                   // [T,B,H] bf16
+  uint16_t* x16;                   // [T,B,We] bf16
+};
+
+int train_tc_forward(sse_handle* h, int s, const int32_t* tok, int B, uint8_t* ws, size_t* ws_off, TcTowerState* ts, uint16_t* kT16,
+                     float* zx, cudaStream_t st) {
+  const sse_config& c = h->cfg;
+  const int T = c.max_seq_length, We = c.embedding_size, E = c.encoding_size;
+  const LstmTower& tw = h->lstm[s];
+  const int H = tw.H, ld = We + H;
+  const int64_t TB = (int64_t)T * B;
+  auto carve = [&](size_t bytes) { size_t o = *ws_off; *ws_off = (o + bytes + 255) / 256 * 256; return ws + o; };
+  ts->sg = reinterpret_cast<float*>(carve((size_t)TB * 5 * H * 4));
+  ts->sc = reinterpret_cast<float*>(carve((size_t)TB * H * 4));
+  ts->u = reinterpret_cast<float*>(carve((size_t)B * E * 4));
+  ts->hlast = reinterpret_cast<float*>(carve((size_t)B * H * 4));
+  ts->h16 = reinterpret_cast<uint16_t*>(carve((size_t)TB * H * 2));
+  ts->x16 = reinterpret_cast<uint16_t*>(carve((size_t)TB * We * 2));
+  int32_t* tok_tm = reinterpret_cast<int32_t*>(carve((size_t)TB * 4));
+  tokens_time_major_kernel<<<(int)std::min<int64_t>(cdiv64(TB, 256), 148 * 4), 256, 0, st>>>(tok, B, T, tok_tm);
+  ++h->launches;
+  SSE_TRY(gather_rows_16(tok_tm, TB, h->params[h->emb_param].dev, We, We, ts->x16, 1, st, &h->launches));
+  // K^T [4H, We+H] bf16: B operand of both forward GEMMs
+  SSE_TRY(transpose_to_16(tw.K, ld, 4 * H, 4 * H, kT16, ld, 1, st, &h->launches));
+  // ZX = X Wx^T over all T*B rows
+  SSE_TRY(gemm_tc(ts->x16, We, kT16, ld, (int)TB, 4 * H, We, 1.f, 0.f, zx, 4 * H, 1, 1, nullptr, 0, st, &h->launches));
+  for (int t = 0; t < T; ++t) {
+    float* z_t = zx + (size_t)t * B * 4 * H;
+    if (t > 0)   // z_t += h_{t-1} Wh^T
+      SSE_TRY(gemm_tc(ts->h16 + (size_t)(t - 1) * B * H, H, kT16 + We, ld, B, 4 * H, H, 1.f, 1.f, z_t, 4 * H, 1, 1, nullptr, 0, st, &h->launches));
+    lstm_fwd_gates_kernel<<<cdiv(B * H, 256), 256, 0, st>>>(z_t, tw.b, t > 0 ? ts->sc + (size_t)(t - 1) * B * H : nullptr, B, H,
+                                                            ts->sg + (size_t)t * B * 5 * H, ts->sc + (size_t)t * B * H,
+                                                            ts->h16 + (size_t)t * B * H, t == T - 1 ? ts->hlast : nullptr);
+    ++h->launches;
+  }
+  SSE_TRY(sgemm(false, false, B, E, H, 1.f, ts->hlast, H, tw.M, E, 0.f, ts->u, E, st, &h->launches));
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
+int train_tc_backward(sse_handle* h, int s, const int32_t* tok, int B, const TcTowerState& ts, const float* du, uint8_t* ws, size_t ws_off,
+                      uint16_t* k16, float* G, float* touched, float* scalars, cudaStream_t st) {
+  const sse_config& c = h->cfg;
+  const int T = c.max_seq_length, We = c.embedding_size, E = c.encoding_size;
+  const LstmTower& tw = h->lstm[s];
+  const int H = tw.H, ld = We + H;
+  const int64_t TB = (int64_t)T * B;
+  const int64_t ldT = (TB + 7) / 8 * 8;
+  float* arena = h->grad_arena;
+  float* gM = arena + h->params[tw.mparam].grad_off;
+  float* gK = arena + h->params[tw.kparam].grad_off;
+  float* gb = arena + h->params[tw.bparam].grad_off;
+  auto carve = [&](size_t bytes) { size_t o = ws_off; ws_off = (o + bytes + 255) / 256 * 256; return ws + o; };
+  uint16_t* dz16 = reinterpret_cast<uint16_t*>(carve((size_t)TB * 4 * H * 2));
+  uint16_t* dzT = reinterpret_cast<uint16_t*>(carve((size_t)4 * H * ldT * 2));
+  uint16_t* xT = reinterpret_cast<uint16_t*>(carve((size_t)We * ldT * 2));
+  uint16_t* hT = reinterpret_cast<uint16_t*>(carve((size_t)H * ldT * 2));
+  float* dx = reinterpret_cast<float*>(carve((size_t)TB * We * 4));
+  float* dh = reinterpret_cast<float*>(carve((size_t)2 * B * H * 4));
+  float* dc = reinterpret_cast<float*>(carve((size_t)B * H * 4));
+  // dM += h_last^T du ; dh_T = du M^T   (small: fp32 SIMT)
+  SSE_TRY(sgemm(true, false, H, E, B, 1.f, ts.hlast, H, du, E, 1.f, gM, E, st, &h->launches));
+  SSE_TRY(sgemm(false, true, B, H, E, 1.f, du, E, tw.M, E, 0.f, dh, H, st, &h->launches));
+  SSE_CUDA_OK(cudaMemsetAsync(dc, 0, (size_t)B * H * 4, st));
+  // K [We+H, 4H] bf16: B operand (N = rows of K, K-dim = 4H) of dz K^T
+  SSE_TRY(convert_to_16(tw.K, ld, 4 * H, 4 * H, k16, 4 * H, 1, st, &h->launches));
+  float* dh_cur = dh;
+  float* dh_next = dh + (size_t)B * H;
+  for (int t = T - 1; t >= 0; --t) {
+    uint16_t* dz_t = dz16 + (size_t)t * B * 4 * H;
+    lstm_bwd_gates16_kernel<<<cdiv(B * H, 256), 256, 0, st>>>(dh_cur, H, dc, ts.sg + (size_t)t * B * 5 * H,
+                                                              t > 0 ? ts.sc + (size_t)(t - 1) * B * H : nullptr, B, H, dz_t);
+    ++h->launches;
+    if (t > 0) {   // dh_{t-1} = dz_t K[We:]^T
+      SSE_TRY(gemm_tc(dz_t, 4 * H, k16 + (size_t)We * 4 * H, 4 * H, B, H, 4 * H, 1.f, 0.f, dh_next, H, 1, 1, nullptr, 0, st, &h->launches));
+      std::swap(dh_cur, dh_next);
+    }
+  }
+  // dX = dZ K[:We]^T over all rows; embedding IndexedSlices from it
+  SSE_TRY(gemm_tc(dz16, 4 * H, k16, 4 * H, (int)TB, We, 4 * H, 1.f, 0.f, dx, We, 1, 1, nullptr, 0, st, &h->launches));
+  embed_scatter_kernel<<<148 * 4, 256, 0, st>>>(tok, B, T, dx, We, We, G, touched, scalars);
+  ++h->launches;
+  // dK[:We] += X^T dZ ;  dK[We:] += Hprev^T dZ (t >= 1) ; db += colsum dZ : K-major copies = transposes over the T*B rows
+  SSE_TRY(transpose16(dz16, TB, 4 * H, 4 * H, dzT, ldT, st, &h->launches));
+  SSE_TRY(transpose16(ts.x16, TB, We, We, xT, ldT, st, &h->launches));
+  const int splits = 8;
+  SSE_TRY(gemm_tc(xT, ldT, dzT, ldT, We, 4 * H, (int)TB, 1.f, 1.f, gK, 4 * H, 1, splits, nullptr, 0, st, &h->launches));
+  if (T > 1) {
+    SSE_TRY(transpose16(ts.h16, TB - B, H, H, hT, ldT, st, &h->launches));
+    SSE_TRY(gemm_tc(hT, ldT, dzT + B, ldT, H, 4 * H, (int)(TB - B), 1.f, 1.f, gK + (size_t)We * 4 * H, 4 * H, 1, splits, nullptr, 0, st, &h->launches));
+  }
+  colsum16_kernel<<<cdiv(4 * H, 32), 256, 0, st>>>(dz16, TB, 4 * H, gb);
+  ++h->launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -278,6 +499,55 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
   // InvalidArgument): replaced by PAD and counted; reported when the step hands scalars back / by sse_token_errors
   SSE_TRY(sanitize_tokens_inplace(d_src, (int64_t)2 * B * T, V, h->tok_bad, st, &h->launches));
   const float* emb = h->params[h->emb_param].dev;
+
+  // ---- tensor-core path (bf16 operands): option train = 2, or auto with the tensor-core precision and supported shapes
+  const bool want_tc = h->opt_train == 2 || (h->opt_train == 0 && c.precision == SSE_PRECISION_TC);
+  if (want_tc && !train_tc_supported(h, B)) {
+    if (h->opt_train == 2) { set_error("tensor-core train step needs We%%8==0, H%%8==0, B%%8==0 (We=%d B=%d)", We, B); return SSE_EINVAL; }
+  } else if (want_tc) {
+    const int64_t TB = (int64_t)T * B;
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t need = al((size_t)TB * 4 * Hmax * 4) + al((size_t)4 * Hmax * (We + Hmax) * 2) * 2 + 2 * al((size_t)B * E * 4) + 3 * al((size_t)B * 4);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int H = h->lstm[s2].H;
+      need += al((size_t)TB * 5 * H * 4) + al((size_t)TB * H * 4) + al((size_t)B * E * 4) + al((size_t)B * H * 4) + al((size_t)TB * H * 2) + al((size_t)TB * We * 2) + al((size_t)TB * 4);
+    }
+    const int64_t ldT = (TB + 7) / 8 * 8;
+    need += al((size_t)TB * 4 * Hmax * 2) + al((size_t)4 * Hmax * ldT * 2) + al((size_t)We * ldT * 2) + al((size_t)Hmax * ldT * 2) + al((size_t)TB * We * 4) +
+            al((size_t)2 * B * Hmax * 4) + al((size_t)B * Hmax * 4) + 4096;
+    SSE_TRY(h->train_tc_ws.ensure(need));
+    uint8_t* tw8 = h->train_tc_ws.as<uint8_t>();
+    size_t o2 = 0;
+    auto carve8 = [&](size_t bytes) { size_t o = o2; o2 = al(o2 + bytes); return tw8 + o; };
+    float* zx = reinterpret_cast<float*>(carve8((size_t)TB * 4 * Hmax * 4));
+    uint16_t* kT16 = reinterpret_cast<uint16_t*>(carve8((size_t)4 * Hmax * (We + Hmax) * 2));
+    uint16_t* k16 = reinterpret_cast<uint16_t*>(carve8((size_t)4 * Hmax * (We + Hmax) * 2));
+    float* du_tc[2] = {reinterpret_cast<float*>(carve8((size_t)B * E * 4)), reinterpret_cast<float*>(carve8((size_t)B * E * 4))};
+    float* rl = reinterpret_cast<float*>(carve8((size_t)B * 4));
+    float* rp = reinterpret_cast<float*>(carve8((size_t)B * 4));
+    float* rn = reinterpret_cast<float*>(carve8((size_t)B * 4));
+    TcTowerState tst[2];
+    for (int s2 = 0; s2 < 2; ++s2)
+      SSE_TRY(train_tc_forward(h, s2, s2 == 0 ? d_src : d_tgt, B, tw8, &o2, &tst[s2], kT16, zx, st));
+    pair_loss_kernel<<<cdiv(B, 8), 256, 0, st>>>(tst[0].u, tst[1].u, d_lab, B, E, 1.0f / (float)B_global, du_tc[0], du_tc[1], rl, rp, rn, nullptr);
+    ++h->launches;
+    reduce_rows_kernel<<<1, 256, 0, st>>>(rl, rp, rn, B, scalars);
+    ++h->launches;
+    for (int s2 = 0; s2 < 2; ++s2)
+      SSE_TRY(train_tc_backward(h, s2, s2 == 0 ? d_src : d_tgt, B, tst[s2], du_tc[s2], tw8, o2, k16, G, touched, scalars, st));
+    SSE_CUDA_OK(cudaGetLastError());
+    if (loss_host || acc_host) {
+      float sc[4];
+      SSE_CUDA_OK(cudaMemcpyAsync(sc, scalars, 16, cudaMemcpyDeviceToHost, st));
+      SSE_CUDA_OK(cudaStreamSynchronize(st));
+      if (loss_host) *loss_host = sc[1];
+      if (acc_host) *acc_host = sc[2] + sc[3];
+      int bad = 0;
+      SSE_TRY(take_token_errors(h, st, &bad));
+      if (bad) { set_error("train step: %d token id(s) outside [0, vocab_size=%d)", bad, V); return SSE_EINVAL; }
+    }
+    return SSE_OK;
+  }
 
   // ---- forward with stash
   TowerStash ts[2];

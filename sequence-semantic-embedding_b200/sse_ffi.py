@@ -90,6 +90,7 @@ _SIGNATURES = {
     "sse_lr_decay": (C.c_int, [_P]),
     "sse_get_scalars": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "sse_set_scalars": (C.c_int, [_P, C.c_float, C.c_int64]),
+    "sse_debug_gemm_tc": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P, _P]),
     "sse_launch_count": (C.c_int64, [_P]),
     "sse_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "sse_tsv_last_error": (C.c_char_p, []),
@@ -375,6 +376,10 @@ class Handle:
 
     def set_scalars(self, lr: float, global_step: int):
         self._check(self.lib.sse_set_scalars(self._h, lr, global_step))
+
+    def debug_gemm_tc(self, a_dev, b_dev, M: int, N: int, K: int, d_dev, fmt: int = 1, split_k: int = 1, alpha: float = 1.0, beta: float = 0.0, stream=None):
+        """test hook: D[M,N] = alpha A[M,K] B[N,K]^T (+ beta D) on the internal tcgen05 GEMM (fp32 in / out, 16-bit operands)"""
+        self._check(self.lib.sse_debug_gemm_tc(self._h, _ptr(a_dev), _ptr(b_dev), M, N, K, fmt, split_k, alpha, beta, _ptr(d_dev), _stream_ptr(stream)))
 
     def launch_count(self) -> int:
         return int(self.lib.sse_launch_count(self._h))
