@@ -566,7 +566,7 @@ def run_b200(args):
             ms_t = float(tt.item())
         fl = 3.0 * Bt * world * 2 * F_ENC
         train = {"metric": "train-step/s", "value": args.train_steps / (ms_t * 1e-3), "ms_per_step": ms_t / args.train_steps,
-                 "pair_rows_per_gpu": Bt, "pair_rows_global": Bt * world, "positives_per_gpu": n_pos, "dtype": h.train_dtype() if hasattr(h, "train_dtype") else "f32",
+                 "pair_rows_per_gpu": Bt, "pair_rows_global": Bt * world, "positives_per_gpu": n_pos, "dtype": "bf16 operands / f32 accumulate, state, stash and optimizer (tcgen05 GEMMs)" if Bt % 8 == 0 and WE % 8 == 0 and H % 8 == 0 else "f32",
                  "flops_per_step": fl, "achieved_tflops": fl / (ms_t / args.train_steps * 1e-3) / 1e12,
                  "parallelism": "data-parallel x%d, all-reduce of the gradient arena" % world if world > 1 else "single GPU"}
 

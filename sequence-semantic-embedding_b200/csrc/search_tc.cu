@@ -40,7 +40,7 @@ constexpr int CAND_CAP = 128;        // candidates per (CTA item, row); compacte
 constexpr int MAX_GROUPS = 64;
 constexpr int DBG_N = 12;            // debug cycle counters per work item
 constexpr int SCAN_THREADS = 384;
-constexpr int FIN_MAXC = 2048;       // candidates per row the finalize kernel can sort
+constexpr int FIN_MAXC = 4096;       // candidates per row the finalize kernel can sort
 constexpr int FIN_MAXR = 256;        // candidates per row re-scored exactly
 // Bound of |fp16-operand dot - exact dot| / (|q| |t|), valid for every supported E (<= 512):
 //   operand rounding: q_i(1+a_i) t_i(1+b_i), |a_i|,|b_i| <= u = 2^-11  ->  sum |q_i t_i| (2u + u^2) <= (2u + u^2) |q||t|
@@ -662,7 +662,7 @@ __device__ __forceinline__ int padded_to_query_row(int p, int gstride, int rpg, 
 // subnormal range keep full fp16 relative precision.  The scan works in the scaled units throughout (qnorm, tau,
 // margin and the candidates' approximate scores all carry the same factor; finalize re-scores in fp32 from the
 // original q), so the scaling never reaches the results.
-__global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, int gstride, int rpg,
+__global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, int Ep, int gstride, int rpg,
                                     __half* __restrict__ qb, float* __restrict__ qnorm) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
@@ -681,10 +681,10 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, 
     scale = ldexpf(1.f, -ex);
   }
   float ss = 0.f;
-  for (int j = lane; j < E; j += 32) {
-    float v = qr >= 0 ? q[(size_t)qr * E + j] * scale : 0.f;
+  for (int j = lane; j < Ep; j += 32) {           // columns [E, Ep): zero padding up to the next multiple of 64
+    float v = (qr >= 0 && j < E) ? q[(size_t)qr * E + j] * scale : 0.f;
     ss = fmaf(v, v, ss);
-    qb[(size_t)row * E + j] = __float2half_rn(v);
+    qb[(size_t)row * Ep + j] = __float2half_rn(v);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -846,10 +846,14 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   for (int c = warp; c < m; c += 4) {
     const float* tr = P.index + (size_t)(ci[c] - P.global_offset) * P.E;
     float acc = 0.f;
-    for (int j = lane * 4; j < P.E; j += 128) {
-      float4 a = *reinterpret_cast<const float4*>(qr + j);
-      float4 b = *reinterpret_cast<const float4*>(tr + j);
-      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    if ((P.E & 3) == 0) {
+      for (int j = lane * 4; j < P.E; j += 128) {
+        float4 a = *reinterpret_cast<const float4*>(qr + j);
+        float4 b = *reinterpret_cast<const float4*>(tr + j);
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      }
+    } else {                      // odd encoding sizes (the reference recipes use E = 50): rows are not 16-byte aligned
+      for (int j = lane; j < P.E; j += 32) acc = fmaf(qr[j], tr[j], acc);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -881,10 +885,14 @@ __global__ void __launch_bounds__(256) fallback_kernel(const __grid_constant__ F
   for (int64_t n = warp; n < P.N; n += nw) {      // ascending n per warp keeps ties at the lower index
     const float* tr = P.index + (size_t)n * P.E;
     float acc = 0.f;
-    for (int j = lane * 4; j < P.E; j += 128) {
-      float4 a = *reinterpret_cast<const float4*>(qr + j);
-      float4 b = *reinterpret_cast<const float4*>(tr + j);
-      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    if ((P.E & 3) == 0) {
+      for (int j = lane * 4; j < P.E; j += 128) {
+        float4 a = *reinterpret_cast<const float4*>(qr + j);
+        float4 b = *reinterpret_cast<const float4*>(tr + j);
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      }
+    } else {
+      for (int j = lane; j < P.E; j += 32) acc = fmaf(qr[j], tr[j], acc);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -970,28 +978,35 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
 
+// Any encoding size up to 512: the fp16 scan copy of the index (and of the queries) is zero-padded to the next multiple
+// of 64 -- exact, the padding contributes 0 to every dot product; the fp32 re-score reads the unpadded rows.
+// k up to SSE_MAX_TOPK: for k > 32 the in-scan threshold tightening is off (it needs 4k list slots), rows whose
+// candidate lists overflow fall back to the exact brute-force kernel.
 bool search_tc_supported(int E, int64_t N, int k) {
-  return E % 64 == 0 && E >= 64 && E <= 512 && k >= 1 && k <= 32 && N >= 8192 && N < ((int64_t)1 << 31) - 256;
+  return E >= 1 && E <= 512 && k >= 1 && k <= SSE_MAX_TOPK && N >= 8192 && N >= 4 * (int64_t)k && N < ((int64_t)1 << 31) - 256;
 }
+static inline int pad64(int e) { return (e + 63) / 64 * 64; }
 
 int search_tc_prepare(TcIndex& ti, const float* index_f32, int64_t N, int E, cudaStream_t st, int64_t* launches) {
   search_tc_release(ti);
   ti.N = N; ti.E = E;
-  size_t bytes = (size_t)N * E * 2 + 64;
+  const int Ep = pad64(E);
+  size_t bytes = (size_t)N * Ep * 2 + 64;
   cudaError_t e = cudaMalloc(&ti.h16, bytes);
   if (e != cudaSuccess) { set_error("cudaMalloc(fp16 index, %zu) failed: %s", bytes, cudaGetErrorString(e)); return SSE_ENOMEM; }
-  SSE_TRY(f32_to_f16(index_f32, ti.h16, N * E, st, launches));
+  if (Ep == E) SSE_TRY(f32_to_f16(index_f32, ti.h16, N * E, st, launches));
+  else SSE_TRY(convert_to_16(index_f32, N, E, E, reinterpret_cast<uint16_t*>(ti.h16), Ep, 0, st, launches));
   // slot for max |t| lives behind the matrix
-  float* tnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.h16) + align_up((size_t)N * E * 2, 16));
+  float* tnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.h16) + align_up((size_t)N * Ep * 2, 16));
   SSE_CUDA_OK(cudaMemsetAsync(tnorm, 0, 4, st));
   max_row_norm_kernel<<<148 * 4, 256, 0, st>>>(index_f32, N, E, tnorm);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
-  SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap), ti.h16, N, E, 128));
-  SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap64), ti.h16, N, E, 64));
+  SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap), ti.h16, N, Ep, 128));
+  SSE_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(ti.tmap64), ti.h16, N, Ep, 64));
   ti.use3d = getenv("SSE_SCAN_NO3D") == nullptr &&
-             make_tmap3d(reinterpret_cast<CUtensorMap*>(ti.tmap3d), ti.h16, N, E, 128) == SSE_OK &&
-             make_tmap3d(reinterpret_cast<CUtensorMap*>(ti.tmap3d64), ti.h16, N, E, 64) == SSE_OK;
+             make_tmap3d(reinterpret_cast<CUtensorMap*>(ti.tmap3d), ti.h16, N, Ep, 128) == SSE_OK &&
+             make_tmap3d(reinterpret_cast<CUtensorMap*>(ti.tmap3d64), ti.h16, N, Ep, 64) == SSE_OK;
   ti.tmap_ok = true;
   return SSE_OK;
 }
@@ -1014,6 +1029,8 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   if (out_stride <= 0) out_stride = k;
   if (!ti.tmap_ok || ti.E != E) { set_error("search_tc: index not prepared"); return SSE_ESTATE; }
   const int64_t N = ti.N;
+  const int E_true = E;
+  E = pad64(E_true);                               // the scan works on the zero-padded fp16 copies
   const int KB = E / KBLK;
   const int m_tiles = cdiv(Q, TILE_M);
   const size_t ring_cap = 232448 - 1024 - 512;
@@ -1181,7 +1198,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   float* tm = reinterpret_cast<float*>(w + o_tm);
   float* tnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.h16) + align_up((size_t)N * E * 2, 16));
 
-  prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E, gstride, rpg, qb, qn);
+  prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E_true, E, gstride, rpg, qb, qn);
   if (launches) ++*launches;
 
   const CUtensorMap& tmi = ti.use3d ? *reinterpret_cast<const CUtensorMap*>(tn == 128 ? ti.tmap3d : ti.tmap3d64)
@@ -1211,7 +1228,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   fp.n_groups = n_groups; fp.mtg = mtg; fp.rpg = rpg; fp.cs = cs; fp.R = R;
   for (int g = 0; g < n_groups; ++g) { fp.group_first_item[g] = sp.group_first_item[g]; fp.group_items[g] = sp.group_items[g]; }
   fp.cand_s = sp.cand_s; fp.cand_i = sp.cand_i; fp.cand_cnt = sp.cand_cnt; fp.margin = mg;
-  fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E; fp.k = k;
+  fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E_true; fp.k = k;
   fp.out_s = out_scores; fp.out_i = out_idx; fp.out_stride = out_stride; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov);
   ti.last_cnt = sp.cand_cnt; ti.last_cnt_n = (int64_t)items * mtg * TILE_M; ti.last_overflow = fp.overflow; ti.last_Q = Q; ti.last_items = items;
   if (want_dbg) {

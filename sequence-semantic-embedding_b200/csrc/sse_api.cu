@@ -73,6 +73,8 @@ void invalidate_derived(sse_handle* h) {
   h->tct[0].valid = h->tct[1].valid = false;
   h->tct[0].ptable_valid = h->tct[1].ptable_valid = false;
   h->emb_f16_valid = false;
+  h->emb_pad_valid = false;
+  h->padw[0].valid = h->padw[1].valid = false;
   h->cnn_tc[0].valid = h->cnn_tc[1].valid = false;
 }
 
@@ -106,11 +108,10 @@ static int ensure_pad_table(sse_handle* h, int side, cudaStream_t st) {
 // the same table in the arithmetic of the tabulated-projection tensor-core kernel (lstm_ptable_kernel run on one all-PAD
 // row, dumping the state it carries past every step: h as the fp16 value of the recurrence, c in fp32), so that a tile
 // started from S[t0] continues bit-identically to a tile that ran the t0 PAD steps itself
-static int ensure_pad_table_tc(sse_handle* h, int side, cudaStream_t st) {
+static int ensure_pad_table_tc(sse_handle* h, int side, int We, int H, cudaStream_t st) {
   PadTable& pt = h->pad_tc[side];
   if (pt.valid) return SSE_OK;
-  const LstmTower& tw = h->lstm[side];
-  const int T = h->cfg.max_seq_length, H = tw.H;
+  const int T = h->cfg.max_seq_length;
   SSE_TRY(pt.buf.ensure((size_t)T * 2 * H * 4 + (size_t)T * 4 + (size_t)H * 4));
   float* tab_h = pt.buf.as<float>();
   float* tab_c = tab_h + (size_t)T * H;
@@ -119,7 +120,7 @@ static int ensure_pad_table_tc(sse_handle* h, int side, cudaStream_t st) {
   SSE_CUDA_OK(cudaMemsetAsync(toks, 0, (size_t)T * 4, st));
   PadSkip ps;
   ps.dump_h = tab_h; ps.dump_c = tab_c;
-  SSE_TRY(lstm_forward_ptable(toks, 1, T, 0, h->cfg.embedding_size, H, h->tct[side], nullptr, nullptr, ps, hout, st, &h->launches));
+  SSE_TRY(lstm_forward_ptable(toks, 1, T, 0, We, H, h->tct[side], nullptr, nullptr, ps, hout, st, &h->launches));
   pt.h = tab_h; pt.c = tab_c; pt.valid = true;
   return SSE_OK;
 }
@@ -211,48 +212,73 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens_in, int B, floa
   const LstmTower& tw = h->lstm[side];
   const int H = tw.H;
   const bool want_tc = h->opt_encoder == 2 || (h->opt_encoder == 0 && c.precision == SSE_PRECISION_TC);
-  if (want_tc && lstm_tc_supported(We, H)) {
+  // The tensor-core kernels tile We and H in blocks of 64.  Other sizes (the reference recipes use We in {30,40,50},
+  // H = 96) run on zero-padded copies of the embedding and the LSTM kernel/bias: a padded hidden unit has z = 0, so
+  // j = tanh(0) = 0 and its c and h stay exactly 0, and padded inputs meet zero weights -- the live units compute the
+  // same sums (sse_model.py:236-275 semantics unchanged).
+  const int Wp = (We + 63) / 64 * 64, Hp = (H + 63) / 64 * 64;
+  if (want_tc && lstm_tc_supported(Wp, Hp)) {
+    const bool padded = Wp != We || Hp != H;
+    const float* emb_x = emb;
+    const float* K_x = tw.K;
+    const float* b_x = tw.b;
+    if (padded) {
+      PaddedWeights& pw = h->padw[side];
+      if (!pw.valid) {
+        if (!pw.K) {
+          SSE_CUDA_OK(cudaMalloc(&pw.K, (size_t)(Wp + Hp) * 4 * Hp * 4));
+          SSE_CUDA_OK(cudaMalloc(&pw.b, (size_t)4 * Hp * 4));
+        }
+        SSE_TRY(pad_lstm_weights(tw.K, tw.b, We, H, Wp, Hp, pw.K, pw.b, st, &h->launches));
+        pw.valid = true;
+      }
+      if (!h->emb_pad_valid) {
+        if (!h->emb_pad) SSE_CUDA_OK(cudaMalloc(&h->emb_pad, (size_t)c.vocab_size * Wp * 4));
+        SSE_TRY(pad_cols(emb, c.vocab_size, We, h->emb_pad, Wp, st, &h->launches));
+        h->emb_pad_valid = true;
+      }
+      emb_x = h->emb_pad; K_x = pw.K; b_x = pw.b;
+    }
     if (!h->emb_f16_valid) {
-      if (!h->emb_f16) SSE_CUDA_OK(cudaMalloc(&h->emb_f16, (size_t)c.vocab_size * We * 2));
-      SSE_TRY(f32_to_f16(emb, h->emb_f16, (int64_t)c.vocab_size * We, st, &h->launches));
+      if (!h->emb_f16) SSE_CUDA_OK(cudaMalloc(&h->emb_f16, (size_t)c.vocab_size * Wp * 2));
+      SSE_TRY(f32_to_f16(emb_x, h->emb_f16, (int64_t)c.vocab_size * Wp, st, &h->launches));
       h->emb_f16_valid = true;
     }
     TcTower& tt = h->tct[side];
-    if (!tt.valid) SSE_TRY(lstm_tc_prepare(tt, tw.K, tw.b, We, H, st, &h->launches));
+    if (!tt.valid) SSE_TRY(lstm_tc_prepare(tt, K_x, b_x, Wp, Hp, st, &h->launches));
     const size_t Bpad = (size_t)cdiv(B, 128) * 128;
-    SSE_TRY(h->enc_ws.ensure((Bpad * H + (size_t)B * H) * 4));
+    SSE_TRY(h->enc_ws.ensure((Bpad * Hp + (size_t)B * Hp) * 4));
     float* cs = h->enc_ws.as<float>();
-    float* hout = cs + Bpad * H;
+    float* hout = cs + Bpad * Hp;
     // kernel choice (lstm_kernel option): 3 = cluster kernel with the tabulated input projection (default whenever the
     // table fits), 2 = cluster kernel with resident W_x and gathered x tiles, 1 = weight-streaming kernel
-    const bool cluster_ok = lstm_cluster_supported(We, H);
-    const bool ptable_ok = lstm_ptable_supported(c.vocab_size, We, H);
+    const bool cluster_ok = lstm_cluster_supported(Wp, Hp);
+    const bool ptable_ok = lstm_ptable_supported(c.vocab_size, Wp, Hp);
     int kern = h->opt_lstm_kernel;
-    if (kern == 2 && !cluster_ok) { set_error("cluster LSTM kernel needs H in {64,128,256}, We%%64==0, We<=256 (We=%d H=%d)", We, H); return SSE_EINVAL; }
-    if (kern == 3 && !ptable_ok) { set_error("table LSTM kernel needs H in {64,128,256} and V*4H*4 <= 2 GiB (V=%d H=%d)", c.vocab_size, H); return SSE_EINVAL; }
+    if (kern == 2 && !cluster_ok) { set_error("cluster LSTM kernel needs H <= 256 (padded to 64/128/256), We <= 256 (We=%d H=%d)", We, H); return SSE_EINVAL; }
+    if (kern == 3 && !ptable_ok) { set_error("table LSTM kernel needs H <= 256 (padded to 64/128/256) and V*4H*4 <= 2 GiB (V=%d H=%d)", c.vocab_size, H); return SSE_EINVAL; }
     // measured (We=H=256, T=50): table kernel 0.22 ms at 600 rows, 0.67 ms at 4800; the weight-streaming kernel is
     // flat ~0.8 ms up to ~5k rows and wins once every SM holds a full 128-row tile (1.44 vs 2.2 ms at 18944 rows)
     if (kern == 0) kern = (ptable_ok && B <= 8192) ? 3 : ((cluster_ok && B <= 1024) ? 2 : 1);
-    if (kern == 3 && !tt.ptable_valid) SSE_TRY(lstm_ptable_prepare(tt, emb, c.vocab_size, tw.K, We, H, st, &h->launches));
+    if (kern == 3 && !tt.ptable_valid) SSE_TRY(lstm_ptable_prepare(tt, emb_x, c.vocab_size, K_x, Wp, Hp, st, &h->launches));
     PadSkip ps;
     if (tp.sorted) {
       // kernel 3 continues bit-identically from a table in its own arithmetic; the other two start from the fp32 table
-      // (equal within the tensor-core tolerance)
-      if (kern == 3) { SSE_TRY(ensure_pad_table_tc(h, side, st)); ps.pad_h = h->pad_tc[side].h; ps.pad_c = h->pad_tc[side].c; }
-      else { SSE_TRY(ensure_pad_table(h, side, st)); ps.pad_h = h->pad[side].h; ps.pad_c = h->pad[side].c; }
-      ps.lead_sorted = tp.lead_sorted;
+      // (equal within the tensor-core tolerance; not available for padded shapes: they run all T steps)
+      if (kern == 3) { SSE_TRY(ensure_pad_table_tc(h, side, Wp, Hp, st)); ps.pad_h = h->pad_tc[side].h; ps.pad_c = h->pad_tc[side].c; ps.lead_sorted = tp.lead_sorted; }
+      else if (!padded) { SSE_TRY(ensure_pad_table(h, side, st)); ps.pad_h = h->pad[side].h; ps.pad_c = h->pad[side].c; ps.lead_sorted = tp.lead_sorted; }
     }
     if (kern == 3) {
-      SSE_TRY(lstm_forward_ptable(tokens, B, T, 0, We, H, tt, nullptr, nullptr, ps, hout, st, &h->launches));
+      SSE_TRY(lstm_forward_ptable(tokens, B, T, 0, Wp, Hp, tt, nullptr, nullptr, ps, hout, st, &h->launches));
     } else if (kern == 2) {
-      SSE_TRY(lstm_forward_cluster(tokens, B, T, 0, h->emb_f16, We, H, tt, nullptr, nullptr, ps, hout, st, &h->launches));
+      SSE_TRY(lstm_forward_cluster(tokens, B, T, 0, h->emb_f16, Wp, Hp, tt, nullptr, nullptr, ps, hout, st, &h->launches));
     } else {
-      SSE_TRY(lstm_forward_tc(tokens, B, T, 0, h->emb_f16, We, H, tt, nullptr, nullptr, ps, cs, hout, st, &h->launches));
+      SSE_TRY(lstm_forward_tc(tokens, B, T, 0, h->emb_f16, Wp, Hp, tt, nullptr, nullptr, ps, cs, hout, st, &h->launches));
     }
-    SSE_TRY(sgemm(false, false, B, E, H, 1.f, hout, H, tw.M, E, 0.f, proj, E, st, &h->launches));
+    SSE_TRY(sgemm(false, false, B, E, H, 1.f, hout, Hp, tw.M, E, 0.f, proj, E, st, &h->launches));
     return finish();
   } else if (h->opt_encoder == 2) {
-    set_error("tcgen05 encoder needs We%%64==0, H%%64==0, We,H<=256 (We=%d H=%d)", We, H);
+    set_error("tcgen05 encoder needs We <= 256 and H <= 256 (We=%d H=%d)", We, H);
     return SSE_EINVAL;
   }
   SSE_TRY(h->enc_ws.ensure((size_t)B * H * 3 * 4));
@@ -279,7 +305,7 @@ int search_device(sse_handle* h, const float* q, int Q, int k, float* scores, in
   const int E = h->cfg.encoding_size;
   bool use_tc = h->opt_search == 2 || (h->opt_search == 0 && h->cfg.precision == SSE_PRECISION_TC);
   if (use_tc && !search_tc_supported(E, h->index_n, k)) {
-    if (h->opt_search == 2) { set_error("tcgen05 search needs E%%64==0, E<=512, k<=32, N>=8192 (E=%d k=%d N=%lld)", E, k, (long long)h->index_n); return SSE_EINVAL; }
+    if (h->opt_search == 2) { set_error("tcgen05 search needs E<=512, k<=128, N>=8192 (E=%d k=%d N=%lld)", E, k, (long long)h->index_n); return SSE_EINVAL; }
     use_tc = false;
   }
   if (use_tc) {
@@ -412,6 +438,8 @@ int sse_destroy(sse_handle* h) {
   lstm_ptable_release(h->tct[0]); lstm_ptable_release(h->tct[1]);
   cnn_tc_release(h->cnn_tc[0]); cnn_tc_release(h->cnn_tc[1]);
   if (h->emb_f16) cudaFree(h->emb_f16);
+  if (h->emb_pad) cudaFree(h->emb_pad);
+  for (int s2 = 0; s2 < 2; ++s2) { if (h->padw[s2].K) cudaFree(h->padw[s2].K); if (h->padw[s2].b) cudaFree(h->padw[s2].b); }
   delete h;
   return SSE_OK;
 }

@@ -205,5 +205,7 @@ int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We
 // small utilities (util.cu)
 int fill_f32(float* p, int64_t n, float v, cudaStream_t st, int64_t* launches);
 int f32_to_f16(const float* src, __half* dst, int64_t n, cudaStream_t st, int64_t* launches);
+int pad_cols(const float* src, int64_t R, int C, float* dst, int Cp, cudaStream_t st, int64_t* launches);
+int pad_lstm_weights(const float* K, const float* b, int We, int H, int Wp, int Hp, float* Kp, float* bp, cudaStream_t st, int64_t* launches);
 
 }  // namespace sse

@@ -11,6 +11,14 @@ struct PadTable {
 };
 }  // namespace sse
 
+namespace sse {
+struct PaddedWeights {            // zero-padded fp32 copies of an LSTM tower's kernel / bias for shapes the tensor-core tiles do not divide
+  float* K = nullptr;             // [We' + H', 4H']
+  float* b = nullptr;             // [4H']
+  bool valid = false;
+};
+}  // namespace sse
+
 struct sse_handle {
   sse_config cfg;
   int num_sms = 148;
@@ -27,6 +35,9 @@ struct sse_handle {
   sse::TcTower tct[2];              // tensor-core copies of the LSTM weights (lazy, invalidated with the weights)
   __half* emb_f16 = nullptr;
   bool emb_f16_valid = false;
+  float* emb_pad = nullptr;         // [V, We'] zero-padded fp32 embedding (padded shapes only)
+  bool emb_pad_valid = false;
+  sse::PaddedWeights padw[2];
   float learning_rate = 0.f;
   int64_t global_step = 0;
 

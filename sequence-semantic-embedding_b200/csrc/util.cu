@@ -44,7 +44,43 @@ __global__ void f32_to_f16_tail(const float* __restrict__ s, __half* __restrict_
   int64_t i = from + threadIdx.x;
   if (i < n) d[i] = __float2half_rn(s[i]);
 }
+// dst [R, Cp] = src [R, C] with zero columns appended
+__global__ void pad_cols_kernel(const float* __restrict__ s, int64_t R, int C, float* __restrict__ d, int Cp) {
+  const int64_t total = R * Cp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Cp;
+    const int c = (int)(i - r * Cp);
+    d[i] = c < C ? s[r * C + c] : 0.f;
+  }
+}
+// LSTM kernel [We+H, 4H] (rows x then h; column blocks i,j,f,o) -> [Wp+Hp, 4Hp] with zero rows / columns for the padding
+__global__ void pad_lstm_kernel(const float* __restrict__ K, const float* __restrict__ b, int We, int H, int Wp, int Hp,
+                                float* __restrict__ Kp, float* __restrict__ bp) {
+  const int64_t total = (int64_t)(Wp + Hp) * 4 * Hp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (4 * Hp)), cc = (int)(i - (int64_t)r * 4 * Hp);
+    const int g = cc / Hp, u = cc - g * Hp;
+    int rs = -1;
+    if (r < We) rs = r;
+    else if (r >= Wp && r - Wp < H) rs = We + (r - Wp);
+    Kp[i] = (rs >= 0 && u < H) ? K[(size_t)rs * 4 * H + g * H + u] : 0.f;
+    if (r == 0) bp[cc] = u < H ? b[g * H + u] : 0.f;
+  }
+}
 }  // namespace
+
+int pad_cols(const float* src, int64_t R, int C, float* dst, int Cp, cudaStream_t st, int64_t* launches) {
+  pad_cols_kernel<<<(int)std::min<int64_t>(cdiv64(R * Cp, 256), 148 * 8), 256, 0, st>>>(src, R, C, dst, Cp);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+int pad_lstm_weights(const float* K, const float* b, int We, int H, int Wp, int Hp, float* Kp, float* bp, cudaStream_t st, int64_t* launches) {
+  pad_lstm_kernel<<<148 * 2, 256, 0, st>>>(K, b, We, H, Wp, Hp, Kp, bp);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
 
 int fill_f32(float* p, int64_t n, float v, cudaStream_t st, int64_t* launches) {
   if (n <= 0) return SSE_OK;

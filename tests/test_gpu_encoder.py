@@ -131,11 +131,13 @@ TOL_TC = 1e-3
 
 
 @pytest.mark.parametrize("We,H,E,T,B", [(256, 256, 256, 50, 300), (64, 64, 32, 12, 128), (128, 192, 64, 20, 77),
-                                        (256, 128, 256, 50, 1), (192, 256, 128, 30, 513)])
+                                        (256, 128, 256, 50, 1), (192, 256, 128, 30, 513),
+                                        # the real reference recipes (makefile:5,42,30): run on zero-padded tiles (We -> 64, H -> 128)
+                                        (50, 96, 64, 80, 130), (40, 96, 50, 50, 70), (30, 96, 64, 60, 37)])
 @pytest.mark.parametrize("kern", [1, 2, 3])   # 1 = weight-streaming kernel (lstm_tc.cu), 2 / 3 = cluster kernels (lstm_cluster.cu; 3 = tabulated input projection)
 def test_tc_lstm_encode_within_tolerance(We, H, E, T, B, kern):
-    if kern >= 2 and H not in (64, 128, 256):
-        pytest.skip("cluster kernel: H in {64,128,256}")
+    if kern >= 2 and (H + 63) // 64 * 64 not in (64, 128, 256):
+        pytest.skip("cluster kernels: H (padded to a multiple of 64) in {64,128,256}")
     mode, V = "dual-encoder", 5000
     h, p = make(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
     h.set_option("encoder", 2)          # force the tcgen05 path (raise if unsupported)
@@ -173,7 +175,7 @@ def test_tc_lstm_pad_skip_and_exact_mode_switch(kern):
     c = h.encode_host(0, tok, True)
     assert np.abs(c - want).max() < TOL_FP32
     with pytest.raises(sse_ffi.SseError):
-        h2, _ = make(mode, 100, 50, 64, 96, 96, 20, precision=sse_ffi.PRECISION_TC)
+        h2, _ = make(mode, 100, 320, 64, 96, 96, 20, precision=sse_ffi.PRECISION_TC)       # We > 256: no tensor-core tower
         h2.set_option("encoder", 2)
         h2.encode_host(0, np.zeros((2, 20), np.int32), True)
     h.close()

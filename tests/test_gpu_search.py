@@ -79,7 +79,9 @@ def test_fewer_targets_than_k_pads():
 
 
 @pytest.mark.parametrize("E,N,Q,k", [(256, 100000, 600, 10), (256, 20000, 130, 10), (256, 50000, 1, 10),
-                                     (128, 33333, 257, 3), (512, 16500, 40, 1), (64, 30000, 300, 32)])
+                                     (128, 33333, 257, 3), (512, 16500, 40, 1), (64, 30000, 300, 32),
+                                     # E = 50 (crosslingual recipe, makefile:42): zero-padded fp16 scan copy; k up to 128 (webserver nbest)
+                                     (50, 20000, 33, 10), (96, 12000, 7, 5), (256, 30000, 40, 128), (64, 9000, 5, 100)])
 def test_tc_search_matches_oracle_and_simt(E, N, Q, k):
     rng = np.random.default_rng(E * 7 + Q)
     tgt, q = unit_rows(rng, N, E), unit_rows(rng, Q, E)
