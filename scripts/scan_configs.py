@@ -6,6 +6,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 shapes = sys.argv[1:] or ["600x1000000", "4800x125000"]
 CONFIGS = [
     ("auto", {}),
+    ("unfused", {"SSE_SCAN_FUSED": "0"}),
     ("pack0", {"SSE_SCAN_PACK": "0"}),
     ("pack1", {"SSE_SCAN_PACK": "1"}),
     ("tn64", {"SSE_SCAN_ACC1": "0"}),

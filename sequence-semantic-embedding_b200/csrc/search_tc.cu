@@ -53,7 +53,8 @@ constexpr int FIN_MAXR = 256;        // candidates per row re-scored exactly
 // Sum < 0.000985; EPS_REL = 0.0011 leaves > 10 % slack at E = 512.
 constexpr float EPS_REL = 0.0011f;
 
-enum { MODE_TILEMAX = 0, MODE_FILTER = 1 };
+enum { MODE_TILEMAX = 0, MODE_FILTER = 1, MODE_FUSED = 2 };
+constexpr int FUSED_MAX_K = 16;     // the fused scan keeps a row's k best sampled tile maxima in registers
 
 struct ScanParams {
   int n_groups;
@@ -62,7 +63,15 @@ struct ScanParams {
   int n_stages;
   int tn;                          // index rows per MMA tile (64 or 128)
   int a_cols;                      // TMEM columns holding the fp16 queries: mtg * E / 2
-  const __half* qb;         // [Qp, E] fp16 queries
+  const __half* qb;         // [Qp, E] fp16 queries (TILEMAX / FILTER; the fused scan converts q32 itself)
+  // fused scan (MODE_FUSED): sample pass + threshold selection + filter pass in ONE launch
+  const float* q32;                // [Q, E_true] fp32 queries
+  int Q, E_true, gstride, rpg;     // padded row p = g * gstride + l  <->  query row g * rpg + l
+  const float* tnorm_max;          // max |t| of the index
+  float* margin_out;               // [Qp] 2*eps per row, written for finalize
+  float* tau_out;                  // [Qp] (debug / tests)
+  unsigned* group_ctr;             // [n_groups] arrival counters of the per-group barrier (zero between searches)
+  int n_s, s_step;                 // sample tiles: tile = js * s_step, js in [0, n_s)
   long long* dbg;                  // optional [items][DBG_N] cycle counters (nullptr = off)
   int dbg_flags;                   // timing experiments only: 1 = no TMA loads, 2 = no MMA issue
   int use3d;                       // one 3-D TMA instruction per index tile (else KB 2-D loads)
@@ -241,6 +250,13 @@ __device__ __forceinline__ void tc_mma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem,
       : "memory");
 }
 
+// Padded row p = g * gstride + l  <->  query row g * rpg + l  (l < rpg): -1 for the padding rows of a group
+__device__ __forceinline__ int padded_row_to_query(int p, int gstride, int rpg, int Q) {
+  const int g = p / gstride, l = p - g * gstride;
+  const int r = g * rpg + l;
+  return (l < rpg && r < Q) ? r : -1;
+}
+
 // KBT / TNT: compile-time E/64 and tile width (0 = take them from the params at run time)
 // A row's candidate list is about to run out of slots (rare: the sampled threshold was loose for this row).
 // Move its k best to the front, tighten the row's threshold to (k-th best approximate score - 2 eps) -- still a
@@ -410,6 +426,13 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   const int mt_count = P.group_mt[g];
   const int j0 = (int)(((int64_t)P.n_j * r_in_g) / R);
   const int j1 = (int)(((int64_t)P.n_j * (r_in_g + 1)) / R);
+  // fused scan: this item first visits its share of the SAMPLE tiles (tile maxima), then -- after the per-group barrier
+  // and the threshold selection in the epilogue -- its share of all tiles (filter)
+  const int js0 = MODE == MODE_FUSED ? (int)(((int64_t)P.n_s * r_in_g) / R) : 0;
+  const int js1 = MODE == MODE_FUSED ? (int)(((int64_t)P.n_s * (r_in_g + 1)) / R) : 0;
+  const int ns_loc = js1 - js0;
+  const int n_loc = ns_loc + (j1 - j0);
+  auto tile_of = [&](int jj) { return jj < ns_loc ? (js0 + jj) * P.s_step : (j0 + jj - ns_loc) * P.tile_step; };
   const int KB = KBT ? KBT : P.kb, NG = P.n_stages, TN = TNT ? TNT : P.tn;   // n_stages = number of TILE slots in the ring
   const int E = KB * KBLK;
   const uint32_t kb_bytes = (uint32_t)TN * KBLK * 2;     // one [TN x 64] fp16 SW128 sub-tile
@@ -447,13 +470,12 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   if (warp == 9) {
     // ===== TMA producer.  Every CTA arms its own full barrier for the slot once its consumers released it and tells the
     // cluster leader; the leader issues ONE multicast load per tile when all cs CTAs are ready (cs == 1: plain load).
-    if (j1 > j0) {     // whole warp, converged; one elected lane issues
+    if (n_loc > 0) {     // whole warp, converged; one elected lane issues
       long long w_empty = 0, w_cl = 0, t_begin = clock64();
       const uint16_t mask = (uint16_t)((1u << cs) - 1u);
-      for (int j = j0; j < j1; ++j) {
-        const int jj = j - j0;
+      for (int jj = 0; jj < n_loc; ++jj) {
         const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
-        const int tile = j * P.tile_step;
+        const int tile = tile_of(jj);
         mbar_wait_timed(bar_empty + 8 * s, ph ^ 1, w_empty, 64);
         if (elect_one_sync()) {
           if (P.dbg_flags & 1) {
@@ -485,13 +507,12 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
     }
   } else if (warp == 8) {
     // ===== MMA issuer (one thread): all MMAs of an accumulator back to back, ONE tcgen05.commit per accumulator =====
-    if (j1 > j0) {     // whole warp, converged; one elected lane issues
+    if (n_loc > 0) {     // whole warp, converged; one elected lane issues
       const uint32_t idesc = make_idesc_f16(TILE_M, TN);
       long long w_full = 0, w_acce = 0, w_a = 0, t_begin = clock64();
       mbar_wait_timed(bar_a, 0, w_a);
       tc_fence_after();
-      for (int j = j0; j < j1; ++j) {
-        const int jj = j - j0;
+      for (int jj = 0; jj < n_loc; ++jj) {
         const int buf = jj & 1;
         const uint32_t use = (uint32_t)(jj >> 1);
         const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
@@ -540,12 +561,59 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
     // ===== epilogue: thread == query row =====
     const int e = warp;
     const int mt = e >> 2, quarter = e & 3;
-    if (mt < mt_count && j1 > j0) {
+    if (mt < mt_count && n_loc > 0) {
       const int lrow = mt * TILE_M + quarter * 32 + lane;             // row within the group
       const int grow = g * P.mtg * TILE_M + lrow;                     // padded global row
       const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      float mg_row = 0.f;                                             // fused: 2*eps of this row
+      bool live_row = true;
       // ---- stage this row's fp16 query into TMEM (A operand): 2 consecutive k per 32-bit column
-      {
+      if (MODE == MODE_FUSED) {
+        // straight from the fp32 queries: scale by a power of two so that max |q_i| lands in [0.5, 1) (see
+        // prep_queries_kernel), convert, and keep the row's margin in a register
+        const int qr = padded_row_to_query(grow, P.gstride, P.rpg, P.Q);
+        live_row = qr >= 0;
+        const int Et = P.E_true;
+        const float* src = P.q32 + (size_t)(live_row ? qr : 0) * Et;
+        const bool vec = (Et & 3) == 0;
+        float mx = 0.f;
+        if (live_row) {
+          if (vec) for (int j = 0; j < Et; j += 4) { const float4 u = __ldg(reinterpret_cast<const float4*>(src + j)); mx = fmaxf(fmaxf(mx, fmaxf(fabsf(u.x), fabsf(u.y))), fmaxf(fabsf(u.z), fabsf(u.w))); }
+          else for (int j = 0; j < Et; ++j) mx = fmaxf(mx, fabsf(__ldg(src + j)));
+        }
+        float scale = 1.f;
+        if (mx > 0.f && mx < CUDART_INF_F) {
+          int ex;
+          frexpf(mx, &ex);
+          ex = max(-100, min(100, ex));
+          scale = ldexpf(1.f, -ex);
+        }
+        float ss = 0.f;
+        const uint32_t a_t = lane_base + (uint32_t)(mt * (E / 2));
+        for (int c = 0; c < E / 2; c += 32) {
+          uint32_t v[32];
+#pragma unroll
+          for (int q4 = 0; q4 < 16; ++q4) {
+            const int j = 2 * c + 4 * q4;
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live_row) {
+              if (vec) { if (j < Et) u = __ldg(reinterpret_cast<const float4*>(src + j)); }
+              else { if (j < Et) u.x = __ldg(src + j); if (j + 1 < Et) u.y = __ldg(src + j + 1); if (j + 2 < Et) u.z = __ldg(src + j + 2); if (j + 3 < Et) u.w = __ldg(src + j + 3); }
+            }
+            const __half2 h0 = __floats2half2_rn(u.x * scale, u.y * scale), h1 = __floats2half2_rn(u.z * scale, u.w * scale);
+            ss = fmaf(u.x * scale, u.x * scale, ss); ss = fmaf(u.y * scale, u.y * scale, ss); ss = fmaf(u.z * scale, u.z * scale, ss); ss = fmaf(u.w * scale, u.w * scale, ss);
+            v[q4 * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h0);
+            v[q4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+          }
+          TMEM_ST_32(a_t + c, v);
+        }
+        mg_row = live_row ? fmaxf(2.f * EPS_REL * sqrtf(ss) * __ldg(P.tnorm_max), 1e-20f) : 0.f;
+        if (r_in_g == 0) P.margin_out[grow] = mg_row;
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a);
+      } else {
         const uint4* src = reinterpret_cast<const uint4*>(P.qb + (size_t)grow * E);
         const uint32_t a_t = lane_base + (uint32_t)(mt * (E / 2));
         for (int c = 0; c < E / 2; c += 32) {
@@ -566,8 +634,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
       int cnt = 0;
       float* my_s = nullptr;
       int32_t* my_i = nullptr;
-      if (MODE == MODE_FILTER) {
-        thr = P.tau[grow];
+      if (MODE != MODE_TILEMAX) {
+        if (MODE == MODE_FILTER) thr = P.tau[grow];
         size_t base = ((size_t)item * (P.mtg * TILE_M) + lrow) * CAND_CAP;
         my_s = P.cand_s + base;
         my_i = P.cand_i + base;
@@ -576,11 +644,60 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
       // the warp that hands the ring slot back: all MMAs of the tile have retired once the LAST accumulator's commit fired
       const bool releases_slot = ACC1 ? (e == 4 * (mt_count - 1)) : (e == 0);
       long long w_accf = 0, w_ld = 0, w_cmp = 0, t_begin = clock64();
-      for (int j = j0; j < j1; ++j) {
-        const int jj = j - j0;
+      for (int jj = 0; jj < n_loc; ++jj) {
+        if (MODE == MODE_FUSED && jj == ns_loc) {
+          // ---- all sample tiles of this item are done: per-group barrier (every epilogue warp of every item of the group
+          // arrives once), then this row's threshold = k-th largest of ITS sampled tile maxima - 2 eps
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) {
+            atomicAdd(P.group_ctr + g, 1u);
+            const unsigned target = (unsigned)(R * mt_count * 4);
+            long long t0w = 0;
+            for (unsigned spins = 0;; ++spins) {
+              unsigned seen;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.group_ctr + g) : "memory");
+              if (seen >= target) break;
+              __nanosleep(64);
+              if ((spins & 0xfff) == 0xfff) {
+                long long now = clock64();
+                if (t0w == 0) t0w = now;
+                else if (now - t0w > 4000000000LL) __trap();
+              }
+            }
+          }
+          __syncwarp();
+          if (live_row) {
+            float top[FUSED_MAX_K];
+#pragma unroll
+            for (int x = 0; x < FUSED_MAX_K; ++x) top[x] = -CUDART_INF_F;
+            const float* tmr = P.tilemax + (size_t)grow * P.n_s;
+            const int kk = P.k;
+            for (int x = 0; x < P.n_s; ++x) {
+              float v = __ldcg(tmr + x);
+              if (v > top[FUSED_MAX_K - 1]) {
+#pragma unroll
+                for (int y = 0; y < FUSED_MAX_K; ++y) {          // sorted insertion (descending)
+                  const float hi = fmaxf(top[y], v);
+                  v = fminf(top[y], v);
+                  top[y] = hi;
+                }
+              }
+            }
+            float kth = -CUDART_INF_F;
+#pragma unroll
+            for (int y = 0; y < FUSED_MAX_K; ++y)
+              if (y == kk - 1) kth = top[y];
+            thr = kth - mg_row;
+            if (r_in_g == 0 && P.tau_out) P.tau_out[grow] = thr;
+          } else {
+            thr = CUDART_INF_F;
+          }
+        }
+        const bool sampling = MODE == MODE_TILEMAX || (MODE == MODE_FUSED && jj < ns_loc);
         const int buf = ACC1 ? mt : (jj & 1);
         const uint32_t use = ACC1 ? (uint32_t)jj : (uint32_t)(jj >> 1);
-        const int tile = j * P.tile_step;
+        const int tile = tile_of(jj);
         const int64_t col0 = (int64_t)tile * TN;
         const bool ragged = col0 + TN > P.N;
         mbar_wait_timed(bar_accf + 8 * buf, use & 1, w_accf);
@@ -614,7 +731,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
               if (cbase + 32 + i >= P.N) vb[i] = 0xff800000u;
             }
           }
-          if (MODE == MODE_TILEMAX) {
+          if (MODE == MODE_TILEMAX || (MODE == MODE_FUSED && sampling)) {
             tmax = fmaxf(tmax, fmaxf(chunk_max(va), chunk_max(vb)));
           } else {
             const int32_t id0 = (int32_t)(P.global_offset + cbase);
@@ -622,19 +739,26 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
             cnt = chunk_filter(vb, thr, my_s, my_i, cnt, id0 + 32);
             // keep >= 64 free slots for the next round
             if (cnt > CAND_CAP - 64) {
-              Compacted cc = compact_candidates(my_s, my_i, cnt, P.k, P.margin[grow], thr);
+              Compacted cc = compact_candidates(my_s, my_i, cnt, P.k, MODE == MODE_FUSED ? mg_row : P.margin[grow], thr);
               cnt = cc.cnt;
               thr = cc.cnt > CAND_CAP ? CUDART_INF_F : cc.thr;   // overflow sentinel: stop collecting, finalize flags the row
             }
           }
           if (P.dbg) w_cmp += clock64() - t_c0;
         }
-        if (MODE == MODE_TILEMAX) P.tilemax[(size_t)j * P.Qp + grow] = tmax;
+        if (MODE == MODE_TILEMAX) P.tilemax[(size_t)(j0 + jj) * P.Qp + grow] = tmax;
+        if (MODE == MODE_FUSED && sampling) P.tilemax[(size_t)grow * P.n_s + js0 + jj] = tmax;      // row-major: the selection reads one row
       }
-      if (MODE == MODE_FILTER) P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + lrow] = cnt;
+      if (MODE == MODE_FUSED && n_loc == ns_loc) {          // an item without filter tiles still owes the group its arrival
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(P.group_ctr + g, 1u);
+      }
+      if (MODE != MODE_TILEMAX) P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + lrow] = cnt;
       if (P.dbg && e == 0 && lane == 0) { P.dbg[item * DBG_N + 6] = w_accf; P.dbg[item * DBG_N + 7] = clock64() - t_begin; P.dbg[item * DBG_N + 8] = w_ld; P.dbg[item * DBG_N + 9] = w_cmp; P.dbg[item * DBG_N + 10] = cnt; }
-    } else if (mt < mt_count && MODE == MODE_FILTER) {
+    } else if (mt < mt_count && MODE != MODE_TILEMAX) {
       P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + mt * TILE_M + quarter * 32 + lane] = 0;
+      if (MODE == MODE_FUSED && lane == 0) atomicAdd(P.group_ctr + g, 1u);      // no tiles at all: arrive, never wait
     }
   }
   tc_fence_before();
@@ -766,6 +890,7 @@ struct FinParams {
   float* out_s;
   int32_t* out_i;
   int32_t* overflow;       // [Q]
+  unsigned* group_ctr;     // fused scan: per-group barrier counters, re-armed (zeroed) here for the next search
 };
 
 // bitonic sort of n (power of two) pairs in smem, order (score desc, idx asc)
@@ -796,6 +921,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   __shared__ int s_total, s_over, s_m;
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
+  if (P.group_ctr && row == 0 && tid < P.n_groups) P.group_ctr[tid] = 0u;
   const int rows_per_group = P.mtg * TILE_M;
   const int g = row / P.rpg, lrow = row % P.rpg;
   const int R = P.cs > 1 ? P.R : P.group_items[g];
@@ -1007,12 +1133,18 @@ int search_tc_prepare(TcIndex& ti, const float* index_f32, int64_t N, int E, cud
   ti.use3d = getenv("SSE_SCAN_NO3D") == nullptr &&
              make_tmap3d(reinterpret_cast<CUtensorMap*>(ti.tmap3d), ti.h16, N, Ep, 128) == SSE_OK &&
              make_tmap3d(reinterpret_cast<CUtensorMap*>(ti.tmap3d64), ti.h16, N, Ep, 64) == SSE_OK;
+  if (!ti.group_ctr) {
+    SSE_CUDA_OK(cudaMalloc(&ti.group_ctr, MAX_GROUPS * sizeof(unsigned)));
+    SSE_CUDA_OK(cudaMemsetAsync(ti.group_ctr, 0, MAX_GROUPS * sizeof(unsigned), st));
+  }
   ti.tmap_ok = true;
   return SSE_OK;
 }
 
 void search_tc_release(TcIndex& ti) {
   if (ti.h16) cudaFree(ti.h16);
+  if (ti.group_ctr) cudaFree(ti.group_ctr);
+  ti.group_ctr = nullptr;
   ti.h16 = nullptr; ti.N = 0; ti.E = 0; ti.tmap_ok = false;
 }
 
@@ -1106,14 +1238,22 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
 
   // specialised instances for the common E = 256 (fully unrolled MMA issue), generic otherwise
   typedef void (*scan_fn)(const CUtensorMap, const ScanParams);
-  scan_fn fn_tilemax, fn_filter;
-  if (KB == 4 && tn == 64) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 64, false>; fn_filter = scan_kernel<MODE_FILTER, 4, 64, false>; }
-  else if (KB == 4 && tn == 128 && !acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 128, false>; fn_filter = scan_kernel<MODE_FILTER, 4, 128, false>; }
-  else if (KB == 4 && tn == 128 && acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 128, true>; fn_filter = scan_kernel<MODE_FILTER, 4, 128, true>; }
-  else if (acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0, true>; fn_filter = scan_kernel<MODE_FILTER, 0, 0, true>; }
-  else { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0, false>; fn_filter = scan_kernel<MODE_FILTER, 0, 0, false>; }
+  scan_fn fn_tilemax, fn_filter, fn_fused;
+  if (KB == 4 && tn == 64) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 64, false>; fn_filter = scan_kernel<MODE_FILTER, 4, 64, false>; fn_fused = scan_kernel<MODE_FUSED, 4, 64, false>; }
+  else if (KB == 4 && tn == 128 && !acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 128, false>; fn_filter = scan_kernel<MODE_FILTER, 4, 128, false>; fn_fused = scan_kernel<MODE_FUSED, 4, 128, false>; }
+  else if (KB == 4 && tn == 128 && acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 128, true>; fn_filter = scan_kernel<MODE_FILTER, 4, 128, true>; fn_fused = scan_kernel<MODE_FUSED, 4, 128, true>; }
+  else if (acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0, true>; fn_filter = scan_kernel<MODE_FILTER, 0, 0, true>; fn_fused = scan_kernel<MODE_FUSED, 0, 0, true>; }
+  else { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0, false>; fn_filter = scan_kernel<MODE_FILTER, 0, 0, false>; fn_fused = scan_kernel<MODE_FUSED, 0, 0, false>; }
+  // Fused scan (default when k <= 16, no clusters): sample pass, threshold selection and filter pass in ONE launch --
+  // the items of an m-group meet at a per-group barrier after their sample tiles (all items are co-resident: the grid
+  // never exceeds the SM count and each CTA takes a whole SM), every epilogue thread then selects its own row's threshold
+  // from the group's tile maxima.  Saves two launches, the second TMEM allocation / query staging and the fp16 query
+  // pre-pass (the queries are scaled and converted while they are staged).  SSE_SCAN_FUSED=0 restores the 3-kernel form.
+  static const bool env_fused = env_int("SSE_SCAN_FUSED", 1) != 0;
+  const bool fused = env_fused && k <= FUSED_MAX_K && cs == 1 && ti.group_ctr != nullptr;
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_tilemax, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  SSE_CUDA_OK(cudaFuncSetAttribute(fn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
 
   // clusters per super-group: fill the SM budget, but never more clusters than can be co-resident (one CTA per SM and
   // the CTAs of a cluster share a GPC, so fewer than num_sms / cs clusters may fit)
@@ -1198,30 +1338,40 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   float* tm = reinterpret_cast<float*>(w + o_tm);
   float* tnorm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ti.h16) + align_up((size_t)N * E * 2, 16));
 
-  prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E_true, E, gstride, rpg, qb, qn);
-  if (launches) ++*launches;
-
   const CUtensorMap& tmi = ti.use3d ? *reinterpret_cast<const CUtensorMap*>(tn == 128 ? ti.tmap3d : ti.tmap3d64)
                                     : *reinterpret_cast<const CUtensorMap*>(tn == 128 ? ti.tmap : ti.tmap64);
   sp.qb = qb;
   sp.use3d = ti.use3d ? 1 : 0;
-
-  // pass A: tile maxima over the strided sample
-  sp.n_j = n_s; sp.tile_step = s_step; sp.tilemax = tm; sp.tau = nullptr;
-  SSE_CUDA_OK(cudaLaunchKernelEx(&lcfg, fn_tilemax, tmi, sp));
-  if (launches) ++*launches;
-  select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, gstride, rpg, qn, tnorm, tau, mg);
-  if (launches) ++*launches;
-
-  // pass B: filter over all tiles
-  sp.n_j = n_tiles; sp.tile_step = 1; sp.tilemax = nullptr; sp.tau = tau; sp.margin = mg; sp.k = k;
+  sp.k = k;
   sp.dbg = want_dbg ? reinterpret_cast<long long*>(w + o_dbg) : nullptr;
   sp.dbg_flags = (want_dbg && getenv("SSE_SCAN_FLAGS")) ? atoi(getenv("SSE_SCAN_FLAGS")) : 0;
   sp.cand_s = reinterpret_cast<float*>(w + o_cs);
   sp.cand_i = reinterpret_cast<int32_t*>(w + o_ci);
   sp.cand_cnt = reinterpret_cast<int32_t*>(w + o_cc);
-  SSE_CUDA_OK(cudaLaunchKernelEx(&lcfg, fn_filter, tmi, sp));
-  if (launches) ++*launches;
+  if (fused) {
+    sp.q32 = q; sp.Q = Q; sp.E_true = E_true; sp.gstride = gstride; sp.rpg = rpg; sp.tnorm_max = tnorm;
+    sp.margin_out = mg; sp.tau_out = tau; sp.group_ctr = ti.group_ctr; sp.n_s = n_s; sp.s_step = s_step;
+    sp.n_j = n_tiles; sp.tile_step = 1; sp.tilemax = tm; sp.tau = nullptr; sp.margin = nullptr;
+    SSE_CUDA_OK(cudaLaunchKernelEx(&lcfg, fn_fused, tmi, sp));
+    if (launches) ++*launches;
+  } else {
+    prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E_true, E, gstride, rpg, qb, qn);
+    if (launches) ++*launches;
+    // pass A: tile maxima over the strided sample
+    sp.n_j = n_s; sp.tile_step = s_step; sp.tilemax = tm; sp.tau = nullptr;
+    {
+      ScanParams spa = sp;
+      spa.dbg = nullptr;
+      SSE_CUDA_OK(cudaLaunchKernelEx(&lcfg, fn_tilemax, tmi, spa));
+    }
+    if (launches) ++*launches;
+    select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, gstride, rpg, qn, tnorm, tau, mg);
+    if (launches) ++*launches;
+    // pass B: filter over all tiles
+    sp.n_j = n_tiles; sp.tile_step = 1; sp.tilemax = nullptr; sp.tau = tau; sp.margin = mg;
+    SSE_CUDA_OK(cudaLaunchKernelEx(&lcfg, fn_filter, tmi, sp));
+    if (launches) ++*launches;
+  }
 
   FinParams fp;
   memset(&fp, 0, sizeof(fp));
@@ -1230,6 +1380,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   fp.cand_s = sp.cand_s; fp.cand_i = sp.cand_i; fp.cand_cnt = sp.cand_cnt; fp.margin = mg;
   fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E_true; fp.k = k;
   fp.out_s = out_scores; fp.out_i = out_idx; fp.out_stride = out_stride; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov);
+  fp.group_ctr = fused ? ti.group_ctr : nullptr;
   ti.last_cnt = sp.cand_cnt; ti.last_cnt_n = (int64_t)items * mtg * TILE_M; ti.last_overflow = fp.overflow; ti.last_Q = Q; ti.last_items = items;
   if (want_dbg) {
     std::vector<long long> hd((size_t)items * DBG_N);

@@ -132,6 +132,7 @@ struct TcIndex {
   alignas(64) unsigned char tmap3d64[128]; // 3-D, box = whole [64 x E] tile
   bool use3d = false;
   bool tmap_ok = false;
+  unsigned* group_ctr = nullptr;    // fused scan: per-m-group barrier counters (device, zero between searches)
   // layout of the last search_tc call's candidate bookkeeping (search_tc_stats)
   const int32_t* last_cnt = nullptr; int64_t last_cnt_n = 0; const int32_t* last_overflow = nullptr; int last_Q = 0, last_items = 0;
 };
