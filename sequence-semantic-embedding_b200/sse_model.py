@@ -70,7 +70,14 @@ class Saver(object):
         lr, gs = self.model.handle.scalars()
         arrays["learning_rate"] = np.float32(lr)
         arrays["global_step"] = np.int64(gs)
-        np.savez(prefix + ".npz", **arrays)
+        # SSE_CHECKPOINT_FORMAT: "npz" (default), "tf" = TensorFlow V2 tensor bundle (<prefix>.index + .data-00000-of-00001,
+        # the files the reference's tf.train.Saver writes, sse_train.py:205,212,232), "both"
+        fmt = os.environ.get("SSE_CHECKPOINT_FORMAT", "npz")
+        if fmt in ("tf", "both"):
+            import tf_bundle
+            tf_bundle.write_bundle(prefix, arrays)
+        if fmt != "tf":
+            np.savez(prefix + ".npz", **arrays)
         d = os.path.dirname(prefix) or "."
         # tf.train.Saver keeps ONE entry per checkpoint name: re-saving `...-BestEver` moves it to the newest
         # position instead of filling the max_to_keep window with duplicates (which would later delete a file

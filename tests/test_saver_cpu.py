@@ -46,3 +46,17 @@ def test_window_rotation_deletes_only_unreferenced_files(tmp_path):
     kept = sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz"))
     assert kept == ["m.ckpt-3.npz", "m.ckpt-4.npz", "m.ckpt-BestEver.npz"]
     assert sse_model.get_checkpoint_state(str(tmp_path)).model_checkpoint_path.endswith("m.ckpt-BestEver")
+
+
+def test_tf_bundle_checkpoint_format(tmp_path, monkeypatch):
+    import tf_bundle
+    monkeypatch.setenv("SSE_CHECKPOINT_FORMAT", "tf")
+    saver = sse_model.Saver(_StubModel(), max_to_keep=2)
+    base = str(tmp_path / "SSE-LSTM.ckpt")
+    for e in range(3):
+        saver.save(None, base, global_step=e)
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["SSE-LSTM.ckpt-1.data-00000-of-00001", "SSE-LSTM.ckpt-1.index", "SSE-LSTM.ckpt-2.data-00000-of-00001", "SSE-LSTM.ckpt-2.index", "checkpoint"]
+    got = tf_bundle.read_bundle(base + "-2", verify_crc=True)
+    assert got["word_embedding"].shape == (3, 2) and int(got["global_step"]) == 7 and abs(float(got["learning_rate"]) - 0.5) < 1e-7
+    assert sse_model.get_checkpoint_state(str(tmp_path)).model_checkpoint_path.endswith("SSE-LSTM.ckpt-2")
