@@ -9,7 +9,7 @@ CXX=${CXX:-g++}
 OUT=../libsse_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default --expt-relaxed-constexpr -Xptxas -v -Wno-deprecated-gpu-targets"
 HOST_FLAGS="-O3 -std=c++17 -fPIC -fvisibility=default"
-SRCS="sse_api.cu lstm_simt.cu lstm_tc.cu lstm_cluster.cu search_simt.cu search_tc.cu cnn.cu util.cu train.cu gemm_tc.cu tok_prep.cu"
+SRCS="sse_api.cu lstm_simt.cu lstm_tc.cu lstm_cluster.cu lstm_gemm.cu search_simt.cu search_tc.cu cnn.cu util.cu train.cu gemm_tc.cu tok_prep.cu"
 HOST_SRCS="tsv_io.cpp subword_tok.cpp"
 HEADERS="sse_common.cuh sse_handle.cuh ../../include/sse_b200.h unicode_alnum.inc $(ls *.cuh 2>/dev/null | tr '\n' ' ')"
 [ "$CLEAN" = "1" ] && rm -rf build

@@ -71,6 +71,7 @@ void invalidate_derived(sse_handle* h) {
   h->pad[0].valid = h->pad[1].valid = false;
   h->pad_tc[0].valid = h->pad_tc[1].valid = false;
   h->tct[0].valid = h->tct[1].valid = false;
+  h->gemm_tw[0].valid = h->gemm_tw[1].valid = false;
   h->tct[0].ptable_valid = h->tct[1].ptable_valid = false;
   h->emb_f16_valid = false;
   h->emb_pad_valid = false;
@@ -217,7 +218,8 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens_in, int B, floa
   // j = tanh(0) = 0 and its c and h stay exactly 0, and padded inputs meet zero weights -- the live units compute the
   // same sums (sse_model.py:236-275 semantics unchanged).
   const int Wp = (We + 63) / 64 * 64, Hp = (H + 63) / 64 * 64;
-  if (want_tc && lstm_tc_supported(Wp, Hp)) {
+  const bool use_gemm_tower = want_tc && (h->opt_lstm_kernel == 4 || !lstm_tc_supported(Wp, Hp)) && lstm_gemm_supported(Wp, Hp);
+  if (want_tc && (lstm_tc_supported(Wp, Hp) || use_gemm_tower)) {
     const bool padded = Wp != We || Hp != H;
     const float* emb_x = emb;
     const float* K_x = tw.K;
@@ -238,6 +240,20 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens_in, int B, floa
         h->emb_pad_valid = true;
       }
       emb_x = h->emb_pad; K_x = pw.K; b_x = pw.b;
+    }
+    if (use_gemm_tower) {
+      // cells wider than the resident-weight kernels hold (H = 512 of BASELINE config 5): one tensor-core GEMM per step
+      GemmTower& gt = h->gemm_tw[side];
+      if (!gt.valid) SSE_TRY(lstm_gemm_prepare(gt, K_x, Wp, Hp, st, &h->launches));
+      const int slab = std::min(B, 8192);
+      SSE_TRY(h->enc_ws.ensure(lstm_gemm_ws_bytes(slab, T, Wp, Hp) + (size_t)B * Hp * 4 + 256));
+      float* hout = reinterpret_cast<float*>(h->enc_ws.as<uint8_t>() + (lstm_gemm_ws_bytes(slab, T, Wp, Hp) + 255) / 256 * 256);
+      for (int b0 = 0; b0 < B; b0 += slab) {
+        const int nb = std::min(slab, B - b0);
+        SSE_TRY(lstm_forward_gemm(tokens + (size_t)b0 * T, nb, T, emb_x, Wp, Hp, gt, b_x, h->enc_ws.p, hout + (size_t)b0 * Hp, Hp, st, &h->launches));
+      }
+      SSE_TRY(sgemm(false, false, B, E, H, 1.f, hout, Hp, tw.M, E, 0.f, proj, E, st, &h->launches));
+      return finish();
     }
     if (!h->emb_f16_valid) {
       if (!h->emb_f16) SSE_CUDA_OK(cudaMalloc(&h->emb_f16, (size_t)c.vocab_size * Wp * 2));
@@ -437,6 +453,7 @@ int sse_destroy(sse_handle* h) {
   lstm_tc_release(h->tct[0]); lstm_tc_release(h->tct[1]);
   lstm_ptable_release(h->tct[0]); lstm_ptable_release(h->tct[1]);
   cnn_tc_release(h->cnn_tc[0]); cnn_tc_release(h->cnn_tc[1]);
+  lstm_gemm_release(h->gemm_tw[0]); lstm_gemm_release(h->gemm_tw[1]);
   if (h->emb_f16) cudaFree(h->emb_f16);
   if (h->emb_pad) cudaFree(h->emb_pad);
   for (int s2 = 0; s2 < 2; ++s2) { if (h->padw[s2].K) cudaFree(h->padw[s2].K); if (h->padw[s2].b) cudaFree(h->padw[s2].b); }
@@ -682,7 +699,7 @@ int sse_set_option(sse_handle* h, const char* key, int value) {
   if (!strcmp(key, "encoder")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_encoder = value; return SSE_OK; }
   if (!strcmp(key, "train")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_train = value; return SSE_OK; }
   if (!strcmp(key, "pad_skip")) { h->opt_pad_skip = value != 0; return SSE_OK; }
-  if (!strcmp(key, "lstm_kernel")) { if (value < 0 || value > 3) return SSE_EINVAL; h->opt_lstm_kernel = value; return SSE_OK; }
+  if (!strcmp(key, "lstm_kernel")) { if (value < 0 || value > 4) return SSE_EINVAL; h->opt_lstm_kernel = value; return SSE_OK; }
   if (!strcmp(key, "search_ctas")) { if (value < 0) return SSE_EINVAL; h->opt_search_ctas = value; return SSE_OK; }
   set_error("sse_set_option: unknown key '%s'", key);
   return SSE_EINVAL;

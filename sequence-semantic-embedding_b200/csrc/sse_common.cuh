@@ -99,6 +99,17 @@ int transpose_to_16(const float* src, int rows, int cols, int64_t lds, uint16_t*
 int gather_rows_16(const int32_t* tokens, int64_t n_tok, const float* emb, int We, int ld, uint16_t* out, int fmt, cudaStream_t st, int64_t* launches);
 int cnn_conv_pool_tc(const uint16_t* X, int n_seq, int T, int ldx, int kf, const uint16_t* Wt, int F, const float* bias, float* pool, int pool_ld,
                      int pool_off, int fmt, cudaStream_t st, int64_t* launches);
+// lstm_gemm.cu: LSTM tower as one gemm_tc call per time step (any We / H multiple of 8: cells wider than 256)
+struct GemmTower {
+  __half* kT16 = nullptr;   // [4H, We+H] fp16 = K^T
+  bool valid = false;
+};
+bool lstm_gemm_supported(int We, int H);
+int lstm_gemm_prepare(GemmTower& gt, const float* K, int We, int H, cudaStream_t st, int64_t* launches);
+void lstm_gemm_release(GemmTower& gt);
+size_t lstm_gemm_ws_bytes(int B, int T, int We, int H);
+int lstm_forward_gemm(const int32_t* tokens, int B, int T, const float* emb, int We, int H, const GemmTower& gt, const float* bias, void* ws,
+                      float* h_out, int ldh, cudaStream_t st, int64_t* launches);
 // cnn.cu, tensor-core path
 struct CnnTc {
   uint16_t* wt[SSE_MAX_CNN_FILTERS] = {};   // [F, k*We] fp16

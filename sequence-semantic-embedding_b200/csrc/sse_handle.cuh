@@ -32,6 +32,7 @@ struct sse_handle {
   sse::CnnTc cnn_tc[2];             // fp16 K-major copies of the CNN filters / projection (lazy, invalidated with the weights)
   sse::PadTable pad[2];             // pad-prefix state tables, fp32 SIMT arithmetic
   sse::PadTable pad_tc[2];          // the same in the arithmetic of lstm_ptable_kernel
+  sse::GemmTower gemm_tw[2];        // K^T fp16 of the GEMM-per-step LSTM tower (lstm_gemm.cu)
   sse::TcTower tct[2];              // tensor-core copies of the LSTM weights (lazy, invalidated with the weights)
   __half* emb_f16 = nullptr;
   bool emb_f16_valid = false;
@@ -56,7 +57,7 @@ struct sse_handle {
 
   int opt_search = 0, opt_encoder = 0;
   int opt_train = 0;                // 0 = auto (tensor cores with SSE_PRECISION_TC), 1 = fp32 SIMT (parity mode), 2 = tensor cores (bf16 operands)
-  int opt_lstm_kernel = 0;          // 0 = auto by batch size; 1 = weight-streaming kernel (lstm_tc.cu); 2 = cluster kernel (lstm_cluster.cu)
+  int opt_lstm_kernel = 0;          // 0 = auto; 1 = weight-streaming kernel (lstm_tc.cu); 2 / 3 = cluster kernels (lstm_cluster.cu); 4 = GEMM per step (lstm_gemm.cu)
   int opt_search_ctas = 0;          // 0 = all SMs; else cap on the scan grid (leaves SMs to a concurrent encoder)
   bool opt_pad_skip = true;         // per-tile pad-prefix start of the LSTM towers (tok_prep.cu)
   int64_t launches = 0;

@@ -198,3 +198,22 @@ def test_tc_lstm_table_follows_parameter_updates():
     assert np.abs(b - O.encode(p2, mode, "src", tok, True)).max() < TOL_TC
     assert np.abs(a - b).max() > 1e-2
     h.close()
+
+
+@pytest.mark.parametrize("mode,We,H,E,T,B,force", [("shared-encoder", 512, 512, 512, 20, 70, 0),      # BASELINE config 5 cell (makefile:17 QnA recipe, T shortened)
+                                                  ("dual-encoder", 320, 384, 128, 12, 33, 0),         # wider than the resident-weight kernels hold
+                                                  ("dual-encoder", 64, 64, 32, 12, 200, 4)])          # forced on a shape the other kernels also run
+def test_tc_lstm_gemm_per_step_tower_within_tolerance(mode, We, H, E, T, B, force):
+    V = 3000
+    h, p = make(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
+    h.set_option("encoder", 2)
+    if force:
+        h.set_option("lstm_kernel", force)
+    rng = np.random.default_rng(We + H)
+    tok = np.concatenate([O.synth_tokens(rng, B - B // 2, T, V, "full"), O.synth_tokens(rng, B // 2, T, V, "real", 4.0)])
+    for side, name in ((sse_ffi.SIDE_SRC, "src"), (sse_ffi.SIDE_TGT, "tgt")):
+        got = h.encode_host(side, tok, True)
+        want = O.encode(p, mode, name, tok, True)
+        err = np.abs(got - want).max()
+        assert 0 < err < TOL_TC, (name, err)
+    h.close()
