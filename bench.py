@@ -76,6 +76,8 @@ def parse():
                     "(default: 2-stage software pipeline over steps: encoder of batch s+1 overlaps the scan of batch s)")
     ap.add_argument("--search-ctas", type=int, default=-1, help="scan grid cap when pipelining (the remaining SMs run the encoder clusters); "
                     "-1 = auto: 108 (= 148 - 5 clusters x 8 CTAs) up to 4 GPUs, uncapped beyond, 0 = uncapped")
+    ap.add_argument("--search-late", type=int, default=0, help="with a scan grid cap: extra LATE scan CTAs that start on the SMs the concurrent encoder frees mid-scan")
+    ap.add_argument("--search-late-share", type=int, default=40, help="tile share of a late scan CTA, percent of a regular one")
     ap.add_argument("--train-steps", type=int, default=5, help="timed train steps for the secondary train-step/s figure (0 = skip)")
     ap.add_argument("--train-rows", type=int, default=0, help="pair rows per GPU per train step (0 = the config's, default 1024 = 512 pos + 512 neg)")
     ap.add_argument("--no-replicas", action="store_true", help="scan one copy of a small (L2-resident) shard every step instead of rotating replicas")
@@ -354,6 +356,8 @@ def run_b200(args):
     if pipeline:
         for hs in scan_handles:
             hs.set_option("search_ctas", args.search_ctas)
+            hs.set_option("search_late_ctas", args.search_late if args.search_ctas else 0)
+            hs.set_option("search_late_share", args.search_late_share)
 
     def encode_all(b, out, scratch, st):
         """this rank's Ql queries through the source encoder; N > 1: all-gather of the [Ql, E] encodings so that every rank
@@ -489,6 +493,7 @@ def run_b200(args):
     # ---- dominant kernel (the index scan) timed alone, CUDA events on the launching stream, for the roofline
     for hs in scan_handles:
         hs.set_option("search_ctas", 0)
+        hs.set_option("search_late_ctas", 0)
     torch.cuda.synchronize()
     encode_all(0, enc2[0], enc_local[0], stream)
     for _ in range(3):
@@ -620,8 +625,10 @@ def run_b200(args):
                    "parallelism": ("index row-shard x%d, %d queries/step: each rank encodes its %d, NCCL all-gather of the [%d,E] encodings, every rank "
                                    "scans its shard for all %d and emits one packed [Q,2k] block, NCCL all-to-all of the per-owner row blocks, "
                                    "merge of G*k candidates for the rank's own %d rows" % (world, Q, Ql, Ql, Q, Ql)) if world > 1 else "single GPU",
-                   "pipeline": ("2-stage over steps: encoder of batch s+1 (its own stream, %d SMs left free by the scan grid cap %d) overlaps the scan of batch s"
-                                % (148 - (args.search_ctas or 148), args.search_ctas or 148)) if pipeline else "none (encode then scan on one stream)",
+                   "pipeline": ("2-stage over steps: encoder of batch s+1 (its own stream, %d SMs left free by the scan grid cap %d%s) overlaps the scan of batch s"
+                                % (148 - (args.search_ctas or 148), args.search_ctas or 148,
+                                   (" + %d late scan CTAs at %d%% share for those SMs once the encoder leaves" % (args.search_late, args.search_late_share))
+                                   if args.search_late and args.search_ctas else "")) if pipeline else "none (encode then scan on one stream)",
                    "timing": "median of %d repeats of the %d-step region (CUDA events, barrier + synchronize on both sides, max over ranks)" % (max(1, args.repeats), args.steps),
                    "l2": (("no flush: the fp16 index shard (%.0f MB) is re-streamed every step and exceeds L2 (126 MB); query batches rotate"
                            % (shard_fp16 / 1e6)) if n_rep == 1 and shard_fp16 > L2_BYTES else

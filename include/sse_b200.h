@@ -209,14 +209,16 @@ int sse_debug_gemm_tc(sse_handle* h, const float* a_dev, const float* b_dev, int
                       float alpha, float beta, float* d_dev, void* stream);
 /* number of kernels this library launched on the handle since creation */
 int64_t sse_launch_count(sse_handle* h);
-/* select kernel variants at run time: key in {"search", "encoder", "lstm_kernel", "pad_skip", "search_ctas", "train"};
+/* select kernel variants at run time: key in {"search", "encoder", "lstm_kernel", "pad_skip", "search_ctas", "search_late_ctas", "search_late_share", "train"};
  * search: 0 auto, 1 simt-fp32, 2 tcgen05-fp16;  encoder: 0 auto, 1 simt-fp32, 2 tcgen05;
  * lstm_kernel (tcgen05 encoder only): 0 auto, 1 weight-streaming kernel, 2 cluster kernel (weights resident in
  * the shared memory of a thread-block cluster), 3 cluster kernel with the input projection tabulated per
  * vocabulary entry (V x 4H fp32 table, rebuilt when parameters change; the default when it fits in 2 GiB);
  * pad_skip: 1 (default) rows are bucketed by their number of leading PADs on the device and every kernel tile starts
  * from the tabulated pad-prefix state instead of running the PAD steps (all entry points), 0 off;  search_ctas: cap on the scan grid (0 = all SMs),
- * so that an encoder launched on another stream can run concurrently on the remaining SMs;
+ * so that an encoder launched on another stream can run concurrently on the remaining SMs;  search_late_ctas /
+ * search_late_share (with a cap): that many EXTRA scan CTAs, numbered last so that they start when the concurrent
+ * kernel frees its SMs, each taking `share` percent of a regular CTA's tile range (default 40);
  * train: 0 auto (tensor cores when the handle was created with SSE_PRECISION_TC and the shapes allow), 1 fp32 SIMT
  * (parity mode), 2 tensor cores (bf16 operands, fp32 accumulation / state / optimizer; error if unsupported). */
 int sse_set_option(sse_handle* h, const char* key, int value);

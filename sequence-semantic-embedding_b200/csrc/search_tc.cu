@@ -81,6 +81,13 @@ struct ScanParams {
   int R;                           // clusters per super-group (a super-group = cs consecutive m-groups)
   int group_first_item[MAX_GROUPS];  // cs == 1: items of group g are [first, first + items)
   int group_items[MAX_GROUPS];
+  // LATE items (cs == 1, optional): extra CTAs numbered after all regular items, meant for SMs that a concurrent kernel
+  // (the encoder of the next batch, on another stream) still holds when the scan starts.  A late item takes late_share/256
+  // of a regular item's tile range, skips the sample pass and never arrives at the group barrier -- it only waits for it.
+  int n_early;                       // items [0, n_early) are regular, [n_early, grid) late
+  int group_first_late[MAX_GROUPS];
+  int group_late[MAX_GROUPS];
+  int late_share;                    // 0..256
   int group_mt[MAX_GROUPS];        // valid m-tiles in the group
   int n_j;                         // tiles visited: tile = tile_base + j * tile_step, j in [0, n_j)
   int tile_step;
@@ -411,25 +418,42 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   const int cs = P.cs;
   const uint32_t rank = cs > 1 ? cluster_ctarank() : 0u;
   int g, r_in_g, R;
+  bool late = false;
+  int R_late = 0;
   if (cs > 1) {
     const int cid = item / cs;
     R = P.R;
     const int sg = cid / R;
     r_in_g = cid - sg * R;
     g = sg * cs + (int)rank;
-  } else {
+  } else if (item < P.n_early) {
     g = 0;
     while (g + 1 < P.n_groups && item >= P.group_first_item[g + 1]) ++g;
     r_in_g = item - P.group_first_item[g];
     R = P.group_items[g];
+    R_late = P.group_late[g];
+  } else {
+    late = true;
+    g = 0;
+    while (g + 1 < P.n_groups && item >= P.group_first_late[g + 1]) ++g;
+    r_in_g = item - P.group_first_late[g];
+    R = P.group_items[g];
+    R_late = P.group_late[g];
   }
   const int mt_count = P.group_mt[g];
-  const int j0 = (int)(((int64_t)P.n_j * r_in_g) / R);
-  const int j1 = (int)(((int64_t)P.n_j * (r_in_g + 1)) / R);
+  // tile range of this item: the group's tiles are split in proportion to the item weights (regular 256, late late_share)
+  int j0, j1;
+  {
+    const int64_t wsum = (int64_t)R * 256 + (int64_t)R_late * P.late_share;
+    const int64_t w0 = late ? (int64_t)R * 256 + (int64_t)r_in_g * P.late_share : (int64_t)r_in_g * 256;
+    const int64_t w1 = w0 + (late ? P.late_share : 256);
+    j0 = (int)(((int64_t)P.n_j * w0) / wsum);
+    j1 = (int)(((int64_t)P.n_j * w1) / wsum);
+  }
   // fused scan: this item first visits its share of the SAMPLE tiles (tile maxima), then -- after the per-group barrier
   // and the threshold selection in the epilogue -- its share of all tiles (filter)
-  const int js0 = MODE == MODE_FUSED ? (int)(((int64_t)P.n_s * r_in_g) / R) : 0;
-  const int js1 = MODE == MODE_FUSED ? (int)(((int64_t)P.n_s * (r_in_g + 1)) / R) : 0;
+  const int js0 = (MODE == MODE_FUSED && !late) ? (int)(((int64_t)P.n_s * r_in_g) / R) : 0;
+  const int js1 = (MODE == MODE_FUSED && !late) ? (int)(((int64_t)P.n_s * (r_in_g + 1)) / R) : 0;
   const int ns_loc = js1 - js0;
   const int n_loc = ns_loc + (j1 - j0);
   auto tile_of = [&](int jj) { return jj < ns_loc ? (js0 + jj) * P.s_step : (j0 + jj - ns_loc) * P.tile_step; };
@@ -651,7 +675,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
           __threadfence();
           __syncwarp();
           if (lane == 0) {
-            atomicAdd(P.group_ctr + g, 1u);
+            if (!late) atomicAdd(P.group_ctr + g, 1u);
             const unsigned target = (unsigned)(R * mt_count * 4);
             long long t0w = 0;
             for (unsigned spins = 0;; ++spins) {
@@ -749,7 +773,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         if (MODE == MODE_TILEMAX) P.tilemax[(size_t)(j0 + jj) * P.Qp + grow] = tmax;
         if (MODE == MODE_FUSED && sampling) P.tilemax[(size_t)grow * P.n_s + js0 + jj] = tmax;      // row-major: the selection reads one row
       }
-      if (MODE == MODE_FUSED && n_loc == ns_loc) {          // an item without filter tiles still owes the group its arrival
+      if (MODE == MODE_FUSED && n_loc == ns_loc && !late) {          // an item without filter tiles still owes the group its arrival
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(P.group_ctr + g, 1u);
@@ -758,7 +782,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
       if (P.dbg && e == 0 && lane == 0) { P.dbg[item * DBG_N + 6] = w_accf; P.dbg[item * DBG_N + 7] = clock64() - t_begin; P.dbg[item * DBG_N + 8] = w_ld; P.dbg[item * DBG_N + 9] = w_cmp; P.dbg[item * DBG_N + 10] = cnt; }
     } else if (mt < mt_count && MODE != MODE_TILEMAX) {
       P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + mt * TILE_M + quarter * 32 + lane] = 0;
-      if (MODE == MODE_FUSED && lane == 0) atomicAdd(P.group_ctr + g, 1u);      // no tiles at all: arrive, never wait
+      if (MODE == MODE_FUSED && lane == 0 && !late) atomicAdd(P.group_ctr + g, 1u);      // no tiles at all: arrive, never wait
     }
   }
   tc_fence_before();
@@ -877,6 +901,8 @@ struct FinParams {
   int cs, R;               // cluster scan layout: item of (group g, range it) = ((g / cs) * R + it) * cs + g % cs
   int group_first_item[MAX_GROUPS];   // cs == 1: items of group g are [first, first + items)
   int group_items[MAX_GROUPS];
+  int group_first_late[MAX_GROUPS];   // late items of group g (see ScanParams)
+  int group_late[MAX_GROUPS];
   const float* cand_s;
   const int32_t* cand_i;
   const int32_t* cand_cnt;
@@ -929,8 +955,9 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   if (tid == 0) { s_total = 0; s_over = 0; }
   __syncthreads();
   // gather candidates (one item at a time per thread; counts are small)
-  for (int it = tid; it < R; it += blockDim.x) {
-    size_t slot = (size_t)(first + it * istride) * rows_per_group + lrow;
+  const int R_l = P.cs > 1 ? 0 : P.group_late[g];
+  for (int it = tid; it < R + R_l; it += blockDim.x) {
+    size_t slot = (size_t)(it < R ? first + it * istride : P.group_first_late[g] + (it - R)) * rows_per_group + lrow;
     int c = P.cand_cnt[slot];
     if (c > CAND_CAP) { atomicExch(&s_over, 1); c = CAND_CAP; }
     int at = atomicAdd(&s_total, c);
@@ -1156,7 +1183,8 @@ static int env_int(const char* name, int dflt) {
 }
 
 int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
-              float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches, int out_stride) {
+              float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches, int out_stride,
+              int late_ctas, int late_share) {
   if (Q <= 0) return SSE_OK;
   if (out_stride <= 0) out_stride = k;
   if (!ti.tmap_ok || ti.E != E) { set_error("search_tc: index not prepared"); return SSE_ESTATE; }
@@ -1309,9 +1337,19 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
       sp.group_items[g] = Rg;
       first += Rg;
     }
+    sp.n_early = first;
+    // late items (see ScanParams): spread over the groups like the regular ones
+    sp.late_share = std::max(0, std::min(256, late_share * 256 / 100));
+    for (int g = 0; g < n_groups; ++g) {
+      int Rl = late_ctas > 0 ? (int)((c_tile + c_mt * sp.group_mt[g]) / cost_sum * late_ctas + 0.5) : 0;
+      sp.group_first_late[g] = first;
+      sp.group_late[g] = Rl;
+      first += Rl;
+    }
     items = first;
     R = sp.group_items[0];
   }
+  if (cs > 1) sp.n_early = items;
   sp.cs = cs; sp.R = R;
   lcfg.gridDim = dim3(items, 1, 1);
 
@@ -1376,7 +1414,10 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   FinParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.n_groups = n_groups; fp.mtg = mtg; fp.rpg = rpg; fp.cs = cs; fp.R = R;
-  for (int g = 0; g < n_groups; ++g) { fp.group_first_item[g] = sp.group_first_item[g]; fp.group_items[g] = sp.group_items[g]; }
+  for (int g = 0; g < n_groups; ++g) {
+    fp.group_first_item[g] = sp.group_first_item[g]; fp.group_items[g] = sp.group_items[g];
+    fp.group_first_late[g] = sp.group_first_late[g]; fp.group_late[g] = sp.group_late[g];
+  }
   fp.cand_s = sp.cand_s; fp.cand_i = sp.cand_i; fp.cand_cnt = sp.cand_cnt; fp.margin = mg;
   fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E_true; fp.k = k;
   fp.out_s = out_scores; fp.out_i = out_idx; fp.out_stride = out_stride; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov);

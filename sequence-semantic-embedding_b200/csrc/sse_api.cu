@@ -331,7 +331,8 @@ int search_device(sse_handle* h, const float* q, int Q, int k, float* scores, in
       int nq = std::min(maxq, Q - q0);
       SSE_TRY(search_tc(q + (size_t)q0 * E, nq, E, h->index_f32, h->tc, h->index_off, k, scores + (size_t)q0 * out_stride,
                         idx + (size_t)q0 * out_stride, h->search_ws,
-                        h->opt_search_ctas > 0 ? std::min(h->opt_search_ctas, h->num_sms) : h->num_sms, st, &h->launches, out_stride));
+                        h->opt_search_ctas > 0 ? std::min(h->opt_search_ctas, h->num_sms) : h->num_sms, st, &h->launches, out_stride,
+                        h->opt_search_ctas > 0 ? h->opt_search_late : 0, h->opt_search_late_share));
     }
     return SSE_OK;
   }
@@ -701,6 +702,8 @@ int sse_set_option(sse_handle* h, const char* key, int value) {
   if (!strcmp(key, "pad_skip")) { h->opt_pad_skip = value != 0; return SSE_OK; }
   if (!strcmp(key, "lstm_kernel")) { if (value < 0 || value > 4) return SSE_EINVAL; h->opt_lstm_kernel = value; return SSE_OK; }
   if (!strcmp(key, "search_ctas")) { if (value < 0) return SSE_EINVAL; h->opt_search_ctas = value; return SSE_OK; }
+  if (!strcmp(key, "search_late_ctas")) { if (value < 0 || value > 1024) return SSE_EINVAL; h->opt_search_late = value; return SSE_OK; }
+  if (!strcmp(key, "search_late_share")) { if (value < 0 || value > 100) return SSE_EINVAL; h->opt_search_late_share = value; return SSE_OK; }
   set_error("sse_set_option: unknown key '%s'", key);
   return SSE_EINVAL;
 }

@@ -153,7 +153,7 @@ int search_tc_prepare(TcIndex& ti, const float* index_f32, int64_t N, int E, cud
 void search_tc_release(TcIndex& ti);
 int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti, int64_t global_offset, int k,
               float* out_scores, int32_t* out_idx, Scratch& ws, int num_sms, cudaStream_t st, int64_t* launches,
-              int out_stride = 0);
+              int out_stride = 0, int late_ctas = 0, int late_share = 0);
 // candidates / fallback rows of the LAST search_tc call on this index (synchronises; for benchmarks and tests)
 struct SearchStats { long long candidates = 0; int rows = 0, fallback_rows = 0, items = 0; };
 int search_tc_stats(const TcIndex& ti, SearchStats* out);

@@ -59,6 +59,8 @@ struct sse_handle {
   int opt_train = 0;                // 0 = auto (tensor cores with SSE_PRECISION_TC), 1 = fp32 SIMT (parity mode), 2 = tensor cores (bf16 operands)
   int opt_lstm_kernel = 0;          // 0 = auto; 1 = weight-streaming kernel (lstm_tc.cu); 2 / 3 = cluster kernels (lstm_cluster.cu); 4 = GEMM per step (lstm_gemm.cu)
   int opt_search_ctas = 0;          // 0 = all SMs; else cap on the scan grid (leaves SMs to a concurrent encoder)
+  int opt_search_late = 0;          // with a cap: extra LATE scan items for the SMs the concurrent kernel frees mid-scan ...
+  int opt_search_late_share = 40;   // ... each taking this percentage of a regular item's tile range
   bool opt_pad_skip = true;         // per-tile pad-prefix start of the LSTM towers (tok_prep.cu)
   int64_t launches = 0;
 };
