@@ -187,6 +187,18 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
                     int B_global, float* loss_host, float* acc_host, void* stream);
 int sse_grad_arena(sse_handle* h, float** dev_ptr_out, int64_t* n_floats_out);
 int sse_train_apply(sse_handle* h, float* loss_host, float* acc_host, float* gnorm_host, void* stream);
+/* Device-side train-batch sampler (replaces the python loop of data.py:95-115 -> Data.get_train_batch).
+ * sse_sampler_set copies the training corpus to the device once: src_rows int32 [n_pos, T] (padded source sequences),
+ * the verified targets of positive i as ver_rows[ver_off[i] .. ver_off[i+1]) (ROW numbers into tgt_rows, CSR; every
+ * positive needs at least one), tgt_rows int32 [n_tgt, T] (the encoded full target space).  All host pointers.
+ * sse_sampler_batch writes the pair rows of the window of positives [start, start + batch_size) -- rows alternate
+ * (source, one verified target, 1.0), (same source, one uniformly drawn NON-verified target, 0.0), exactly the layout
+ * sse_train_step consumes -- into device buffers sized [2*batch_size, T] / [2*batch_size]; *rows_out = rows written
+ * (shorter near the end of the corpus, as data.py:97-98).  Draws are a hash of (seed, step, positive): reproducible. */
+int sse_sampler_set(sse_handle* h, const int32_t* src_rows, int64_t n_pos, const int64_t* ver_off, const int32_t* ver_rows,
+                    const int32_t* tgt_rows, int64_t n_tgt);
+int sse_sampler_batch(sse_handle* h, int64_t start, int batch_size, uint64_t seed, uint64_t step, int32_t* src_dev,
+                      int32_t* tgt_dev, float* labels_dev, int* rows_out, void* stream);
 /* learning_rate_decay_op, sse_model.py:123-124 */
 int sse_lr_decay(sse_handle* h);
 int sse_get_scalars(sse_handle* h, float* learning_rate, int64_t* global_step);

@@ -345,6 +345,8 @@ int search_device(sse_handle* h, const float* q, int Q, int k, float* scores, in
 // =============================================================================
 extern "C" {
 
+static void sampler_free(sse_handle* h);
+
 const char* sse_last_error(void) { return get_error(); }
 const char* sse_version(void) { return "sse_b200 0.1 sm_100a"; }
 
@@ -448,6 +450,7 @@ int sse_destroy(sse_handle* h) {
   h->pad_tc[0].buf.release(); h->pad_tc[1].buf.release();
   h->tok_ws.release(); h->proj_ws.release(); h->train_tc_ws.release();
   if (h->tok_bad) cudaFree(h->tok_bad);
+  sampler_free(h);
   if (h->index_f32 && h->index_owned) cudaFree(h->index_f32);
   if (h->grad_arena) cudaFree(h->grad_arena);
   search_tc_release(h->tc);
@@ -665,6 +668,50 @@ int sse_debug_gemm_tc(sse_handle* h, const float* a_dev, const float* b_dev, int
   SSE_TRY(convert_to_16(a_dev, M, K, K, a16, ldk, fmt, st, &h->launches));
   SSE_TRY(convert_to_16(b_dev, N, K, K, b16, ldk, fmt, st, &h->launches));
   return gemm_tc(a16, ldk, b16, ldk, M, N, K, alpha, beta, d_dev, N, fmt, split_k, nullptr, 0, st, &h->launches);
+}
+
+static void sampler_free(sse_handle* h) {
+  if (h->smp_src) cudaFree(h->smp_src);
+  if (h->smp_ver) cudaFree(h->smp_ver);
+  if (h->smp_tgt) cudaFree(h->smp_tgt);
+  if (h->smp_off) cudaFree(h->smp_off);
+  h->smp_src = h->smp_ver = h->smp_tgt = nullptr; h->smp_off = nullptr; h->smp_P = h->smp_N = 0;
+}
+
+int sse_sampler_set(sse_handle* h, const int32_t* src_rows, int64_t n_pos, const int64_t* ver_off, const int32_t* ver_rows, const int32_t* tgt_rows,
+                    int64_t n_tgt) {
+  if (!h || !src_rows || !ver_off || !ver_rows || !tgt_rows || n_pos < 1 || n_tgt < 2) { set_error("sse_sampler_set: bad argument"); return SSE_EINVAL; }
+  SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
+  const int T = h->cfg.max_seq_length;
+  const int64_t nnz = ver_off[n_pos];
+  for (int64_t i = 0; i < n_pos; ++i)
+    if (ver_off[i + 1] <= ver_off[i]) { set_error("sse_sampler_set: positive %lld has no verified target", (long long)i); return SSE_EINVAL; }
+  for (int64_t x = 0; x < nnz; ++x)
+    if (ver_rows[x] < 0 || ver_rows[x] >= n_tgt) { set_error("sse_sampler_set: verified target row out of range"); return SSE_EINVAL; }
+  sampler_free(h);
+  SSE_CUDA_OK(cudaMalloc(&h->smp_src, (size_t)n_pos * T * 4));
+  SSE_CUDA_OK(cudaMalloc(&h->smp_off, (size_t)(n_pos + 1) * 8));
+  SSE_CUDA_OK(cudaMalloc(&h->smp_ver, (size_t)nnz * 4));
+  SSE_CUDA_OK(cudaMalloc(&h->smp_tgt, (size_t)n_tgt * T * 4));
+  SSE_CUDA_OK(cudaMemcpy(h->smp_src, src_rows, (size_t)n_pos * T * 4, cudaMemcpyHostToDevice));
+  SSE_CUDA_OK(cudaMemcpy(h->smp_off, ver_off, (size_t)(n_pos + 1) * 8, cudaMemcpyHostToDevice));
+  SSE_CUDA_OK(cudaMemcpy(h->smp_ver, ver_rows, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+  SSE_CUDA_OK(cudaMemcpy(h->smp_tgt, tgt_rows, (size_t)n_tgt * T * 4, cudaMemcpyHostToDevice));
+  h->smp_P = n_pos; h->smp_N = n_tgt;
+  return SSE_OK;
+}
+
+int sse_sampler_batch(sse_handle* h, int64_t start, int batch_size, uint64_t seed, uint64_t step, int32_t* src_dev, int32_t* tgt_dev, float* labels_dev,
+                      int* rows_out, void* stream) {
+  if (!h || !src_dev || !tgt_dev || !labels_dev || batch_size < 1 || start < 0) { set_error("sse_sampler_batch: bad argument"); return SSE_EINVAL; }
+  if (!h->smp_src) { set_error("sse_sampler_batch: no corpus registered (sse_sampler_set)"); return SSE_ESTATE; }
+  if (start >= h->smp_P) { set_error("sse_sampler_batch: start %lld beyond the %lld positives", (long long)start, (long long)h->smp_P); return SSE_EINVAL; }
+  SSE_CUDA_OK(cudaSetDevice(h->cfg.device));
+  const int B = (int)std::min<int64_t>(batch_size, h->smp_P - start);        // short window near the end (data.py:97-98)
+  SSE_TRY(sample_train_batch(h->smp_src, h->smp_off, h->smp_ver, h->smp_tgt, h->smp_N, h->cfg.max_seq_length, start, B, seed, step, src_dev, tgt_dev,
+                             labels_dev, (cudaStream_t)stream, &h->launches));
+  if (rows_out) *rows_out = 2 * B;
+  return SSE_OK;
 }
 
 int sse_l2_normalize_rows(sse_handle* h, float* x_dev, int rows, int cols, void* stream) {

@@ -169,6 +169,8 @@ size_t tok_prep_ws_bytes(int B, int T);
 int tok_prep(const int32_t* tokens, int B, int T, int V, bool sort, void* ws, TokPrep* out, int* bad_total, cudaStream_t st,
              int64_t* launches);
 int sanitize_tokens_inplace(int32_t* tokens, int64_t n, int V, int* bad_total, cudaStream_t st, int64_t* launches);
+int sample_train_batch(const int32_t* src_rows, const int64_t* ver_off, const int32_t* ver_rows, const int32_t* tgt_rows, int64_t N, int T, int64_t start,
+                       int B, uint64_t seed, uint64_t step, int32_t* src_out, int32_t* tgt_out, float* lab_out, cudaStream_t st, int64_t* launches);
 int unpermute_rows(const float* x, float* y, const int32_t* perm, int rows, int cols, int normalize, cudaStream_t st, int64_t* launches);
 // per-tile pad-prefix start of the tensor-core LSTM kernels (all null = off)
 struct PadSkip {

@@ -55,6 +55,11 @@ struct sse_handle {
   int64_t grad_floats = 0;          // dense (non-embedding) part
   int64_t arena_floats = 0;
 
+  // device-resident training corpus of the batch sampler (sse_sampler_set)
+  int32_t *smp_src = nullptr, *smp_ver = nullptr, *smp_tgt = nullptr;
+  int64_t* smp_off = nullptr;
+  int64_t smp_P = 0, smp_N = 0;
+
   int opt_search = 0, opt_encoder = 0;
   int opt_train = 0;                // 0 = auto (tensor cores with SSE_PRECISION_TC), 1 = fp32 SIMT (parity mode), 2 = tensor cores (bf16 operands)
   int opt_lstm_kernel = 0;          // 0 = auto; 1 = weight-streaming kernel (lstm_tc.cu); 2 / 3 = cluster kernels (lstm_cluster.cu); 4 = GEMM per step (lstm_gemm.cu)

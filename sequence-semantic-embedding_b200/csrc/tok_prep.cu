@@ -196,3 +196,60 @@ int unpermute_rows(const float* x, float* y, const int32_t* perm, int rows, int 
 }
 
 }  // namespace sse
+
+// ======================================================================================================================
+// Device-side train-batch sampler (reference data.py:95-115).  The corpus lives in HBM as arrays -- source
+// rows [P,T], the verified-target lists in CSR form over target ROW numbers, target rows [N,T] -- and one launch writes the
+// step's 2B pair rows straight into the buffers sse_train_step consumes: rows alternate (positive pair, 1.0), (random
+// NON-verified target, 0.0) for the window of positives [start, start + B).  Same rule and layout as the reference's
+// python loop; the random stream is a counter-based hash of (seed, step, row, draw) instead of numpy's (the reference is
+// unseeded), so the distribution is the same and a (seed, step) pair is reproducible.
+namespace sse {
+namespace {
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {      // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// warp per positive: lane 0 draws, all lanes copy the token rows
+__global__ void sample_train_batch_kernel(const int32_t* __restrict__ src_rows, const int64_t* __restrict__ ver_off, const int32_t* __restrict__ ver_rows,
+                                          const int32_t* __restrict__ tgt_rows, int64_t N, int T, int64_t start, int B, uint64_t seed, uint64_t step,
+                                          int32_t* __restrict__ src_out, int32_t* __restrict__ tgt_out, float* __restrict__ lab_out) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= B) return;
+  const int64_t i = start + w;
+  const int64_t o0 = ver_off[i], cnt = ver_off[i + 1] - o0;
+  int pos = 0, neg = 0;
+  if (lane == 0) {
+    const uint64_t base = mix64(seed ^ mix64(step * 0x100000001B3ull + (uint64_t)i));
+    pos = ver_rows[o0 + (int64_t)(mix64(base) % (uint64_t)cnt)];
+    for (uint64_t d = 1;; ++d) {                      // rejection: a target that is NOT verified for this source
+      neg = (int)(mix64(base + d) % (uint64_t)N);
+      bool clash = false;
+      for (int64_t x = 0; x < cnt; ++x) clash |= ver_rows[o0 + x] == neg;
+      if (!clash || d > 64 || cnt >= N) break;
+    }
+  }
+  pos = __shfl_sync(0xffffffffu, pos, 0);
+  neg = __shfl_sync(0xffffffffu, neg, 0);
+  for (int t = lane; t < T; t += 32) {
+    const int32_t sv = src_rows[(size_t)i * T + t];
+    src_out[(size_t)(2 * w) * T + t] = sv;
+    src_out[(size_t)(2 * w + 1) * T + t] = sv;
+    tgt_out[(size_t)(2 * w) * T + t] = tgt_rows[(size_t)pos * T + t];
+    tgt_out[(size_t)(2 * w + 1) * T + t] = tgt_rows[(size_t)neg * T + t];
+  }
+  if (lane == 0) { lab_out[2 * w] = 1.f; lab_out[2 * w + 1] = 0.f; }
+}
+}  // namespace
+
+int sample_train_batch(const int32_t* src_rows, const int64_t* ver_off, const int32_t* ver_rows, const int32_t* tgt_rows, int64_t N, int T, int64_t start,
+                       int B, uint64_t seed, uint64_t step, int32_t* src_out, int32_t* tgt_out, float* lab_out, cudaStream_t st, int64_t* launches) {
+  if (B <= 0) return SSE_OK;
+  sample_train_batch_kernel<<<cdiv(B, 8), 256, 0, st>>>(src_rows, ver_off, ver_rows, tgt_rows, N, T, start, B, seed, step, src_out, tgt_out, lab_out);
+  if (launches) ++*launches;
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+}  // namespace sse

@@ -108,7 +108,43 @@ class Data(object):
         labels = numpy.tile(numpy.array([1.0, 0.0], numpy.float32), B)
         return src, tgt, labels
 
+    def device_sampler(self, handle, seed=0):
+        """Device-side sampler: the corpus arrays go to the GPU once; every call of the returned object's
+        next_batch() is ONE kernel writing the step's pair rows into device buffers that sse_train_step consumes."""
+        if not hasattr(self, "_src_rows"):
+            self._build_arrays()
+        return DeviceSampler(handle, self._src_rows, self._ver_off, self._ver_rows, self._tgt_rows, self.rng, seed)
+
     def get_test_batch(self, batch_size):
         num_samples = len(self.rawEvalCorpus)
         idx = self.rng.randint(0, num_samples - batch_size) + batch_size
         return self.rawEvalCorpus[idx:idx + batch_size]
+
+
+class DeviceSampler(object):
+    """Train batches drawn on the GPU (csrc/tok_prep.cu: sample_train_batch_kernel).  Same rule and row layout as
+    Data.get_train_batch (reference data.py:95-115); the window start is drawn on the host (one integer), positives /
+    negatives by a counter-based hash of (seed, step, positive) on the device."""
+
+    def __init__(self, handle, src_rows, ver_off, ver_rows, tgt_rows, rng, seed=0):
+        import torch
+        self.h, self.rng, self.seed, self.step = handle, rng, int(seed), 0
+        self.P, self.T = int(src_rows.shape[0]), int(src_rows.shape[1])
+        handle.sampler_set(src_rows, ver_off, ver_rows, tgt_rows)
+        self._torch = torch
+        self._buf = {}
+
+    def next_batch(self, batch_size, start=None, stream=None):
+        """-> (src int32 [2B,T], tgt int32 [2B,T], labels float32 [2B]) device tensors (views of reused buffers)"""
+        torch = self._torch
+        if batch_size not in self._buf:
+            dev = torch.device("cuda", int(self.h.cfg.device))
+            self._buf[batch_size] = (torch.empty(2 * batch_size, self.T, dtype=torch.int32, device=dev),
+                                     torch.empty(2 * batch_size, self.T, dtype=torch.int32, device=dev),
+                                     torch.empty(2 * batch_size, dtype=torch.float32, device=dev))
+        src, tgt, lab = self._buf[batch_size]
+        if start is None:        # reference window rule: never starts in the first batch_size samples, short windows near the end
+            start = int(self.rng.randint(0, self.P - batch_size)) + batch_size
+        n = self.h.sampler_batch(start, batch_size, self.seed, self.step, src, tgt, lab, stream)
+        self.step += 1
+        return src[:n], tgt[:n], lab[:n]

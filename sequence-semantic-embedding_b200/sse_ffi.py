@@ -87,6 +87,8 @@ _SIGNATURES = {
     "sse_train_grads": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
     "sse_grad_arena": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "sse_train_apply": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
+    "sse_sampler_set": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int64]),
+    "sse_sampler_batch": (C.c_int, [_P, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, _P, _P, _P, C.POINTER(C.c_int), _P]),
     "sse_lr_decay": (C.c_int, [_P]),
     "sse_get_scalars": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "sse_set_scalars": (C.c_int, [_P, C.c_float, C.c_int64]),
@@ -364,6 +366,26 @@ class Handle:
             return None
         self._check(self.lib.sse_train_apply(self._h, C.byref(loss), C.byref(acc), C.byref(gn), _stream_ptr(stream)))
         return loss.value, acc.value, gn.value
+
+    def sampler_set(self, src_rows: np.ndarray, ver_off: np.ndarray, ver_rows: np.ndarray, tgt_rows: np.ndarray):
+        """register the training corpus with the device-side batch sampler (arrays as built by data.Data._build_arrays)"""
+        src_rows = np.ascontiguousarray(src_rows, dtype=np.int32)
+        tgt_rows = np.ascontiguousarray(tgt_rows, dtype=np.int32)
+        ver_off = np.ascontiguousarray(ver_off, dtype=np.int64)
+        ver_rows = np.ascontiguousarray(ver_rows, dtype=np.int32)
+        if src_rows.ndim != 2 or src_rows.shape[1] != self.T or tgt_rows.ndim != 2 or tgt_rows.shape[1] != self.T:
+            raise SseError("sampler rows must be [*, %d]" % self.T)
+        if ver_off.shape[0] != src_rows.shape[0] + 1 or int(ver_off[-1]) != ver_rows.shape[0]:
+            raise SseError("ver_off / ver_rows do not describe %d positives" % src_rows.shape[0])
+        self._check(self.lib.sse_sampler_set(self._h, src_rows.ctypes.data, src_rows.shape[0], ver_off.ctypes.data, ver_rows.ctypes.data,
+                                             tgt_rows.ctypes.data, tgt_rows.shape[0]))
+
+    def sampler_batch(self, start: int, batch_size: int, seed: int, step: int, src_dev, tgt_dev, labels_dev, stream=None) -> int:
+        """device tensors [2*batch_size,T] int32 x2 and [2*batch_size] float32 are filled; returns the number of pair rows written"""
+        n = C.c_int()
+        self._check(self.lib.sse_sampler_batch(self._h, start, batch_size, seed, step, _ptr(src_dev), _ptr(tgt_dev), _ptr(labels_dev), C.byref(n),
+                                               _stream_ptr(stream)))
+        return int(n.value)
 
     def lr_decay(self):
         self._check(self.lib.sse_lr_decay(self._h))

@@ -181,3 +181,52 @@ def test_micro_batcher_coalesces_concurrent_single_query_callers_on_the_gpu():
         assert np.array_equal(i, want_i[j])
         assert np.abs(s - want_s[j]).max() < 1e-5 * max(1.0, np.abs(want_s).max())
     h.close()
+
+
+def test_device_side_train_batch_sampler_follows_the_reference_rule():
+    """data.py:95-115 on the device: window of consecutive positives, rows alternate (source, a verified target, 1.0),
+    (same source, a NON-verified target, 0.0); reproducible per (seed, step); feeds sse_train_step directly."""
+    import torch
+    mode, V, We, E, H, T = "dual-encoder", 300, 16, 16, 32, 8
+    P, N, B = 500, 60, 64
+    rng = np.random.default_rng(12)
+    src_rows = O.synth_tokens(rng, P, T, V, "real", 3.0)
+    tgt_rows = O.synth_tokens(rng, N, T, V, "real", 4.0)
+    counts = rng.integers(1, 4, size=P)
+    ver_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    ver_rows = np.concatenate([rng.choice(N, size=c, replace=False) for c in counts]).astype(np.int32)
+    p = O.init_params(mode, V, We, E, H, H, seed=2)
+    h = sse_ffi.Handle(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_FP32)
+    h.set_params(p)
+    h.sampler_set(src_rows, ver_off, ver_rows, tgt_rows)
+    src = torch.empty(2 * B, T, dtype=torch.int32, device="cuda")
+    tgt = torch.empty_like(src)
+    lab = torch.empty(2 * B, device="cuda")
+    start = 200
+    n = h.sampler_batch(start, B, 7, 3, src, tgt, lab)
+    torch.cuda.synchronize()
+    assert n == 2 * B
+    s_, t_, l_ = src.cpu().numpy(), tgt.cpu().numpy(), lab.cpu().numpy()
+    assert np.array_equal(l_, np.tile(np.array([1.0, 0.0], np.float32), B))
+    tgt_key = {tuple(r): j for j, r in enumerate(map(tuple, tgt_rows))}
+    assert len(tgt_key) == N                                             # distinct target rows, so rows identify targets
+    negs = []
+    for w in range(B):
+        i = start + w
+        ver = set(ver_rows[ver_off[i]:ver_off[i + 1]].tolist())
+        assert np.array_equal(s_[2 * w], src_rows[i]) and np.array_equal(s_[2 * w + 1], src_rows[i])
+        assert tgt_key[tuple(t_[2 * w])] in ver                          # the positive pair's target is verified for this source
+        assert tgt_key[tuple(t_[2 * w + 1])] not in ver                  # the negative is not
+        negs.append(tgt_key[tuple(t_[2 * w + 1])])
+    assert len(set(negs)) > B // 4                                       # negatives spread over the target space
+    src2, tgt2, lab2 = torch.empty_like(src), torch.empty_like(tgt), torch.empty_like(lab)
+    h.sampler_batch(start, B, 7, 3, src2, tgt2, lab2)
+    assert torch.equal(tgt, tgt2)                                        # same (seed, step) -> same draw
+    h.sampler_batch(start, B, 7, 4, src2, tgt2, lab2)
+    assert not torch.equal(tgt, tgt2)
+    assert h.sampler_batch(P - 10, B, 7, 5, src2, tgt2, lab2) == 20      # short window at the end of the corpus (data.py:97-98)
+    loss, acc, gn = h.train_step(src, tgt, lab)                          # device buffers feed the train step as they are
+    assert np.isfinite(loss) and gn > 0
+    with pytest.raises(sse_ffi.SseError):
+        h.sampler_batch(P, B, 7, 5, src2, tgt2, lab2)
+    h.close()
