@@ -6,13 +6,11 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 shapes = sys.argv[1:] or ["600x1000000", "4800x125000"]
 CONFIGS = [
     ("auto", {}),
-    ("unfused", {"SSE_SCAN_FUSED": "0"}),
     ("pack0", {"SSE_SCAN_PACK": "0"}),
-    ("pack1", {"SSE_SCAN_PACK": "1"}),
+    ("fused", {"SSE_SCAN_FUSED": "1"}),
+    ("fused pack0", {"SSE_SCAN_FUSED": "1", "SSE_SCAN_PACK": "0"}),
     ("tn64", {"SSE_SCAN_ACC1": "0"}),
-    ("mtg1", {"SSE_SCAN_MTG": "1"}),
     ("cluster", {"SSE_SCAN_CLUSTER": "1"}),
-    ("cluster mtg1", {"SSE_SCAN_CLUSTER": "1", "SSE_SCAN_MTG": "1"}),
 ]
 only = os.environ.get("SCAN_CONFIGS")
 for name, env in CONFIGS:

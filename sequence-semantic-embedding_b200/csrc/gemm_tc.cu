@@ -379,7 +379,11 @@ int gemm_tc(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int 
   const bool atomic = split_k > 1;
 #define LAUNCH_GEMM(BN_, EPI_)                                                                                               \
   do {                                                                                                                        \
-    SSE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + G_STAGES_MAX * ((size_t)128 * KBLK * 2 + (size_t)BN_ * KBLK * 2) + 256))); \
+    static bool attr_set = false;          /* once per instantiation: the call costs about as much as a small GEMM */        \
+    if (!attr_set) {                                                                                                          \
+      SSE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + G_STAGES_MAX * ((size_t)128 * KBLK * 2 + (size_t)BN_ * KBLK * 2) + 256))); \
+      attr_set = true;                                                                                                        \
+    }                                                                                                                         \
     gemm_tc_kernel<BN_, EPI_><<<grid, G_THREADS, smem, st>>>(ta, tb, p);                                                      \
   } while (0)
   if (BN == 64) { if (atomic) LAUNCH_GEMM(64, EPI_ATOMIC); else LAUNCH_GEMM(64, EPI_STORE); }

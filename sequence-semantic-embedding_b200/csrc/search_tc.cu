@@ -40,7 +40,7 @@ constexpr int CAND_CAP = 128;        // candidates per (CTA item, row); compacte
 constexpr int MAX_GROUPS = 64;
 constexpr int DBG_N = 12;            // debug cycle counters per work item
 constexpr int SCAN_THREADS = 384;
-constexpr int FIN_MAXC = 4096;       // candidates per row the finalize kernel can sort
+constexpr int FIN_MAXC_SMALL = 2048, FIN_MAXC_LARGE = 4096;   // candidates per row the finalize kernel can sort (k <= 32 / larger k)
 constexpr int FIN_MAXR = 256;        // candidates per row re-scored exactly
 // Bound of |fp16-operand dot - exact dot| / (|q| |t|), valid for every supported E (<= 512):
 //   operand rounding: q_i(1+a_i) t_i(1+b_i), |a_i|,|b_i| <= u = 2^-11  ->  sum |q_i t_i| (2u + u^2) <= (2u + u^2) |q||t|
@@ -476,7 +476,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < NG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_cle + 8 * s, (uint32_t)cs); }
     mbar_init(bar_a, mt_count * 4);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, ACC1 ? 4 : mt_count * 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, (ACC1 && mt_count > 1) ? 4 : mt_count * 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -490,6 +490,11 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_col0 = (uint32_t)P.a_cols;          // accumulators sit behind the query columns
+  // accumulator scheme of THIS item: ACC1 pairs the two m-tiles (one accumulator each); an item with a single live m-tile
+  // (the remainder group of a fully packed batch) would have nothing to overlap with, so it alternates between the two
+  // accumulators over tiles instead (double buffer), exactly like the !ACC1 scheme with one m-tile
+  const bool pair_acc = ACC1 && mt_count > 1;
+  const int acc_mtg = ACC1 ? 1 : P.mtg;                  // m-tiles per double-buffer half in the !pair_acc addressing
 
   if (warp == 9) {
     // ===== TMA producer.  Every CTA arms its own full barrier for the slot once its consumers released it and tells the
@@ -540,7 +545,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         const int buf = jj & 1;
         const uint32_t use = (uint32_t)(jj >> 1);
         const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
-        if (!ACC1) mbar_wait_timed(bar_acce + 8 * buf, (use & 1) ^ 1, w_acce);
+        if (!pair_acc) mbar_wait_timed(bar_acce + 8 * buf, (use & 1) ^ 1, w_acce);
         mbar_wait_timed(bar_full + 8 * s, ph, w_full);
         const uint64_t bd0 = make_sw128_desc(smem_u32(b_smem + (size_t)s * slot_bytes));
         const uint32_t bd_lo = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
@@ -548,11 +553,11 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           if (mt < mt_count) {
-            if (ACC1) mbar_wait_timed(bar_acce + 8 * mt, ((uint32_t)jj & 1) ^ 1, w_acce);
+            if (pair_acc) mbar_wait_timed(bar_acce + 8 * mt, ((uint32_t)jj & 1) ^ 1, w_acce);
             tc_fence_after();
             if (elect_one_sync()) {
               if (!(P.dbg_flags & 2)) {
-                const uint32_t d = tmem_base + acc_col0 + (uint32_t)(ACC1 ? mt * TN : (buf * P.mtg + mt) * TN);
+                const uint32_t d = tmem_base + acc_col0 + (uint32_t)(pair_acc ? mt * TN : (buf * acc_mtg + mt) * TN);
                 const uint32_t a0 = tmem_base + (uint32_t)(mt * (E / 2));
                 if (KBT > 0) {
 #pragma unroll
@@ -569,12 +574,12 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
                                      (kb | k4) ? 1u : 0u);
                 }
               }
-              if (ACC1) tc_commit(bar_accf + 8 * mt);
+              if (pair_acc) tc_commit(bar_accf + 8 * mt);
             }
             __syncwarp();
           }
         }
-        if (!ACC1) {
+        if (!pair_acc) {
           if (elect_one_sync()) tc_commit(bar_accf + 8 * buf);      // accumulators complete == this ring slot fully read
           __syncwarp();
         }
@@ -666,7 +671,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
       }
       const int n_chunks = TN / 32;
       // the warp that hands the ring slot back: all MMAs of the tile have retired once the LAST accumulator's commit fired
-      const bool releases_slot = ACC1 ? (e == 4 * (mt_count - 1)) : (e == 0);
+      const bool releases_slot = pair_acc ? (e == 4 * (mt_count - 1)) : (e == 0);
       long long w_accf = 0, w_ld = 0, w_cmp = 0, t_begin = clock64();
       for (int jj = 0; jj < n_loc; ++jj) {
         if (MODE == MODE_FUSED && jj == ns_loc) {
@@ -719,8 +724,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
           }
         }
         const bool sampling = MODE == MODE_TILEMAX || (MODE == MODE_FUSED && jj < ns_loc);
-        const int buf = ACC1 ? mt : (jj & 1);
-        const uint32_t use = ACC1 ? (uint32_t)jj : (uint32_t)(jj >> 1);
+        const int buf = pair_acc ? mt : (jj & 1);
+        const uint32_t use = pair_acc ? (uint32_t)jj : (uint32_t)(jj >> 1);
         const int tile = tile_of(jj);
         const int64_t col0 = (int64_t)tile * TN;
         const bool ragged = col0 + TN > P.N;
@@ -728,7 +733,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         tc_fence_after();
         // the MMAs of this tile have retired: hand its ring slot back to the TMA producer
         if (releases_slot && lane == 0) mbar_arrive(bar_empty + 8 * ((uint32_t)jj % NG));
-        const uint32_t taddr = lane_base + acc_col0 + (uint32_t)(ACC1 ? mt * TN : (buf * P.mtg + mt) * TN);
+        const uint32_t taddr = lane_base + acc_col0 + (uint32_t)(pair_acc ? mt * TN : (buf * acc_mtg + mt) * TN);
         float tmax = -CUDART_INF_F;
         // 64 accumulator columns per round: both TMEM loads in flight together; after the last round's data has
         // landed in registers the accumulator buffer goes straight back to the MMA warp, and the compares run
@@ -912,6 +917,7 @@ struct FinParams {
   int64_t global_offset;
   int64_t N;
   int Q, E, k;
+  int maxc;                // candidate capacity of the finalize kernel's shared-memory lists
   int out_stride;          // row stride of out_s / out_i in elements (k, or 2k when both live in one packed [Q,2k] block)
   float* out_s;
   int32_t* out_i;
@@ -942,8 +948,10 @@ __device__ void bitonic_sort_pairs(float* s, int32_t* id, int n) {
 }
 
 __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ FinParams P) {
-  __shared__ float cs[FIN_MAXC];
-  __shared__ int32_t ci[FIN_MAXC];
+  extern __shared__ float fin_dyn[];                   // cs [maxc] | ci [maxc]: 2048 entries for k <= 32 (16 KB: 4+ rows per SM in flight), 4096 above
+  const int FIN_MAXC = P.maxc;
+  float* cs = fin_dyn;
+  int32_t* ci = reinterpret_cast<int32_t*>(fin_dyn + FIN_MAXC);
   __shared__ int s_total, s_over, s_m;
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
@@ -1272,12 +1280,14 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   else if (KB == 4 && tn == 128 && acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 4, 128, true>; fn_filter = scan_kernel<MODE_FILTER, 4, 128, true>; fn_fused = scan_kernel<MODE_FUSED, 4, 128, true>; }
   else if (acc1) { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0, true>; fn_filter = scan_kernel<MODE_FILTER, 0, 0, true>; fn_fused = scan_kernel<MODE_FUSED, 0, 0, true>; }
   else { fn_tilemax = scan_kernel<MODE_TILEMAX, 0, 0, false>; fn_filter = scan_kernel<MODE_FILTER, 0, 0, false>; fn_fused = scan_kernel<MODE_FUSED, 0, 0, false>; }
-  // Fused scan (default when k <= 16, no clusters): sample pass, threshold selection and filter pass in ONE launch --
+  // Fused scan (EXPERIMENT, SSE_SCAN_FUSED=1; k <= 16, no clusters): sample pass, threshold selection and filter pass in ONE launch --
   // the items of an m-group meet at a per-group barrier after their sample tiles (all items are co-resident: the grid
   // never exceeds the SM count and each CTA takes a whole SM), every epilogue thread then selects its own row's threshold
   // from the group's tile maxima.  Saves two launches, the second TMEM allocation / query staging and the fp16 query
-  // pre-pass (the queries are scaled and converted while they are staged).  SSE_SCAN_FUSED=0 restores the 3-kernel form.
-  static const bool env_fused = env_int("SSE_SCAN_FUSED", 1) != 0;
+  // pre-pass (the queries are scaled and converted while they are staged).  Measured SLOWER than the 3-kernel form in its
+  // first version (600 x 1M: +0.07 ms): every epilogue thread walks its row's 488 sampled maxima with L2-latency-bound
+  // loads, 59 items per group repeat the same selection, and the other roles idle meanwhile.  Off by default.
+  static const bool env_fused = env_int("SSE_SCAN_FUSED", 0) != 0;
   const bool fused = env_fused && k <= FUSED_MAX_K && cs == 1 && ti.group_ctr != nullptr;
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_tilemax, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1436,7 +1446,8 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
               nm[c], mn, sm / items, mx, items, nsg, R, cs, mtg, (int)acc1, n_tiles / R, tn, NS);
     }
   }
-  finalize_kernel<<<Q, 128, 0, st>>>(fp);
+  fp.maxc = k <= 32 ? FIN_MAXC_SMALL : FIN_MAXC_LARGE;
+  finalize_kernel<<<Q, 128, (size_t)fp.maxc * 8, st>>>(fp);
   if (launches) ++*launches;
   fallback_kernel<<<Q, 256, (size_t)8 * k * 8, st>>>(fp);
   if (launches) ++*launches;
