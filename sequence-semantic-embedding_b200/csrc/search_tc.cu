@@ -702,8 +702,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
             for (int x = 0; x < FUSED_MAX_K; ++x) top[x] = -CUDART_INF_F;
             const float* tmr = P.tilemax + (size_t)grow * P.n_s;
             const int kk = P.k;
-            for (int x = 0; x < P.n_s; ++x) {
-              float v = __ldcg(tmr + x);
+            auto offer = [&](float v) {
               if (v > top[FUSED_MAX_K - 1]) {
 #pragma unroll
                 for (int y = 0; y < FUSED_MAX_K; ++y) {          // sorted insertion (descending)
@@ -712,7 +711,25 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
                   top[y] = hi;
                 }
               }
+            };
+            // the row's n_s sampled maxima, 64 values per batch of 16 independent 16-byte loads (the row was written by
+            // other SMs: L2 reads; a one-value-at-a-time walk pays the L2 latency n_s times -- measured +70 us)
+            const bool vec4 = (P.n_s & 3) == 0 && ((reinterpret_cast<uintptr_t>(tmr) & 15) == 0);
+            int x = 0;
+            if (vec4) {
+              for (; x + 64 <= P.n_s; x += 64) {
+                float4 b[16];
+#pragma unroll
+                for (int y = 0; y < 16; ++y) b[y] = __ldcg(reinterpret_cast<const float4*>(tmr + x) + y);
+#pragma unroll
+                for (int y = 0; y < 16; ++y) { offer(b[y].x); offer(b[y].y); offer(b[y].z); offer(b[y].w); }
+              }
+              for (; x + 4 <= P.n_s; x += 4) {
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(tmr + x));
+                offer(b.x); offer(b.y); offer(b.z); offer(b.w);
+              }
             }
+            for (; x < P.n_s; ++x) offer(__ldcg(tmr + x));
             float kth = -CUDART_INF_F;
 #pragma unroll
             for (int y = 0; y < FUSED_MAX_K; ++y)
