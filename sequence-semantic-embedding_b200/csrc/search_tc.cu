@@ -345,6 +345,12 @@ __device__ __forceinline__ int chunk_filter(const uint32_t (&v)[32], float thr, 
   return cnt;
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start once every block of its predecessor has executed launch_dependents (or exited); it must execute wait before it
+// touches anything the predecessor writes.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- cluster helpers (multicast variant)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -490,6 +496,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_col0 = (uint32_t)P.a_cols;          // accumulators sit behind the query columns
+  pdl_launch_dependents();                               // (PDL) the next kernel of the search may be scheduled behind this grid
   // accumulator scheme of THIS item: ACC1 pairs the two m-tiles (one accumulator each); an item with a single live m-tile
   // (the remainder group of a fully packed batch) would have nothing to overlap with, so it alternates between the two
   // accumulators over tiles instead (double buffer), exactly like the !ACC1 scheme with one m-tile
@@ -643,6 +650,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a);
       } else {
+        if (MODE == MODE_TILEMAX) pdl_wait();                         // qb comes from prep_queries, the kernel right before the sample pass
         const uint4* src = reinterpret_cast<const uint4*>(P.qb + (size_t)grow * E);
         const uint32_t a_t = lane_base + (uint32_t)(mt * (E / 2));
         for (int c = 0; c < E / 2; c += 32) {
@@ -664,7 +672,12 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
       float* my_s = nullptr;
       int32_t* my_i = nullptr;
       if (MODE != MODE_TILEMAX) {
-        if (MODE == MODE_FILTER) thr = P.tau[grow];
+        if (MODE == MODE_FILTER) {
+          // (PDL) everything above -- TMEM allocation, barrier set-up, query staging, the first index tiles in flight -- may
+          // have run while select_tau was still executing; tau / margin are its outputs
+          pdl_wait();
+          thr = P.tau[grow];
+        }
         size_t base = ((size_t)item * (P.mtg * TILE_M) + lrow) * CAND_CAP;
         my_s = P.cand_s + base;
         my_i = P.cand_i + base;
@@ -834,6 +847,7 @@ __device__ __forceinline__ int padded_to_query_row(int p, int gstride, int rpg, 
 // original q), so the scaling never reaches the results.
 __global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, int Ep, int gstride, int rpg,
                                     __half* __restrict__ qb, float* __restrict__ qnorm) {
+  pdl_launch_dependents();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= Qp) return;
@@ -881,6 +895,8 @@ __global__ void max_row_norm_kernel(const float* __restrict__ x, int64_t N, int 
 __global__ void select_tau_kernel(const float* __restrict__ tilemax, int n_s, int Qp, int Q, int k, int gstride, int rpg,
                                   const float* __restrict__ qnorm, const float* __restrict__ tnorm_max,
                                   float* __restrict__ tau, float* __restrict__ margin) {
+  pdl_launch_dependents();                 // the filter scan may set itself up (TMEM, staging, first tiles) while this runs
+  pdl_wait();                              // tilemax is the sample pass's output
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= Qp) return;
@@ -1305,6 +1321,9 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   // first version (600 x 1M: +0.07 ms): every epilogue thread walks its row's 488 sampled maxima with L2-latency-bound
   // loads, 59 items per group repeat the same selection, and the other roles idle meanwhile.  Off by default.
   static const bool env_fused = env_int("SSE_SCAN_FUSED", 0) != 0;
+  // Programmatic dependent launch between the kernels of one search (SSE_SCAN_PDL=1): the filter scan's CTAs are
+  // scheduled as soon as the sample pass's CTAs leave their SMs and overlap their whole set-up with select_tau.
+  static const bool env_pdl = env_int("SSE_SCAN_PDL", 0) != 0;
   const bool fused = env_fused && k <= FUSED_MAX_K && cs == 1 && ti.group_ctr != nullptr;
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_tilemax, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1422,6 +1441,15 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   } else {
     prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E_true, E, gstride, rpg, qb, qn);
     if (launches) ++*launches;
+    cudaLaunchAttribute pattr[2];
+    int n_scan_attrs = lcfg.numAttrs;
+    if (env_pdl) {
+      for (int a = 0; a < n_scan_attrs; ++a) pattr[a] = lcfg.attrs[a];
+      pattr[n_scan_attrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      pattr[n_scan_attrs].val.programmaticStreamSerializationAllowed = 1;
+      lcfg.attrs = pattr;
+      lcfg.numAttrs = n_scan_attrs + 1;
+    }
     // pass A: tile maxima over the strided sample
     sp.n_j = n_s; sp.tile_step = s_step; sp.tilemax = tm; sp.tau = nullptr;
     {
@@ -1430,7 +1458,19 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
       SSE_CUDA_OK(cudaLaunchKernelEx(&lcfg, fn_tilemax, tmi, spa));
     }
     if (launches) ++*launches;
-    select_tau_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(tm, n_s, Qp, Q, k, gstride, rpg, qn, tnorm, tau, mg);
+    {
+      cudaLaunchConfig_t scfg;
+      memset(&scfg, 0, sizeof(scfg));
+      scfg.gridDim = dim3(cdiv(Qp, 8), 1, 1);
+      scfg.blockDim = dim3(256, 1, 1);
+      scfg.stream = st;
+      cudaLaunchAttribute sattr[1];
+      sattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      sattr[0].val.programmaticStreamSerializationAllowed = 1;
+      scfg.attrs = sattr;
+      scfg.numAttrs = env_pdl ? 1 : 0;
+      SSE_CUDA_OK(cudaLaunchKernelEx(&scfg, select_tau_kernel, (const float*)tm, n_s, Qp, Q, k, gstride, rpg, (const float*)qn, (const float*)tnorm, tau, mg));
+    }
     if (launches) ++*launches;
     // pass B: filter over all tiles
     sp.n_j = n_tiles; sp.tile_step = 1; sp.tilemax = nullptr; sp.tau = tau; sp.margin = mg;
