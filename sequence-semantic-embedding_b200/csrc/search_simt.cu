@@ -181,6 +181,7 @@ int search_simt(const float* q, int Q, int E, const float* index, int64_t N, int
   int want = max(1, (2 * num_sms) / q_tiles);
   int64_t n_tiles = cdiv64(max((int64_t)1, N), BN);
   int n_chunks = (int)std::min<int64_t>(want, n_tiles);
+  n_chunks = std::max(1, std::min(n_chunks, (96 * 1024) / (8 * k)));       // the merge holds n_chunks * k candidates per row in shared memory
   int64_t tiles_per_chunk = cdiv64(n_tiles, n_chunks);
   n_chunks = (int)cdiv64(n_tiles, tiles_per_chunk);
   int64_t cols_per_chunk = tiles_per_chunk * BN;

@@ -980,12 +980,15 @@ __device__ void bitonic_sort_pairs(float* s, int32_t* id, int n) {
   __syncthreads();
 }
 
+constexpr int FIN_MAX_ITEMS = 512;     // work items one m-group can have (regular + late)
+
 __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ FinParams P) {
   extern __shared__ float fin_dyn[];                   // cs [maxc] | ci [maxc]: 2048 entries for k <= 32 (16 KB: 4+ rows per SM in flight), 4096 above
   const int FIN_MAXC = P.maxc;
   float* cs = fin_dyn;
   int32_t* ci = reinterpret_cast<int32_t*>(fin_dyn + FIN_MAXC);
-  __shared__ int s_total, s_over, s_m;
+  __shared__ int s_off[FIN_MAX_ITEMS + 1];             // prefix sums of the per-item candidate counts of this row
+  __shared__ int s_over, s_m;
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
   if (P.group_ctr && row == 0 && tid < P.n_groups) P.group_ctr[tid] = 0u;
@@ -993,25 +996,47 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   const int g = row / P.rpg, lrow = row % P.rpg;
   const int R = P.cs > 1 ? P.R : P.group_items[g];
   const int first = P.cs > 1 ? (g / P.cs) * P.R * P.cs + g % P.cs : P.group_first_item[g], istride = P.cs;
-  if (tid == 0) { s_total = 0; s_over = 0; }
-  __syncthreads();
-  // gather candidates (one item at a time per thread; counts are small)
   const int R_l = P.cs > 1 ? 0 : P.group_late[g];
-  for (int it = tid; it < R + R_l; it += blockDim.x) {
-    size_t slot = (size_t)(it < R ? first + it * istride : P.group_first_late[g] + (it - R)) * rows_per_group + lrow;
-    int c = P.cand_cnt[slot];
+  const int n_it = min(R + R_l, FIN_MAX_ITEMS);
+  auto slot_of = [&](int it) { return (size_t)(it < R ? first + it * istride : P.group_first_late[g] + (it - R)) * rows_per_group + lrow; };
+  if (tid == 0) { s_over = (R + R_l > FIN_MAX_ITEMS) ? 1 : 0; s_off[0] = 0; }
+  __syncthreads();
+  // ---- gather: counts of every item in parallel, prefix sum, then ONE candidate per thread-iteration (all loads of the
+  // block in flight together; a thread-per-item copy loop serialised 2-3 dependent L2 round trips per item)
+  for (int it = tid; it < n_it; it += blockDim.x) {
+    int c = P.cand_cnt[slot_of(it)];
     if (c > CAND_CAP) { atomicExch(&s_over, 1); c = CAND_CAP; }
-    int at = atomicAdd(&s_total, c);
-    if (at + c > FIN_MAXC) { atomicExch(&s_over, 1); continue; }
-    for (int x = 0; x < c; ++x) { cs[at + x] = P.cand_s[slot * CAND_CAP + x]; ci[at + x] = P.cand_i[slot * CAND_CAP + x]; }
+    s_off[it + 1] = c;
   }
   __syncthreads();
-  int total = min(s_total, FIN_MAXC);
+  if (tid < 32) {                                      // warp scan over the (<= 512) counts
+    int carry = 0;
+    for (int base = 0; base < n_it; base += 32) {
+      const int i = base + tid;
+      int v = i < n_it ? s_off[i + 1] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (tid >= o) v += u; }
+      if (i < n_it) s_off[i + 1] = v + carry;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  __syncthreads();
+  const int total_all = s_off[n_it];
+  if (total_all > FIN_MAXC) { if (tid == 0) s_over = 1; }
+  __syncthreads();
   if (s_over) {
     if (tid == 0) P.overflow[row] = 1;
     return;
   }
   if (tid == 0) P.overflow[row] = 0;
+  const int total = total_all;
+  for (int e = tid; e < total; e += blockDim.x) {
+    int lo = 0, hi = n_it;                             // item with s_off[it] <= e < s_off[it + 1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid; }
+    const size_t src = slot_of(lo) * CAND_CAP + (e - s_off[lo]);
+    cs[e] = P.cand_s[src];
+    ci[e] = P.cand_i[src];
+  }
   int n2 = 1;
   while (n2 < total) n2 <<= 1;
   for (int x = total + tid; x < n2; x += blockDim.x) { cs[x] = -CUDART_INF_F; ci[x] = 0x7fffffff; }
@@ -1034,24 +1059,30 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
     if (tid == 0) P.overflow[row] = 1;
     return;
   }
-  // exact fp32 re-score of the m survivors: warp per candidate
-  const int warp = tid >> 5, lane = tid & 31;
-  const float* qr = P.q + (size_t)row * P.E;
-  for (int c = warp; c < m; c += 4) {
-    const float* tr = P.index + (size_t)(ci[c] - P.global_offset) * P.E;
-    float acc = 0.f;
-    if ((P.E & 3) == 0) {
-      for (int j = lane * 4; j < P.E; j += 128) {
-        float4 a = *reinterpret_cast<const float4*>(qr + j);
-        float4 b = *reinterpret_cast<const float4*>(tr + j);
-        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+  // ---- exact fp32 re-score of the m survivors: 8 lanes per candidate, 16 candidates per pass (m is ~k + a few: one pass)
+  {
+    const int sub = tid & 7, grp = tid >> 3;
+    const float* qr = P.q + (size_t)row * P.E;
+    for (int c0 = 0; c0 < m; c0 += 16) {
+      const int c = c0 + grp;
+      float acc = 0.f;
+      if (c < m) {
+        const float* tr = P.index + (size_t)(ci[c] - P.global_offset) * P.E;
+        if ((P.E & 3) == 0) {
+          for (int j = sub * 4; j < P.E; j += 32) {
+            const float4 a = *reinterpret_cast<const float4*>(qr + j);
+            const float4 b = *reinterpret_cast<const float4*>(tr + j);
+            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+          }
+        } else {                    // odd encoding sizes (the reference recipes use E = 50): rows are not 16-byte aligned
+          for (int j = sub; j < P.E; j += 8) acc = fmaf(qr[j], tr[j], acc);
+        }
       }
-    } else {                      // odd encoding sizes (the reference recipes use E = 50): rows are not 16-byte aligned
-      for (int j = lane; j < P.E; j += 32) acc = fmaf(qr[j], tr[j], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (c < m && sub == 0) cs[c] = acc;
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) cs[c] = acc;
   }
   __syncthreads();
   int m2 = 1;

@@ -86,7 +86,9 @@ __device__ __forceinline__ void copy_row_thread(const int32_t* __restrict__ src,
   }
 }
 
-// B <= one block's worth of work: everything in ONE launch
+// B <= one block's worth of work: everything in ONE launch.  REGS = true (T even, T <= 64): a thread reads its row ONCE into
+// registers (all loads in flight together) and writes it from there; otherwise the row is read twice in unrolled batches.
+template <bool REGS>
 __global__ void __launch_bounds__(TP_THREADS) tok_prep_fused_kernel(const int32_t* __restrict__ tok, int B, int T, int V, int sort,
                                                                     int32_t* __restrict__ stok, int32_t* __restrict__ perm,
                                                                     int32_t* __restrict__ lead_sorted, int* __restrict__ bad_total) {
@@ -96,6 +98,50 @@ __global__ void __launch_bounds__(TP_THREADS) tok_prep_fused_kernel(const int32_
   for (int i = threadIdx.x; i < T; i += TP_THREADS) hist[i] = 0;
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
+  if (REGS) {
+    // B <= TP_THREADS here: one row per thread
+    const int r = threadIdx.x;
+    int2 v[32];
+    int lead = T, bad = 0;
+    if (r < B) {
+      const int2* r2 = reinterpret_cast<const int2*>(tok + (size_t)r * T);
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = t < T / 2 ? __ldg(r2 + t) : make_int2(0, 0);
+#pragma unroll
+      for (int t = 31; t >= 0; --t) {
+        if (t < T / 2) {
+          const bool o0 = v[t].x < 0 || v[t].x >= V, o1 = v[t].y < 0 || v[t].y >= V;
+          bad += (int)o0 + (int)o1;
+          if (o0) v[t].x = 0;
+          if (o1) v[t].y = 0;
+          if (v[t].y != 0) lead = 2 * t + 1;
+          if (v[t].x != 0) lead = 2 * t;
+        }
+      }
+      if (lead > T - 1) lead = T - 1;
+      if (sort) atomicAdd(&hist[lead], 1);
+      if (bad) atomicAdd(&s_bad, bad);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_bad) atomicAdd(bad_total, s_bad);
+      if (sort) {
+        int run = 0;
+        for (int p = T - 1; p >= 0; --p) { const int c = hist[p]; hist[p] = run; run += c; }
+      }
+    }
+    __syncthreads();
+    if (r < B) {
+      const int pos = sort ? atomicAdd(&hist[lead], 1) : r;
+      int2* d2 = reinterpret_cast<int2*>(stok + (size_t)pos * T);
+#pragma unroll
+      for (int t = 0; t < 32; ++t)
+        if (t < T / 2) d2[t] = v[t];
+      perm[pos] = r;
+      lead_sorted[pos] = lead;
+    }
+    return;
+  }
   int bad_t = 0;
   for (int r = threadIdx.x; r < B; r += TP_THREADS) {
     int lead, bad;
@@ -216,7 +262,10 @@ int tok_prep(const int32_t* tokens, int B, int T, int V, bool sort, void* ws, To
   out->sorted = sort;
   if (B <= 0) return SSE_OK;
   if (B <= 8192 && T <= TP_MAX_T) {
-    tok_prep_fused_kernel<<<1, TP_THREADS, (size_t)B * 2, st>>>(tokens, B, T, V, sort ? 1 : 0, out->stok, out->perm, out->lead_sorted, bad_total);
+    if (B <= TP_THREADS && (T & 1) == 0 && T <= 64)
+      tok_prep_fused_kernel<true><<<1, TP_THREADS, (size_t)B * 2, st>>>(tokens, B, T, V, sort ? 1 : 0, out->stok, out->perm, out->lead_sorted, bad_total);
+    else
+      tok_prep_fused_kernel<false><<<1, TP_THREADS, (size_t)B * 2, st>>>(tokens, B, T, V, sort ? 1 : 0, out->stok, out->perm, out->lead_sorted, bad_total);
     if (launches) ++*launches;
   } else {
     SSE_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)T * 4, st));

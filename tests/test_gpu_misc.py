@@ -191,7 +191,8 @@ def test_device_side_train_batch_sampler_follows_the_reference_rule():
     P, N, B = 500, 60, 64
     rng = np.random.default_rng(12)
     src_rows = O.synth_tokens(rng, P, T, V, "real", 3.0)
-    tgt_rows = O.synth_tokens(rng, N, T, V, "real", 4.0)
+    tgt_rows = O.synth_tokens(rng, N, T, V, "full")                    # full-length rows: distinct, so a row identifies its target
+    tgt_rows[:, 1] = 2 + np.arange(N)
     counts = rng.integers(1, 4, size=P)
     ver_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     ver_rows = np.concatenate([rng.choice(N, size=c, replace=False) for c in counts]).astype(np.int32)
