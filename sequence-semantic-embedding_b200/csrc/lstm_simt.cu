@@ -158,16 +158,20 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(
 
 // ---- generic tiled SGEMM: C = alpha * op(A) op(B) + beta * C ------------------
 // op(A) is [M,K], op(B) is [K,N]; row-major storage with leading dimensions.
+// gridDim.z > 1: split-K -- slice z covers k in [z * kchunk, (z+1) * kchunk) and ADDS alpha * partial into C atomically
+// (C must already hold beta * C_old; beta is ignored)
 __global__ void __launch_bounds__(256) sgemm_kernel(bool ta, bool tb, int M, int N, int Kd, float alpha,
                                                     const float* __restrict__ A, int lda,
                                                     const float* __restrict__ Bm, int ldb, float beta,
-                                                    float* __restrict__ C, int ldc) {
+                                                    float* __restrict__ C, int ldc, int kchunk) {
   __shared__ __align__(16) float As[BK][64 + 4];
   __shared__ __align__(16) float Bs[BK][64 + 4];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < Kd; k0 += BK) {
+  const int kbeg = blockIdx.z * kchunk;
+  const int Kend = min(Kd, kbeg + kchunk);
+  for (int k0 = kbeg; k0 < Kend; k0 += BK) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       int idx = tid + e * 256;
@@ -176,13 +180,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(bool ta, bool tb, int M, int
       if (!ta) { r = idx >> 4; kk = idx & 15; } else { kk = idx >> 6; r = idx & 63; }
       int gm = m0 + r, gk = k0 + kk;
       float v = 0.f;
-      if (gm < M && gk < Kd) v = ta ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      if (gm < M && gk < Kend) v = ta ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
       As[kk][r] = v;
       int c2, kk2;
       if (!tb) { kk2 = idx >> 6; c2 = idx & 63; } else { c2 = idx >> 4; kk2 = idx & 15; }
       int gn = n0 + c2, gk2 = k0 + kk2;
       float w = 0.f;
-      if (gn < N && gk2 < Kd) w = tb ? Bm[(size_t)gn * ldb + gk2] : Bm[(size_t)gk2 * ldb + gn];
+      if (gn < N && gk2 < Kend) w = tb ? Bm[(size_t)gn * ldb + gk2] : Bm[(size_t)gk2 * ldb + gn];
       Bs[kk2][c2] = w;
     }
     __syncthreads();
@@ -207,6 +211,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(bool ta, bool tb, int M, int
       int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
       float v = alpha * acc[i][j];
+      if (gridDim.z > 1) { atomicAdd(C + (size_t)gm * ldc + gn, v); continue; }
       if (beta != 0.f) v += beta * C[(size_t)gm * ldc + gn];
       C[(size_t)gm * ldc + gn] = v;
     }
@@ -262,10 +267,22 @@ int lstm_forward_simt(const int32_t* tokens, int B, int T, int t_start, const fl
 }
 
 int sgemm(bool ta, bool tb, int M, int N, int Kd, float alpha, const float* A, int lda, const float* Bm, int ldb,
-          float beta, float* C, int ldc, cudaStream_t st, int64_t* launches) {
+          float beta, float* C, int ldc, cudaStream_t st, int64_t* launches, bool allow_split) {
   if (M <= 0 || N <= 0) return SSE_OK;
   dim3 grid(cdiv(N, 64), cdiv(M, 64));
-  sgemm_kernel<<<grid, 256, 0, st>>>(ta, tb, M, N, Kd, alpha, A, lda, Bm, ldb, beta, C, ldc);
+  // few output tiles and a long contraction (the small GEMMs around the towers: u = h M, dM = h^T du, dh = du M^T): split K
+  // over blockIdx.z so the machine is busy; partial sums are added atomically (C = beta * C first).  Only on request
+  // (the bf16 train step): the summation order is not deterministic, which the exact fp32 paths must not inherit.
+  int splits = 1;
+  if (allow_split && grid.x * grid.y < 48 && Kd >= 256 && (beta == 0.f || beta == 1.f) && (beta == 1.f || ldc == N)) splits = std::min(16, Kd / 64);
+  int kchunk = Kd;
+  if (splits > 1) {
+    kchunk = cdiv(cdiv(Kd, splits), BK) * BK;
+    splits = cdiv(Kd, kchunk);
+    if (beta == 0.f) SSE_CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * N * 4, st));
+    grid.z = splits;
+  }
+  sgemm_kernel<<<grid, 256, 0, st>>>(ta, tb, M, N, Kd, alpha, A, lda, Bm, ldb, beta, C, ldc, kchunk);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
   return SSE_OK;

@@ -82,7 +82,7 @@ int lstm_forward_simt(const int32_t* tokens, int B, int T, int t_start, const fl
                       float** h_final, cudaStream_t st, int64_t* launches,
                       const int32_t* lead = nullptr, const float* pad_h = nullptr, const float* pad_c = nullptr);   // per-row pad-prefix start
 int sgemm(bool ta, bool tb, int M, int N, int Kd, float alpha, const float* A, int lda, const float* Bm, int ldb,
-          float beta, float* C, int ldc, cudaStream_t st, int64_t* launches);
+          float beta, float* C, int ldc, cudaStream_t st, int64_t* launches, bool allow_split = false);
 int l2norm_rows(float* x, int rows, int cols, cudaStream_t st, int64_t* launches);
 int l2norm_rows_out(const float* x, float* y, int rows, int cols, cudaStream_t st, int64_t* launches);
 

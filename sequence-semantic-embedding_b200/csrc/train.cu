@@ -367,7 +367,7 @@ int train_tc_forward(sse_handle* h, int s, const int32_t* tok, int B, uint8_t* w
                                                             ts->h16 + (size_t)t * B * H, t == T - 1 ? ts->hlast : nullptr);
     ++h->launches;
   }
-  SSE_TRY(sgemm(false, false, B, E, H, 1.f, ts->hlast, H, tw.M, E, 0.f, ts->u, E, st, &h->launches));
+  SSE_TRY(sgemm(false, false, B, E, H, 1.f, ts->hlast, H, tw.M, E, 0.f, ts->u, E, st, &h->launches, true));
   SSE_CUDA_OK(cudaGetLastError());
   return SSE_OK;
 }
@@ -393,8 +393,8 @@ int train_tc_backward(sse_handle* h, int s, const int32_t* tok, int B, const TcT
   float* dh = reinterpret_cast<float*>(carve((size_t)2 * B * H * 4));
   float* dc = reinterpret_cast<float*>(carve((size_t)B * H * 4));
   // dM += h_last^T du ; dh_T = du M^T   (small: fp32 SIMT)
-  SSE_TRY(sgemm(true, false, H, E, B, 1.f, ts.hlast, H, du, E, 1.f, gM, E, st, &h->launches));
-  SSE_TRY(sgemm(false, true, B, H, E, 1.f, du, E, tw.M, E, 0.f, dh, H, st, &h->launches));
+  SSE_TRY(sgemm(true, false, H, E, B, 1.f, ts.hlast, H, du, E, 1.f, gM, E, st, &h->launches, true));
+  SSE_TRY(sgemm(false, true, B, H, E, 1.f, du, E, tw.M, E, 0.f, dh, H, st, &h->launches, true));
   SSE_CUDA_OK(cudaMemsetAsync(dc, 0, (size_t)B * H * 4, st));
   // K [We+H, 4H] bf16: B operand (N = rows of K, K-dim = 4H) of dz K^T
   SSE_TRY(convert_to_16(tw.K, ld, 4 * H, 4 * H, k16, 4 * H, 1, st, &h->launches));
