@@ -16,6 +16,19 @@ namespace sse {
 namespace {
 
 constexpr int TP_THREADS = 1024;
+
+// bin[key] += (number of active lanes holding `key`); returns this lane's rank among them + the old bin value: ONE
+// shared-memory atomic per distinct key and warp instead of one per lane (same-address atomics serialise)
+__device__ __forceinline__ int warp_agg_add(int* bins, int key) {
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, key);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&bins[key], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
+}
 constexpr int TP_MAX_T = 2048;        // histogram bins held in shared memory
 
 // warp per row: number of leading PADs (clamped to T-1) and number of out-of-range ids
@@ -119,7 +132,7 @@ __global__ void __launch_bounds__(TP_THREADS) tok_prep_fused_kernel(const int32_
         }
       }
       if (lead > T - 1) lead = T - 1;
-      if (sort) atomicAdd(&hist[lead], 1);
+      if (sort) warp_agg_add(hist, lead);
       if (bad) atomicAdd(&s_bad, bad);
     }
     __syncthreads();
@@ -132,7 +145,7 @@ __global__ void __launch_bounds__(TP_THREADS) tok_prep_fused_kernel(const int32_
     }
     __syncthreads();
     if (r < B) {
-      const int pos = sort ? atomicAdd(&hist[lead], 1) : r;
+      const int pos = sort ? warp_agg_add(hist, lead) : r;
       int2* d2 = reinterpret_cast<int2*>(stok + (size_t)pos * T);
 #pragma unroll
       for (int t = 0; t < 32; ++t)
