@@ -6,6 +6,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 shapes = sys.argv[1:] or ["600x1000000", "4800x125000"]
 CONFIGS = [
     ("auto", {}),
+    ("nospan", {"SSE_SCAN_SPAN": "0"}),
     ("pdl", {"SSE_SCAN_PDL": "1"}),
     ("pack0", {"SSE_SCAN_PACK": "0"}),
     ("fused", {"SSE_SCAN_FUSED": "1"}),

@@ -84,6 +84,11 @@ struct ScanParams {
   // LATE items (cs == 1, optional): extra CTAs numbered after all regular items, meant for SMs that a concurrent kernel
   // (the encoder of the next batch, on another stream) still holds when the scan starts.  A late item takes late_share/256
   // of a regular item's tile range, skips the sample pass and never arrives at the group barrier -- it only waits for it.
+  // SPANNING items (cs == 1, equal packing, not fused): the (group, tile) pairs of ALL m-groups form one list of
+  // n_groups * n_j units that is cut into gridDim.x equal pieces, so every CTA carries the same work whatever the ratio of
+  // CTAs to groups (19 groups on 148 SMs: 7 items per group used 133 SMs).  A piece that crosses a group boundary has two
+  // SEGMENTS: the CTA restages its queries (TMEM A operand) between them and keeps a separate candidate slot per segment.
+  int span;
   int n_early;                       // items [0, n_early) are regular, [n_early, grid) late
   int group_first_late[MAX_GROUPS];
   int group_late[MAX_GROUPS];
@@ -449,20 +454,47 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   const int mt_count = P.group_mt[g];
   // tile range of this item: the group's tiles are split in proportion to the item weights (regular 256, late late_share)
   int j0, j1;
-  {
+  int g2 = 0, k0 = 0, k1 = 0;         // second segment (spanning items only): group g2, tiles [k0, k1)
+  int slot = item, slot2 = 0;         // candidate slots of the two segments
+  if (P.span) {
+    const int64_t U = (int64_t)P.n_groups * P.n_j;
+    const int64_t u0 = U * item / gridDim.x, u1 = U * (item + 1) / gridDim.x;
+    g = (int)(u0 / P.n_j);
+    j0 = (int)(u0 - (int64_t)g * P.n_j);
+    const int64_t gend = (int64_t)(g + 1) * P.n_j;
+    j1 = (int)(min(u1, gend) - (int64_t)g * P.n_j);
+    if (u1 > gend) { g2 = g + 1; k0 = 0; k1 = (int)(u1 - gend); }
+    // slot numbering: one slot per (item, segment), in item order; every group boundary that falls strictly inside an
+    // earlier item (or this one) adds a slot
+    int extra = 0;
+    for (int b = 1; b < P.n_groups; ++b) {
+      const int64_t ub = (int64_t)b * P.n_j;
+      const int ii = (int)((ub * gridDim.x + gridDim.x - 1) / U) - 1;        // candidate item containing unit ub
+      for (int c = max(0, ii - 1); c <= min((int)gridDim.x - 1, ii + 1); ++c) {
+        const int64_t c0 = U * c / gridDim.x, c1 = U * (c + 1) / gridDim.x;
+        if (c0 < ub && ub < c1 && c < item) ++extra;
+      }
+    }
+    slot = item + extra;
+    slot2 = slot + 1;
+    r_in_g = 0; R = 1;
+  } else {
     const int64_t wsum = (int64_t)R * 256 + (int64_t)R_late * P.late_share;
     const int64_t w0 = late ? (int64_t)R * 256 + (int64_t)r_in_g * P.late_share : (int64_t)r_in_g * 256;
     const int64_t w1 = w0 + (late ? P.late_share : 256);
     j0 = (int)(((int64_t)P.n_j * w0) / wsum);
     j1 = (int)(((int64_t)P.n_j * w1) / wsum);
   }
+  const int na = j1 - j0;             // tiles of the first segment
   // fused scan: this item first visits its share of the SAMPLE tiles (tile maxima), then -- after the per-group barrier
   // and the threshold selection in the epilogue -- its share of all tiles (filter)
   const int js0 = (MODE == MODE_FUSED && !late) ? (int)(((int64_t)P.n_s * r_in_g) / R) : 0;
   const int js1 = (MODE == MODE_FUSED && !late) ? (int)(((int64_t)P.n_s * (r_in_g + 1)) / R) : 0;
   const int ns_loc = js1 - js0;
-  const int n_loc = ns_loc + (j1 - j0);
-  auto tile_of = [&](int jj) { return jj < ns_loc ? (js0 + jj) * P.s_step : (j0 + jj - ns_loc) * P.tile_step; };
+  const int n_loc = ns_loc + na + (k1 - k0);
+  auto tile_of = [&](int jj) {
+    return jj < ns_loc ? (js0 + jj) * P.s_step : (jj - ns_loc < na ? (j0 + jj - ns_loc) * P.tile_step : (k0 + jj - ns_loc - na) * P.tile_step);
+  };
   const int KB = KBT ? KBT : P.kb, NG = P.n_stages, TN = TNT ? TNT : P.tn;   // n_stages = number of TILE slots in the ring
   const int E = KB * KBLK;
   const uint32_t kb_bytes = (uint32_t)TN * KBLK * 2;     // one [TN x 64] fp16 SW128 sub-tile
@@ -549,6 +581,10 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
       mbar_wait_timed(bar_a, 0, w_a);
       tc_fence_after();
       for (int jj = 0; jj < n_loc; ++jj) {
+        if (P.span && k1 > k0 && jj == na) {       // second segment: the epilogue has restaged the queries of group g2
+          mbar_wait_timed(bar_a, 1, w_a);
+          tc_fence_after();
+        }
         const int buf = jj & 1;
         const uint32_t use = (uint32_t)(jj >> 1);
         const uint32_t s = (uint32_t)jj % NG, ph = ((uint32_t)jj / NG) & 1;
@@ -598,8 +634,13 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
     const int e = warp;
     const int mt = e >> 2, quarter = e & 3;
     if (mt < mt_count && n_loc > 0) {
+     const int nseg = (P.span && k1 > k0) ? 2 : 1;
+     for (int seg = 0; seg < nseg; ++seg) {       // spanning items: second pass for the tiles that belong to the next m-group
+      const int gs = seg ? g2 : g;
+      const int slot_s = seg ? slot2 : slot;
+      const int jj_lo = seg ? ns_loc + na : 0, jj_hi = seg ? n_loc : ns_loc + na;
       const int lrow = mt * TILE_M + quarter * 32 + lane;             // row within the group
-      const int grow = g * P.mtg * TILE_M + lrow;                     // padded global row
+      const int grow = gs * P.mtg * TILE_M + lrow;                    // padded global row
       const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
       float mg_row = 0.f;                                             // fused: 2*eps of this row
       bool live_row = true;
@@ -678,7 +719,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
           pdl_wait();
           thr = P.tau[grow];
         }
-        size_t base = ((size_t)item * (P.mtg * TILE_M) + lrow) * CAND_CAP;
+        size_t base = ((size_t)slot_s * (P.mtg * TILE_M) + lrow) * CAND_CAP;
         my_s = P.cand_s + base;
         my_i = P.cand_i + base;
       }
@@ -686,7 +727,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
       // the warp that hands the ring slot back: all MMAs of the tile have retired once the LAST accumulator's commit fired
       const bool releases_slot = pair_acc ? (e == 4 * (mt_count - 1)) : (e == 0);
       long long w_accf = 0, w_ld = 0, w_cmp = 0, t_begin = clock64();
-      for (int jj = 0; jj < n_loc; ++jj) {
+      for (int jj = jj_lo; jj < jj_hi; ++jj) {
         if (MODE == MODE_FUSED && jj == ns_loc) {
           // ---- all sample tiles of this item are done: per-group barrier (every epilogue warp of every item of the group
           // arrives once), then this row's threshold = k-th largest of ITS sampled tile maxima - 2 eps
@@ -805,7 +846,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
           }
           if (P.dbg) w_cmp += clock64() - t_c0;
         }
-        if (MODE == MODE_TILEMAX) P.tilemax[(size_t)(j0 + jj) * P.Qp + grow] = tmax;
+        if (MODE == MODE_TILEMAX) P.tilemax[(size_t)(tile_of(jj) / P.tile_step) * P.Qp + grow] = tmax;
         if (MODE == MODE_FUSED && sampling) P.tilemax[(size_t)grow * P.n_s + js0 + jj] = tmax;      // row-major: the selection reads one row
       }
       if (MODE == MODE_FUSED && n_loc == ns_loc && !late) {          // an item without filter tiles still owes the group its arrival
@@ -813,8 +854,9 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
         __syncwarp();
         if (lane == 0) atomicAdd(P.group_ctr + g, 1u);
       }
-      if (MODE != MODE_TILEMAX) P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + lrow] = cnt;
+      if (MODE != MODE_TILEMAX) P.cand_cnt[(size_t)slot_s * (P.mtg * TILE_M) + lrow] = cnt;
       if (P.dbg && e == 0 && lane == 0) { P.dbg[item * DBG_N + 6] = w_accf; P.dbg[item * DBG_N + 7] = clock64() - t_begin; P.dbg[item * DBG_N + 8] = w_ld; P.dbg[item * DBG_N + 9] = w_cmp; P.dbg[item * DBG_N + 10] = cnt; }
+     }
     } else if (mt < mt_count && MODE != MODE_TILEMAX) {
       P.cand_cnt[(size_t)item * (P.mtg * TILE_M) + mt * TILE_M + quarter * 32 + lane] = 0;
       if (MODE == MODE_FUSED && lane == 0 && !late) atomicAdd(P.group_ctr + g, 1u);      // no tiles at all: arrive, never wait
@@ -846,8 +888,9 @@ __device__ __forceinline__ int padded_to_query_row(int p, int gstride, int rpg, 
 // margin and the candidates' approximate scores all carry the same factor; finalize re-scores in fp32 from the
 // original q), so the scaling never reaches the results.
 __global__ void prep_queries_kernel(const float* __restrict__ q, int Q, int Qp, int E, int Ep, int gstride, int rpg,
-                                    __half* __restrict__ qb, float* __restrict__ qnorm) {
+                                    __half* __restrict__ qb, float* __restrict__ qnorm, int32_t* __restrict__ ov_count) {
   pdl_launch_dependents();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ov_count = 0;
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= Qp) return;
@@ -941,6 +984,9 @@ struct FinParams {
   int group_items[MAX_GROUPS];
   int group_first_late[MAX_GROUPS];   // late items of group g (see ScanParams)
   int group_late[MAX_GROUPS];
+  int span;                           // spanning items: the candidate slots of group g are [span_first[g], span_first[g] + span_n[g])
+  int span_first[MAX_GROUPS];
+  int span_n[MAX_GROUPS];
   const float* cand_s;
   const int32_t* cand_i;
   const int32_t* cand_cnt;
@@ -954,7 +1000,9 @@ struct FinParams {
   int out_stride;          // row stride of out_s / out_i in elements (k, or 2k when both live in one packed [Q,2k] block)
   float* out_s;
   int32_t* out_i;
-  int32_t* overflow;       // [Q]
+  int32_t* overflow;       // [Q] flags
+  int32_t* ov_list;        // [Q] rows that need the brute-force fallback, ov_list[-1].. see ov_count
+  int32_t* ov_count;       // number of entries of ov_list (zeroed at the start of every search by prep_queries / the fused scan)
   unsigned* group_ctr;     // fused scan: per-group barrier counters, re-armed (zeroed) here for the next search
 };
 
@@ -983,7 +1031,7 @@ __device__ void bitonic_sort_pairs(float* s, int32_t* id, int n) {
 constexpr int FIN_MAX_ITEMS = 512;     // work items one m-group can have (regular + late)
 
 __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ FinParams P) {
-  extern __shared__ float fin_dyn[];                   // cs [maxc] | ci [maxc]: 2048 entries for k <= 32 (16 KB: 4+ rows per SM in flight), 4096 above
+  extern __shared__ float fin_dyn[];                   // cs [maxc] | ci [maxc] | tmp [maxc] | sv [FIN_MAXR]: maxc = 2048 for k <= 32 (25 KB: 8 rows per SM in flight), 4096 above
   const int FIN_MAXC = P.maxc;
   float* cs = fin_dyn;
   int32_t* ci = reinterpret_cast<int32_t*>(fin_dyn + FIN_MAXC);
@@ -994,9 +1042,9 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   if (P.group_ctr && row == 0 && tid < P.n_groups) P.group_ctr[tid] = 0u;
   const int rows_per_group = P.mtg * TILE_M;
   const int g = row / P.rpg, lrow = row % P.rpg;
-  const int R = P.cs > 1 ? P.R : P.group_items[g];
-  const int first = P.cs > 1 ? (g / P.cs) * P.R * P.cs + g % P.cs : P.group_first_item[g], istride = P.cs;
-  const int R_l = P.cs > 1 ? 0 : P.group_late[g];
+  const int R = P.span ? P.span_n[g] : (P.cs > 1 ? P.R : P.group_items[g]);
+  const int first = P.span ? P.span_first[g] : (P.cs > 1 ? (g / P.cs) * P.R * P.cs + g % P.cs : P.group_first_item[g]), istride = P.span ? 1 : P.cs;
+  const int R_l = (P.cs > 1 || P.span) ? 0 : P.group_late[g];
   const int n_it = min(R + R_l, FIN_MAX_ITEMS);
   auto slot_of = [&](int it) { return (size_t)(it < R ? first + it * istride : P.group_first_late[g] + (it - R)) * rows_per_group + lrow; };
   if (tid == 0) { s_over = (R + R_l > FIN_MAX_ITEMS) ? 1 : 0; s_off[0] = 0; }
@@ -1025,7 +1073,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
   if (total_all > FIN_MAXC) { if (tid == 0) s_over = 1; }
   __syncthreads();
   if (s_over) {
-    if (tid == 0) P.overflow[row] = 1;
+    if (tid == 0) { P.overflow[row] = 1; P.ov_list[atomicAdd(P.ov_count, 1)] = row; }
     return;
   }
   if (tid == 0) P.overflow[row] = 0;
@@ -1037,26 +1085,49 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
     cs[e] = P.cand_s[src];
     ci[e] = P.cand_i[src];
   }
-  int n2 = 1;
-  while (n2 < total) n2 <<= 1;
-  for (int x = total + tid; x < n2; x += blockDim.x) { cs[x] = -CUDART_INF_F; ci[x] = 0x7fffffff; }
-  bitonic_sort_pairs(cs, ci, n2);
-  // survivors: approx >= A_k - margin
+  // ---- k-th best APPROXIMATE score: k rounds of block-wide max extraction on a scratch copy (no full sort: a bitonic sort
+  // of ~256 pairs is 36 barrier-separated stages; measured 2.6 k instructions per warp at 14 cycles each)
+  float* tmp = reinterpret_cast<float*>(ci + FIN_MAXC);      // [maxc] scratch scores, later the exact scores of the survivors
+  int32_t* sv = reinterpret_cast<int32_t*>(tmp + FIN_MAXC);  // [FIN_MAXR] survivor ids
+  __shared__ float s_wv[4];
+  __shared__ int s_we[4];
+  __shared__ float s_kth;
   const int k = P.k;
-  if (tid == 0) {
-    int m = total;
-    if (total >= k) {
-      float cut = cs[k - 1] - P.margin[g * rows_per_group + lrow];
-      int lo = k, hi = total;          // first index with cs < cut (sorted descending)
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (cs[mid] >= cut) lo = mid + 1; else hi = mid; }
-      m = lo;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < total; e += blockDim.x) tmp[e] = cs[e];
+  if (tid == 0) { s_m = 0; s_kth = -CUDART_INF_F; }
+  __syncthreads();
+  if (total >= k) {
+    for (int r = 0; r < k; ++r) {
+      float bs = -CUDART_INF_F;
+      int be = 0x7fffffff;
+      for (int e = tid; e < total; e += blockDim.x) { const float v = tmp[e]; if (v > bs) { bs = v; be = e; } }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int oe = __shfl_xor_sync(0xffffffffu, be, o);
+        if (os > bs || (os == bs && oe < be)) { bs = os; be = oe; }
+      }
+      if (lane == 0) { s_wv[warp] = bs; s_we[warp] = be; }
+      __syncthreads();
+      float gs = s_wv[0];
+      int ge = s_we[0];
+#pragma unroll
+      for (int w2 = 1; w2 < 4; ++w2) { const float os = s_wv[w2]; const int oe = s_we[w2]; if (os > gs || (os == gs && oe < ge)) { gs = os; ge = oe; } }
+      if (tid == 0) { s_kth = gs; if (ge < total) tmp[ge] = -CUDART_INF_F; }
+      __syncthreads();
     }
-    s_m = m;
+    // survivors: approx >= A_k - margin (order is irrelevant: the exact scores decide)
+    const float cut = s_kth - P.margin[g * rows_per_group + lrow];
+    for (int e = tid; e < total; e += blockDim.x)
+      if (cs[e] >= cut) { const int pos = atomicAdd(&s_m, 1); if (pos < FIN_MAXR) sv[pos] = ci[e]; }
+  } else {
+    for (int e = tid; e < total; e += blockDim.x) { const int pos = atomicAdd(&s_m, 1); if (pos < FIN_MAXR) sv[pos] = ci[e]; }
   }
   __syncthreads();
-  int m = s_m;
+  const int m = s_m;
   if (m > FIN_MAXR) {
-    if (tid == 0) P.overflow[row] = 1;
+    if (tid == 0) { P.overflow[row] = 1; P.ov_list[atomicAdd(P.ov_count, 1)] = row; }
     return;
   }
   // ---- exact fp32 re-score of the m survivors: 8 lanes per candidate, 16 candidates per pass (m is ~k + a few: one pass)
@@ -1067,12 +1138,12 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
       const int c = c0 + grp;
       float acc = 0.f;
       if (c < m) {
-        const float* tr = P.index + (size_t)(ci[c] - P.global_offset) * P.E;
+        const float* tr = P.index + (size_t)(sv[c] - P.global_offset) * P.E;
         if ((P.E & 3) == 0) {
           for (int j = sub * 4; j < P.E; j += 32) {
-            const float4 a = *reinterpret_cast<const float4*>(qr + j);
-            const float4 b = *reinterpret_cast<const float4*>(tr + j);
-            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+            const float4 a4 = *reinterpret_cast<const float4*>(qr + j);
+            const float4 b4 = *reinterpret_cast<const float4*>(tr + j);
+            acc = fmaf(a4.x, b4.x, acc); acc = fmaf(a4.y, b4.y, acc); acc = fmaf(a4.z, b4.z, acc); acc = fmaf(a4.w, b4.w, acc);
           }
         } else {                    // odd encoding sizes (the reference recipes use E = 50): rows are not 16-byte aligned
           for (int j = sub; j < P.E; j += 8) acc = fmaf(qr[j], tr[j], acc);
@@ -1081,26 +1152,34 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (c < m && sub == 0) cs[c] = acc;
+      if (c < m && sub == 0) tmp[c] = acc;
     }
   }
   __syncthreads();
-  int m2 = 1;
-  while (m2 < m) m2 <<= 1;
-  for (int x = m + tid; x < m2; x += blockDim.x) { cs[x] = -CUDART_INF_F; ci[x] = 0x7fffffff; }
-  bitonic_sort_pairs(cs, ci, m2);
-  for (int x = tid; x < k; x += blockDim.x) {
-    bool ok = x < m;
-    P.out_s[(size_t)row * P.out_stride + x] = ok ? cs[x] : -CUDART_INF_F;
-    P.out_i[(size_t)row * P.out_stride + x] = ok ? ci[x] : -1;
+  // ---- final order (exact score desc, id asc) by rank counting among the m survivors; rank r < k goes to output slot r
+  for (int c = tid; c < m; c += blockDim.x) {
+    const float sc = tmp[c];
+    const int32_t ic = sv[c];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) rank += pair_before(tmp[j], sv[j], sc, ic) ? 1 : 0;
+    if (rank < k) {
+      P.out_s[(size_t)row * P.out_stride + rank] = sc;
+      P.out_i[(size_t)row * P.out_stride + rank] = ic;
+    }
+  }
+  for (int x = m + tid; x < k; x += blockDim.x) {
+    P.out_s[(size_t)row * P.out_stride + x] = -CUDART_INF_F;
+    P.out_i[(size_t)row * P.out_stride + x] = -1;
   }
 }
 
 // rows flagged by finalize: brute-force exact fp32 top-k (rare: pathological ties / clustered index)
 __global__ void __launch_bounds__(256) fallback_kernel(const __grid_constant__ FinParams P) {
   extern __shared__ float dyn[];   // per warp k scores + k idx
-  const int row = blockIdx.x;
-  if (!P.overflow[row]) return;
+  const int n_over = *P.ov_count;  // a fixed small grid walks the (usually empty) list: no per-row block launch
+  for (int oi = blockIdx.x; oi < n_over; oi += gridDim.x) {
+  const int row = P.ov_list[oi];
+  __syncthreads();
   const int k = P.k, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float* ls = dyn + (size_t)warp * k * 2;
   int32_t* li = reinterpret_cast<int32_t*>(ls + k);
@@ -1150,6 +1229,7 @@ __global__ void __launch_bounds__(256) fallback_kernel(const __grid_constant__ F
       P.out_i[(size_t)row * P.out_stride + x] = reinterpret_cast<int32_t*>(dyn + (size_t)bw * k * 2 + k)[head[bw]];
       ++head[bw];
     }
+  }
   }
 }
 
@@ -1355,7 +1435,10 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   // Programmatic dependent launch between the kernels of one search (SSE_SCAN_PDL=1): the filter scan's CTAs are
   // scheduled as soon as the sample pass's CTAs leave their SMs and overlap their whole set-up with select_tau.
   static const bool env_pdl = env_int("SSE_SCAN_PDL", 0) != 0;
-  const bool fused = env_fused && k <= FUSED_MAX_K && cs == 1 && ti.group_ctr != nullptr;
+  // spanning items (see ScanParams): whenever the groups are packed equally and the CTA budget is not a multiple of the group count
+  static const int env_span = env_int("SSE_SCAN_SPAN", -1);
+  bool span = cs == 1 && !pack_full && n_groups > 1 && late_ctas == 0 && (env_span >= 0 ? env_span != 0 : true);
+  const bool fused = env_fused && k <= FUSED_MAX_K && cs == 1 && ti.group_ctr != nullptr && !span;
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_tilemax, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1427,8 +1510,34 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
     R = sp.group_items[0];
   }
   if (cs > 1) sp.n_early = items;
+  int total_slots = items;
+  int span_first[MAX_GROUPS], span_n[MAX_GROUPS];
+  if (span) {
+    // one flat list of n_groups * n_tiles units cut into `items` equal pieces (same cut for the sample pass with n_s units per group)
+    items = std::max(n_groups, std::min(budget, (int)std::min<int64_t>((int64_t)n_groups * n_s, 1 << 20)));
+    sp.span = 1;
+    sp.n_early = items;
+    for (int g = 0; g < n_groups; ++g) sp.group_mt[g] = sp.group_mt[0];
+    // candidate slots of the FILTER pass: one per (item, segment), numbered in item order
+    const int64_t U = (int64_t)n_groups * n_tiles;
+    int slot = 0;
+    for (int g = 0; g < n_groups; ++g) { span_first[g] = -1; span_n[g] = 0; }
+    for (int i = 0; i < items; ++i) {
+      const int64_t u0 = U * i / items, u1 = U * (i + 1) / items;
+      const int ga = (int)(u0 / n_tiles);
+      if (span_first[ga] < 0) span_first[ga] = slot;
+      ++span_n[ga]; ++slot;
+      if (u1 > (int64_t)(ga + 1) * n_tiles) {
+        const int gb = ga + 1;
+        if (span_first[gb] < 0) span_first[gb] = slot;
+        ++span_n[gb]; ++slot;
+      }
+    }
+    total_slots = slot;
+  }
   sp.cs = cs; sp.R = R;
   lcfg.gridDim = dim3(items, 1, 1);
+  const int list_items = span ? total_slots : items;      // candidate lists to allocate / walk
 
   // workspace carve
   size_t off = 0;
@@ -1438,10 +1547,12 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   size_t o_tau = carve((size_t)Qp * 4);
   size_t o_mg = carve((size_t)Qp * 4);
   size_t o_tm = carve((size_t)n_s * Qp * 4);
-  size_t o_cs = carve((size_t)items * mtg * TILE_M * CAND_CAP * 4);
-  size_t o_ci = carve((size_t)items * mtg * TILE_M * CAND_CAP * 4);
-  size_t o_cc = carve((size_t)items * mtg * TILE_M * 4);
+  size_t o_cs = carve((size_t)list_items * mtg * TILE_M * CAND_CAP * 4);
+  size_t o_ci = carve((size_t)list_items * mtg * TILE_M * CAND_CAP * 4);
+  size_t o_cc = carve((size_t)list_items * mtg * TILE_M * 4);
   size_t o_ov = carve((size_t)Qp * 4);
+  size_t o_ovl = carve((size_t)Qp * 4);
+  size_t o_ovc = carve(16);
   const bool want_dbg = getenv("SSE_SCAN_DEBUG") != nullptr;
   size_t o_dbg = carve(want_dbg ? (size_t)items * DBG_N * 8 : 8);
   SSE_TRY(ws.ensure(off));
@@ -1470,7 +1581,7 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
     SSE_CUDA_OK(cudaLaunchKernelEx(&lcfg, fn_fused, tmi, sp));
     if (launches) ++*launches;
   } else {
-    prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E_true, E, gstride, rpg, qb, qn);
+    prep_queries_kernel<<<cdiv(Qp, 8), 256, 0, st>>>(q, Q, Qp, E_true, E, gstride, rpg, qb, qn, reinterpret_cast<int32_t*>(w + o_ovc));
     if (launches) ++*launches;
     cudaLaunchAttribute pattr[2];
     int n_scan_attrs = lcfg.numAttrs;
@@ -1515,12 +1626,14 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   for (int g = 0; g < n_groups; ++g) {
     fp.group_first_item[g] = sp.group_first_item[g]; fp.group_items[g] = sp.group_items[g];
     fp.group_first_late[g] = sp.group_first_late[g]; fp.group_late[g] = sp.group_late[g];
+    if (span) { fp.span_first[g] = span_first[g]; fp.span_n[g] = span_n[g]; }
   }
+  fp.span = span ? 1 : 0;
   fp.cand_s = sp.cand_s; fp.cand_i = sp.cand_i; fp.cand_cnt = sp.cand_cnt; fp.margin = mg;
   fp.q = q; fp.index = index_f32; fp.global_offset = global_offset; fp.N = N; fp.Q = Q; fp.E = E_true; fp.k = k;
-  fp.out_s = out_scores; fp.out_i = out_idx; fp.out_stride = out_stride; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov);
+  fp.out_s = out_scores; fp.out_i = out_idx; fp.out_stride = out_stride; fp.overflow = reinterpret_cast<int32_t*>(w + o_ov); fp.ov_list = reinterpret_cast<int32_t*>(w + o_ovl); fp.ov_count = reinterpret_cast<int32_t*>(w + o_ovc);
   fp.group_ctr = fused ? ti.group_ctr : nullptr;
-  ti.last_cnt = sp.cand_cnt; ti.last_cnt_n = (int64_t)items * mtg * TILE_M; ti.last_overflow = fp.overflow; ti.last_Q = Q; ti.last_items = items;
+  ti.last_cnt = sp.cand_cnt; ti.last_cnt_n = (int64_t)list_items * mtg * TILE_M; ti.last_overflow = fp.overflow; ti.last_Q = Q; ti.last_items = items;
   if (want_dbg) {
     std::vector<long long> hd((size_t)items * DBG_N);
     cudaStreamSynchronize(st);
@@ -1535,9 +1648,14 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
     }
   }
   fp.maxc = k <= 32 ? FIN_MAXC_SMALL : FIN_MAXC_LARGE;
-  finalize_kernel<<<Q, 128, (size_t)fp.maxc * 8, st>>>(fp);
+  {
+    static bool fin_attr = false;
+    if (!fin_attr) { SSE_CUDA_OK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIN_MAXC_LARGE * 12 + FIN_MAXR * 4)); fin_attr = true; }
+  }
+  finalize_kernel<<<Q, 128, (size_t)fp.maxc * 12 + FIN_MAXR * 4, st>>>(fp);
   if (launches) ++*launches;
-  fallback_kernel<<<Q, 256, (size_t)8 * k * 8, st>>>(fp);
+  if (fused) SSE_CUDA_OK(cudaMemsetAsync(fp.ov_count, 0, 4, st));      // (the 3-kernel form zeroes it in prep_queries)
+  fallback_kernel<<<std::min(Q, 128), 256, (size_t)8 * k * 8, st>>>(fp);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
   return SSE_OK;
