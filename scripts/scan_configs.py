@@ -13,6 +13,12 @@ CONFIGS = [
     ("fused pack0", {"SSE_SCAN_FUSED": "1", "SSE_SCAN_PACK": "0"}),
     ("tn64", {"SSE_SCAN_ACC1": "0"}),
     ("cluster", {"SSE_SCAN_CLUSTER": "1"}),
+    ("cost100", {"SSE_SCAN_COST": "100,1100"}),
+    ("cost500", {"SSE_SCAN_COST": "500,1000"}),
+    ("cost780", {"SSE_SCAN_COST": "780,1000"}),
+    ("cost1000", {"SSE_SCAN_COST": "1000,1000"}),
+    ("cost1300", {"SSE_SCAN_COST": "1300,1000"}),
+    ("cost780pdl", {"SSE_SCAN_COST": "780,1000", "SSE_SCAN_PDL": "1"}),
 ]
 only = os.environ.get("SCAN_CONFIGS")
 for name, env in CONFIGS:

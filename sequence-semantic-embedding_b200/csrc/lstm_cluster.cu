@@ -533,12 +533,13 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_c
 // shared memory (H=256): h ping 64 KB | h pong 64 KB | Wh slice 64 KB.  TMEM: one [128 x 128] fp32 accumulator.
 // warps: 0-7 epilogue (warp w: lane quarter w%4, unit half w/4) | 8 MMA issuer + TMEM alloc + weight load | 9 slice exchange
 constexpr int P2_ROWS = 128;
-constexpr int P2_THREADS = 320;
 constexpr int P2_SUB_BYTES = P2_ROWS * 32;      // one sub-slice: [128 rows x 16 units] fp16, SWIZZLE_32B K-major
+constexpr int P2_TRACE_STEPS = 48;              // debug: per-step timestamps of CTA 0
+constexpr int P2_DEFAULT_EW = 16, P2_DEFAULT_GATE = 1;
 
 struct LstmP2Params {
   const int32_t* tokens;      // [B, T]
-  const float* ptable;        // [V, 4H] fp32, chunk-major, scaled, bias folded in
+  const float* ptable;        // [V, 4H] fp32, scaled, bias folded in; column order: see ptab_col()
   const float* init_h;
   const float* init_c;
   const int32_t* lead_sorted; // optional [B]: leading PADs of each (sorted) row -> per-tile start step (tok_prep.cu)
@@ -548,13 +549,44 @@ struct LstmP2Params {
   float* dump_c;              // run on one all-PAD row this IS the pad-prefix table of this kernel's own arithmetic
   float* h_out;               // [B, H]
   int B, T, t_start, H;
-  int gate_math;              // 0: ex2/rcp form (8 MUFU per unit); 1: tanh.approx form (5 MUFU per unit) -- same accuracy on the
-                              // encodings (4.5e-5 vs the fp32 oracle) but measured 15% SLOWER per step, kept as an experiment knob
-  long long* dbg;
+  int poll_ns;                // back-off of the MMA / exchange warps' barrier polls (0 = none)
+  long long* dbg;             // optional [grid][16] cycle counters, then [P2_TRACE_STEPS][8] timestamps of CTA 0
 };
 
-__global__ void __launch_bounds__(P2_THREADS, 1)
+// Column order of the table (and of W_x / the bias it is built from).  The epilogue thread (row r, unit group `sub`) of
+// pass p needs, for its UPP = 16 / NSUB units, all four gate values: they sit in ONE contiguous run of 4 * UPP floats
+//   col(c, p, sub, g, i) = c * 128 + p * 64 + sub * 4 * UPP + g * UPP + i        (unit = 32 c + 16 p + UPP sub + i)
+// so a pass is one 128-byte (8 epilogue warps) or 64-byte (16 warps) gather per thread instead of four 32-byte pieces of
+// four different lines (the L1 data pipe was ~40 % busy with the chunk-major order).
+__host__ __device__ __forceinline__ int ptab_col(int c, int g, int j, int upp) {
+  const int p = j >> 4, w = j & 15;
+  return c * 128 + p * 64 + (w / upp) * 4 * upp + g * upp + (w % upp);
+}
+
+#define TMEM_LD_4(taddr, v)                                                                       \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"                       \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])                                    \
+               : "r"(taddr))
+
+__device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+// EW: epilogue warps (8: thread == batch row x 16 units, 16: x 8 units -- four warps per SM sub-partition keep the MUFU
+// pipe fed).  GATE: 0 = ex2 / rcp form (8 MUFU per unit), 1 = tanh.approx form (sigmoid(z) = 0.5 tanh(z/2) + 0.5: 5 MUFU),
+// 2 = form 1 with tanh(o/2) and tanh(c) of a unit computed by ONE tanh.approx.f16x2 (4 MUFU; their product h is rounded
+// to fp16 for the recurrence anyway).
+// warps: 0..EW-1 epilogue (warp w: TMEM lane quarter w % 4, unit group w / 4) | EW: MMA issuer + TMEM alloc + weight
+// load | EW+1: slice exchange
+template <int EW, int GATE>
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
 lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_constant__ LstmP2Params P, int kb_first) {
+  constexpr int NSUB = EW / 4;          // unit groups per pass
+  constexpr int UPP = 16 / NSUB;        // units per thread and pass
+  constexpr int UPT = 2 * UPP;          // units per thread
+  constexpr int W_MMA = EW, W_XCH = EW + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -574,6 +606,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   }
   const bool has_init = init_h != nullptr;
   const int nsteps = P.T - t0;
+  long long* trace = (P.dbg && blockIdx.x == 0) ? P.dbg + (size_t)gridDim.x * 16 : nullptr;
 
   // h tile = 2*CL sub-slices of 16 hidden units: sub-slice m = units [16 m, 16 m + 16) = CTA m/2's pass m%2,
   // [128 rows x 32 B] fp16, SWIZZLE_32B K-major -- exactly the A operand of k-step m.
@@ -583,17 +616,17 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   const uint32_t bar_wf = smem_u32(bars + 0);
   const uint32_t bar_accf = smem_u32(bars + 1);    // [2 accumulators]
   const uint32_t bar_hr = smem_u32(bars + 3);      // [2 tiles][2 passes]: all CL sub-slices of that pass have landed
-  const uint32_t bar_sl = smem_u32(bars + 7);      // [2 tiles][2 passes]: own sub-slice written by the 8 epilogue warps
+  const uint32_t bar_sl = smem_u32(bars + 7);      // [2 tiles][2 passes]: own sub-slice written by the EW epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_wf, 1);
     for (int b = 0; b < 2; ++b) mbar_init(bar_accf + 8 * b, 1);
-    for (int b = 0; b < 4; ++b) { mbar_init(bar_hr + 8 * b, 2); mbar_init(bar_sl + 8 * b, 8); }
+    for (int b = 0; b < 4; ++b) { mbar_init(bar_hr + 8 * b, 2); mbar_init(bar_sl + 8 * b, EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -603,7 +636,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   cluster_sync_all();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == W_MMA) {
     // ===== W_h slice load (once) + MMA issuer =====
     if (elect_one_sync()) {
       mbar_expect_tx(bar_wf, (uint32_t)KBh * W_TILE_BYTES);
@@ -628,8 +661,9 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
           else mbar_expect_tx(bar, (uint32_t)(CL - 1) * P2_SUB_BYTES);
         }
         __syncwarp();
-        mbar_wait_timed<false>(bar, n & 1, w_hr);
+        mbar_wait_timed<false>(bar, n & 1, w_hr, (uint32_t)P.poll_ns);
         tc_fence_after();
+        if (trace && lane == 0 && s < P2_TRACE_STEPS) trace[s * 8 + 4 + p] = clock64();
         if (elect_one_sync()) {
           for (int q = 0; q < CL; ++q) {
             const int m = 2 * q + p;
@@ -642,7 +676,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
       }
     }
     if (P.dbg && lane == 0) { P.dbg[blockIdx.x * 16 + 0] = w_hr; P.dbg[blockIdx.x * 16 + 3] = clock64() - t_begin; }
-  } else if (warp == 9) {
+  } else if (warp == W_XCH) {
     // ===== sub-slice exchange =====
     const uint32_t peer_h = map_to_cta(smem_u32(h_smem), (uint32_t)(lane < CL ? lane : 0));
     const uint32_t peer_bar = map_to_cta(bar_hr, (uint32_t)(lane < CL ? lane : 0));
@@ -656,18 +690,19 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
       const int tb = s & 1;
       const uint32_t n = (uint32_t)((s >> 1) + ((tb == 1 && has_init) ? 1 : 0));
       for (int p = 0; p < 2; ++p) {
-        mbar_wait<false>(bar_sl + 8 * (tb * 2 + p), n & 1);
+        mbar_wait<false>(bar_sl + 8 * (tb * 2 + p), n & 1, (uint32_t)P.poll_ns);
         const uint32_t off = (uint32_t)((tb * 2 * CL + 2 * (int)rank + p) * P2_SUB_BYTES);
         if (lane < CL && lane != (int)rank) bulk_copy_to_peer(peer_h + off, smem_u32(h_smem) + off, P2_SUB_BYTES, peer_bar + 8 * (tb * 2 + p));
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_hr + 8 * (tb * 2 + p));
+        if (trace && lane == 0 && s < P2_TRACE_STEPS) trace[s * 8 + 6 + p] = clock64();
       }
     }
   } else {
-    // ===== epilogue: thread == (batch row, 16 of this CTA's 32 hidden units), c in registers.
-    //       pass p of unit-half `half` covers units 16 p + 8 half + [0, 8) of the slice, so that the two halves of
+    // ===== epilogue: thread == (batch row, UPT of this CTA's 32 hidden units), c in registers.
+    //       pass p of unit group `sub` covers units 16 p + UPP sub + [0, UPP) of the slice, so that the NSUB groups of
     //       pass p together complete sub-slice 2 rank + p, which leaves for the peers while pass 1 is still computing
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, sub = warp >> 2;
     const int r = quarter * 32 + lane;
     const int grow = row0 + r;
     const bool valid = grow < P.B;
@@ -675,13 +710,13 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t row_off32 = (uint32_t)(r * 32);
     const uint32_t sw32 = (uint32_t)((r >> 2) & 1);            // SWIZZLE_32B: 16-byte chunk c of row r sits at c ^ ((r >> 2) & 1)
-    float c[16];
+    float c[UPT];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) c[u] = has_init ? __ldg(init_c + rank * 32 + (u >> 3) * 16 + half * 8 + (u & 7)) : 0.f;
+    for (int u = 0; u < UPT; ++u) c[u] = has_init ? __ldg(init_c + rank * 32 + (u / UPP) * 16 + sub * UPP + (u % UPP)) : 0.f;
     if (has_init) {
       // the broadcast initial state is the same for every row: each CTA fills its own tile 1 (= "step -1"), all sub-slices
       const uint32_t t1 = smem_u32(h_smem) + (uint32_t)(2 * CL * P2_SUB_BYTES) + row_off32;
-      for (int m = half; m < 2 * CL; m += 2)
+      for (int m = sub; m < 2 * CL; m += NSUB)
         for (int j = 0; j < 2; ++j) {
           uint32_t pk[4];
 #pragma unroll
@@ -693,21 +728,25 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar_sl + 8 * 2); mbar_arrive(bar_sl + 8 * 3); }
     }
-    const uint32_t own_sub = smem_u32(h_smem) + (2 * rank) * P2_SUB_BYTES + row_off32 + (((uint32_t)half ^ sw32) * 16);
-    const size_t pcol = (size_t)rank * 128 + half * 8;
+    // byte offset of this thread's UPP units inside the 32-byte row of a sub-slice (16-byte chunks are XOR-swizzled)
+    const uint32_t ubyte = (uint32_t)(sub * UPP * 2);
+    const uint32_t own_sub = smem_u32(h_smem) + (2 * rank) * P2_SUB_BYTES + row_off32 + (((ubyte >> 4) ^ sw32) * 16) + (ubyte & 15);
+    const size_t pcol = (size_t)rank * 128 + sub * 4 * UPP;
     constexpr float NL2E = -1.4426950408889634f;
     long long w_accf = 0, w_math = 0, tq = 0, t_begin = clock64();
     const bool dbgt = P.dbg != nullptr;
-    // table row of step s: pg[g][p * 8 + i] = P[token][gate g, unit 16 p + 8 half + i].  Each half of the NEXT step's
-    // row is fetched right after the corresponding pass of this step has been published: it lands in registers that
-    // just died, and no global load is in flight when the next publish executes its memory barrier
+    // table values of step s: pg[p][g * UPP + i] = P[token][gate g, unit 16 p + UPP sub + i].  Each pass's run of the NEXT
+    // step's row is fetched right after the corresponding pass of this step has been published: it lands in registers
+    // that just died, and no global load is in flight when the next publish executes its memory barrier
     // (fence.proxy.async lowers to MEMBAR.ALL.CTA, which would otherwise wait out the L2 latency on the critical path).
-    float pg[4][16];
+    float pg[2][4 * UPP];
     int tok_next = nsteps > 1 ? __ldg(trow + 1) : 0;
     {
       const float* prow = P.ptable + (size_t)__ldg(trow) * 4 * P.H + pcol;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) { ldg_v8(prow + g * 32, pg[g]); ldg_v8(prow + g * 32 + 16, pg[g] + 8); }
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int x = 0; x < 4 * UPP; x += 8) ldg_v8(prow + p * 64 + x, pg[p] + x);
     }
     for (int s = 0; s < nsteps; ++s) {
       const bool last = s == nsteps - 1;
@@ -717,68 +756,85 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
         tc_fence_after();
       }
       if (dbgt) tq = clock64();
+      if (trace && warp == 0 && lane == 0 && s < P2_TRACE_STEPS) trace[s * 8 + 0] = tq;
       const uint32_t tile_sub = own_sub + (uint32_t)((s & 1) * 2 * CL * P2_SUB_BYTES);
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
-        uint32_t vi[8], vj[8], vf[8], vo[8];
+        uint32_t v[4][UPP];
         if (has_state) {
-          const uint32_t acc = lane_base + (uint32_t)((s & 1) * 128 + p * 16 + half * 8);
-          TMEM_LD_8(acc, vi);
-          TMEM_LD_8(acc + 32, vj);
-          TMEM_LD_8(acc + 64, vf);
-          TMEM_LD_8(acc + 96, vo);
+          const uint32_t acc = lane_base + (uint32_t)((s & 1) * 128 + p * 16 + sub * UPP);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (UPP == 8) { TMEM_LD_8(acc + 32 * g, v[g]); }
+            else { TMEM_LD_4(acc + 32 * g, v[g]); }
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) vi[i] = vj[i] = vf[i] = vo[i] = 0u;
-        }
-        float hv[8];
+          for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int u = p * 8 + i;
-          const float bi = pg[0][u], bj = pg[1][u], bf = pg[2][u], bo = pg[3][u];
-          if (P.gate_math == 1) {
+            for (int i = 0; i < UPP; ++i) v[g][i] = 0u;
+        }
+        float hv[UPP];
+#pragma unroll
+        for (int i = 0; i < UPP; ++i) {
+          const int u = p * UPP + i;
+          const float bi = pg[p][i], bj = pg[p][UPP + i], bf = pg[p][2 * UPP + i], bo = pg[p][3 * UPP + i];
+          const float ai = __uint_as_float(v[0][i]), aj = __uint_as_float(v[1][i]), af = __uint_as_float(v[2][i]), ao = __uint_as_float(v[3][i]);
+          if (GATE == 0) {
+            const float ei = ex2_approx(fminf(fmaf(ai, NL2E, bi), 57.f));
+            const float ej = ex2_approx(fminf(fmaf(aj, 2.f * NL2E, bj), 57.f));
+            const float ef = ex2_approx(fminf(fmaf(af, NL2E, bf), 57.f));
+            const float eo = ex2_approx(fminf(fmaf(ao, NL2E, bo), 57.f));
+            const float pj = (1.f - ej) * rcp_approx((1.f + ei) * (1.f + ej));
+            c[u] = fmaf(c[u], rcp_approx(1.f + ef), pj);
+            const float ec = ex2_approx(fminf(c[u] * (2.f * NL2E), 57.f));
+            hv[i] = (1.f - ec) * rcp_approx((1.f + ec) * (1.f + eo));
+          } else {
             // table scaled by 1/2 (1 for the candidate gate): sigmoid(z) = 0.5 tanh(z / 2) + 0.5
-            const float ti = tanh_approx(fmaf(__uint_as_float(vi[i]), 0.5f, bi));
-            const float tj = tanh_approx(__uint_as_float(vj[i]) + bj);
-            const float tf = tanh_approx(fmaf(__uint_as_float(vf[i]), 0.5f, bf));
-            const float to = tanh_approx(fmaf(__uint_as_float(vo[i]), 0.5f, bo));
+            const float ti = tanh_approx(fmaf(ai, 0.5f, bi));
+            const float tj = tanh_approx(aj + bj);
+            const float tf = tanh_approx(fmaf(af, 0.5f, bf));
             c[u] = fmaf(c[u], fmaf(0.5f, tf, 0.5f), fmaf(0.5f, ti, 0.5f) * tj);
-            hv[i] = fmaf(0.5f, to, 0.5f) * tanh_approx(c[u]);
-            continue;
+            if (GATE == 1) {
+              const float to = tanh_approx(fmaf(ao, 0.5f, bo));
+              hv[i] = fmaf(0.5f, to, 0.5f) * tanh_approx(c[u]);
+            } else {
+              const uint32_t t2 = tanh_f16x2(pack_f16x2(fmaf(ao, 0.5f, bo), c[u]));       // low half: o gate, high half: cell
+              const float2 tt = __half22float2(*reinterpret_cast<const __half2*>(&t2));
+              hv[i] = fmaf(0.5f, tt.x, 0.5f) * tt.y;
+            }
           }
-          const float ei = ex2_approx(fminf(fmaf(__uint_as_float(vi[i]), NL2E, bi), 57.f));
-          const float ej = ex2_approx(fminf(fmaf(__uint_as_float(vj[i]), 2.f * NL2E, bj), 57.f));
-          const float ef = ex2_approx(fminf(fmaf(__uint_as_float(vf[i]), NL2E, bf), 57.f));
-          const float eo = ex2_approx(fminf(fmaf(__uint_as_float(vo[i]), NL2E, bo), 57.f));
-          const float pj = (1.f - ej) * rcp_approx((1.f + ei) * (1.f + ej));
-          c[u] = fmaf(c[u], rcp_approx(1.f + ef), pj);
-          const float ec = ex2_approx(fminf(c[u] * (2.f * NL2E), 57.f));
-          hv[i] = (1.f - ec) * rcp_approx((1.f + ec) * (1.f + eo));
         }
         if (P.dump_h && grow == 0) {        // pad-prefix table generation: the state this kernel itself carries past step t0 + s
-          float* dh = P.dump_h + (size_t)(t0 + s) * P.H + rank * 32 + p * 16 + half * 8;
-          float* dc = P.dump_c + (size_t)(t0 + s) * P.H + rank * 32 + p * 16 + half * 8;
+          float* dh = P.dump_h + (size_t)(t0 + s) * P.H + rank * 32 + p * 16 + sub * UPP;
+          float* dc = P.dump_c + (size_t)(t0 + s) * P.H + rank * 32 + p * 16 + sub * UPP;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { dh[i] = __half2float(__float2half_rn(hv[i])); dc[i] = c[p * 8 + i]; }
+          for (int i = 0; i < UPP; ++i) { dh[i] = __half2float(__float2half_rn(hv[i])); dc[i] = c[p * UPP + i]; }
         }
         if (!last) {
-          const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]), p2 = pack_f16x2(hv[4], hv[5]), p3 = pack_f16x2(hv[6], hv[7]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_sub + (uint32_t)(p * P2_SUB_BYTES)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
-          // this pass's half sub-slice is in place (and, for p == 1, the accumulator fully read): publish it
+          if (UPP == 8) {
+            const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]), p2 = pack_f16x2(hv[4 % UPP], hv[5 % UPP]), p3 = pack_f16x2(hv[6 % UPP], hv[7 % UPP]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_sub + (uint32_t)(p * P2_SUB_BYTES)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+          } else {
+            const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]);
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile_sub + (uint32_t)(p * P2_SUB_BYTES)), "r"(p0), "r"(p1) : "memory");
+          }
+          // this pass's part of the sub-slice is in place (and, for p == 1, the accumulator fully read): publish it
           if (p == 1) tc_fence_before();
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_sl + 8 * ((s & 1) * 2 + p));
+          if (trace && warp == 0 && lane == 0 && s < P2_TRACE_STEPS) trace[s * 8 + 1 + p] = clock64();
           {
-            const float* prow = P.ptable + (size_t)tok_next * 4 * P.H + pcol + p * 16;
+            const float* prow = P.ptable + (size_t)tok_next * 4 * P.H + pcol + p * 64;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) ldg_v8(prow + g * 32, pg[g] + p * 8);
+            for (int x = 0; x < 4 * UPP; x += 8) ldg_v8(prow + x, pg[p] + x);
           }
         } else if (valid) {
-          float* ho = P.h_out + (size_t)grow * P.H + rank * 32 + p * 16 + half * 8;
-          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+          float* ho = P.h_out + (size_t)grow * P.H + rank * 32 + p * 16 + sub * UPP;
+#pragma unroll
+          for (int i = 0; i < UPP; i += 4) *reinterpret_cast<float4*>(ho + i) = make_float4(hv[i], hv[i + 1], hv[i + 2], hv[i + 3]);
         }
       }
       if (s + 2 < nsteps) tok_next = __ldg(trow + s + 2);
@@ -792,30 +848,31 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 8) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
   }
 }
 
-// Wxp[k][n'] = scale_g * K[k][g*H + 32c + j]   (n' = c*128 + g*32 + j), k < We
-__global__ void ptable_wx_kernel(const float* __restrict__ K, int We, int H, int gate_math, float* __restrict__ Wxp) {
+// Wxp[k][col] = scale_g * K[k][g*H + 32c + j], col = ptab_col(c, g, j, upp)  (the table's column order), k < We
+__global__ void ptable_wx_kernel(const float* __restrict__ K, int We, int H, int tanh_form, int upp, float* __restrict__ Wxp) {
   const int64_t total = (int64_t)We * 4 * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i / (4 * H)), np = (int)(i - (int64_t)k * 4 * H);
     const int c = np >> 7, g = (np >> 5) & 3, j = np & 31;
-    const float sc = gate_math == 1 ? (g == 1 ? 1.f : 0.5f) : (g == 1 ? -2.885390081777927f : -1.4426950408889634f);
-    Wxp[i] = sc * K[(size_t)k * 4 * H + g * H + c * 32 + j];
+    const float sc = tanh_form ? (g == 1 ? 1.f : 0.5f) : (g == 1 ? -2.885390081777927f : -1.4426950408889634f);
+    Wxp[(size_t)k * 4 * H + ptab_col(c, g, j, upp)] = sc * K[(size_t)k * 4 * H + g * H + c * 32 + j];
   }
 }
-// P[v][n'] = bias_r[n']  (the GEMM then accumulates the projection on top)
-__global__ void ptable_bias_kernel(const float* __restrict__ bias_r, int64_t V, int H4, int gate_math, float* __restrict__ Pt) {
+// P[v][col] = bias_r[c*128 + g*32 + j]  (the GEMM then accumulates the projection on top)
+__global__ void ptable_bias_kernel(const float* __restrict__ bias_r, int64_t V, int H4, int tanh_form, int upp, float* __restrict__ Pt) {
   const int64_t total = V * H4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int np = (int)(i % H4);
+    const int c = np >> 7, g = (np >> 5) & 3, j = np & 31;
     float b = bias_r[np];                       // -log2e (-2 log2e for g == 1) x (b [+1 forget])
-    if (gate_math == 1) b *= -0.34657359027997264f;   // (-log2e)(b) -> b/2 for i,f,o and (-2 log2e)(b) -> b for j: the same factor -ln2/2
-    Pt[i] = b;
+    if (tanh_form) b *= -0.34657359027997264f;  // (-log2e)(b) -> b/2 for i,f,o and (-2 log2e)(b) -> b for j: the same factor -ln2/2
+    Pt[i - np + ptab_col(c, g, j, upp)] = b;
   }
 }
 
@@ -893,11 +950,16 @@ int lstm_ptable_prepare(TcTower& tt, const float* emb, int64_t V, const float* K
   if (!tt.ptable) { SSE_CUDA_OK(cudaMalloc(&tt.ptable, (size_t)V * 4 * H * 4)); tt.ptable_rows = V; }
   if (!tt.wxp) SSE_CUDA_OK(cudaMalloc(&tt.wxp, (size_t)We * 4 * H * 4));
   float* wxp = tt.wxp;
-  const int gate_math = getenv("SSE_LSTM_GATE_MATH") ? atoi(getenv("SSE_LSTM_GATE_MATH")) : 0;
+  // kernel variant (fixed per table: it sets the table's scaling and column order): SSE_LSTM_GATE_MATH 0 / 1 / 2,
+  // SSE_LSTM_EW 8 / 16 epilogue warps
+  const int gate_math = getenv("SSE_LSTM_GATE_MATH") ? std::max(0, std::min(2, atoi(getenv("SSE_LSTM_GATE_MATH")))) : P2_DEFAULT_GATE;
+  const int ew = getenv("SSE_LSTM_EW") ? (atoi(getenv("SSE_LSTM_EW")) == 8 ? 8 : 16) : P2_DEFAULT_EW;
   tt.ptable_mode = gate_math;
-  ptable_wx_kernel<<<148, 256, 0, st>>>(K, We, H, gate_math, wxp);
+  tt.ptable_ew = ew;
+  const int upp = 64 / ew;
+  ptable_wx_kernel<<<148, 256, 0, st>>>(K, We, H, gate_math != 0, upp, wxp);
   if (launches) ++*launches;
-  ptable_bias_kernel<<<148 * 8, 256, 0, st>>>(tt.bias_r, V, 4 * H, gate_math, tt.ptable);
+  ptable_bias_kernel<<<148 * 8, 256, 0, st>>>(tt.bias_r, V, 4 * H, gate_math != 0, upp, tt.ptable);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
   // rows in slabs that keep the GEMM's M within int range and friendly to the SIMT kernel
@@ -917,19 +979,25 @@ int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We
   p.tokens = tokens; p.ptable = tt.ptable; p.init_h = init_h; p.init_c = init_c; p.h_out = h_out;
   p.lead_sorted = ps.lead_sorted; p.pad_h = ps.pad_h; p.pad_c = ps.pad_c; p.dump_h = ps.dump_h; p.dump_c = ps.dump_c;
   p.B = B; p.T = T; p.t_start = t_start; p.H = H; p.dbg = nullptr;
-  p.gate_math = tt.ptable_mode;
+  static const int poll_ns = getenv("SSE_LSTM_POLL") ? atoi(getenv("SSE_LSTM_POLL")) : 32;
+  p.poll_ns = poll_ns;
+  typedef void (*p2_fn)(const CUtensorMap, const LstmP2Params, int);
+  const int ew = tt.ptable_ew;
+  p2_fn fn = ew == 8 ? (tt.ptable_mode == 0 ? lstm_ptable_kernel<8, 0> : tt.ptable_mode == 1 ? lstm_ptable_kernel<8, 1> : lstm_ptable_kernel<8, 2>)
+                     : (tt.ptable_mode == 0 ? lstm_ptable_kernel<16, 0> : tt.ptable_mode == 1 ? lstm_ptable_kernel<16, 1> : lstm_ptable_kernel<16, 2>);
   const int CL = H / 32, KBh = H / KBLK;
   const int n_clusters = cdiv(B, P2_ROWS);
   const int grid = n_clusters * CL;
   const size_t smem = 1024 + (size_t)2 * 2 * CL * P2_SUB_BYTES + (size_t)KBh * W_TILE_BYTES + 256;
   const bool want_dbg = getenv("SSE_LSTM_DEBUG") != nullptr;
   long long* d_dbg = nullptr;
-  if (want_dbg) { cudaMalloc(&d_dbg, (size_t)grid * 128); cudaMemset(d_dbg, 0, (size_t)grid * 128); p.dbg = d_dbg; }
-  SSE_CUDA_OK(cudaFuncSetAttribute(lstm_ptable_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t dbg_bytes = (size_t)grid * 128 + (size_t)P2_TRACE_STEPS * 64;
+  if (want_dbg) { cudaMalloc(&d_dbg, dbg_bytes); cudaMemset(d_dbg, 0, dbg_bytes); p.dbg = d_dbg; }
+  SSE_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(P2_THREADS, 1, 1);
+  cfg.blockDim = dim3((unsigned)(ew + 2) * 32, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -939,14 +1007,24 @@ int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SSE_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_ptable_kernel, *reinterpret_cast<const CUtensorMap*>(tt.tmap2d), p, We / KBLK));
+  SSE_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, *reinterpret_cast<const CUtensorMap*>(tt.tmap2d), p, We / KBLK));
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
   if (want_dbg) {
-    std::vector<long long> hd((size_t)grid * 16);
+    std::vector<long long> hd((size_t)grid * 16 + (size_t)P2_TRACE_STEPS * 8);
     cudaStreamSynchronize(st);
     cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
     cudaFree(d_dbg);
+    fprintf(stderr, "[lstm ptable dbg] variant: %d epilogue warps, gate math %d, poll back-off %d ns\n", ew, tt.ptable_mode, poll_ns);
+    {   // CTA 0's timeline of a few mid-sequence steps, relative to the step's accumulator-ready time
+      const long long* tr = hd.data() + (size_t)grid * 16;
+      for (int s = 20; s < std::min(24, T - t_start - 1); ++s) {
+        const long long a = tr[s * 8 + 0];
+        fprintf(stderr, "[lstm ptable trace] step %2d: acc ready +0 | pass0 published %+lld | pass1 published %+lld | own copies issued p0 %+lld p1 %+lld | "
+                        "NEXT step: h pass0 landed %+lld, pass1 landed %+lld, acc ready %+lld\n",
+                s, tr[s * 8 + 1] - a, tr[s * 8 + 2] - a, tr[s * 8 + 6] - a, tr[s * 8 + 7] - a, tr[(s + 1) * 8 + 4] - a, tr[(s + 1) * 8 + 5] - a, tr[(s + 1) * 8 + 0] - a);
+      }
+    }
     const char* nm[8] = {"mma_wait_hready", "-", "-", "mma_total", "epi_wait_accf", "epi_total", "-", "epi_ld+math+store"};
     for (int c = 0; c < 8; ++c) {
       if (nm[c][0] == '-') continue;

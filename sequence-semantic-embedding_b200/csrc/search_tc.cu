@@ -1486,7 +1486,10 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
     // CTAs of different groups that share a range run concurrently, so the index is fetched from HBM about once per
     // distinct item count and the other groups' reads of the same tiles hit L2.  A lighter last group (one live
     // m-tile) gets fewer items, in proportion to its per-tile cost (per m-tile MMA time + a small per-tile constant).
-    const double c_tile = acc1 ? 100.0 : 400.0, c_mt = acc1 ? 1100.0 : 550.0;
+    // measured per-tile cost (in-kernel counters, 600 x 1M, ACC1): an item with two live m-tiles 2687 cycles, with one 1719
+    // -- a single m-tile cannot amortise the 64 KB tile fill -- i.e. c_tile : c_mt = 0.78 : 1 (SSE_SCAN_COST="c_tile,c_mt")
+    double c_tile = acc1 ? 780.0 : 400.0, c_mt = acc1 ? 1000.0 : 550.0;
+    if (const char* ce = getenv("SSE_SCAN_COST")) { double a = 0, b = 0; if (sscanf(ce, "%lf,%lf", &a, &b) == 2 && a >= 0 && b > 0) { c_tile = a; c_mt = b; } }
     double cost_sum = 0;
     for (int g = 0; g < n_groups; ++g) cost_sum += c_tile + c_mt * sp.group_mt[g];
     int first = 0;
@@ -1645,6 +1648,18 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
       for (int i = 0; i < items; ++i) { long long v = hd[(size_t)i * DBG_N + c]; mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
       fprintf(stderr, "[scan dbg] %-16s min %10lld avg %10lld max %10lld  (items %d = %d sg x %d clusters x cs %d, mtg %d acc1 %d, tiles/cluster ~%d, tn %d, NS %d)\n",
               nm[c], mn, sm / items, mx, items, nsg, R, cs, mtg, (int)acc1, n_tiles / R, tn, NS);
+    }
+    if (cs == 1 && !span) {      // per m-group view: which group's items set the kernel's duration
+      for (int g = 0; g < n_groups; ++g) {
+        const int i0 = sp.group_first_item[g], n = sp.group_items[g];
+        long long tot = 0, tmx = 0, wf = 0, wa = 0, ec = 0;
+        for (int i = i0; i < i0 + n; ++i) {
+          const long long* d = &hd[(size_t)i * DBG_N];
+          tot += d[4]; tmx = std::max(tmx, d[4]); wf += d[2]; wa += d[3]; ec += d[9];
+        }
+        fprintf(stderr, "[scan dbg] group %2d: %3d items x ~%d tiles, m-tiles %d | mma_total avg %lld max %lld | wait_full avg %lld | wait_acce avg %lld | epi_compare avg %lld\n",
+                g, n, n_tiles / std::max(n, 1), sp.group_mt[g], tot / n, tmx, wf / n, wa / n, ec / n);
+      }
     }
   }
   fp.maxc = k <= 32 ? FIN_MAXC_SMALL : FIN_MAXC_LARGE;

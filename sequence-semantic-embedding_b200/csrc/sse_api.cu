@@ -291,6 +291,8 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens_in, int B, floa
     } else {
       SSE_TRY(lstm_forward_tc(tokens, B, T, 0, h->emb_f16, Wp, Hp, tt, nullptr, nullptr, ps, cs, hout, st, &h->launches));
     }
+    if (project_rows_supported(B, H, E))       // query batches: projection + l2-norm + un-permutation in one launch
+      return project_rows(hout, Hp, tw.M, H, E, B, tp.sorted ? tp.perm : nullptr, normalize, out, st, &h->launches);
     SSE_TRY(sgemm(false, false, B, E, H, 1.f, hout, Hp, tw.M, E, 0.f, proj, E, st, &h->launches));
     return finish();
   } else if (h->opt_encoder == 2) {

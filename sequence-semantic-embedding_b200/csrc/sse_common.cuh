@@ -172,6 +172,10 @@ int sanitize_tokens_inplace(int32_t* tokens, int64_t n, int V, int* bad_total, c
 int sample_train_batch(const int32_t* src_rows, const int64_t* ver_off, const int32_t* ver_rows, const int32_t* tgt_rows, int64_t N, int T, int64_t start,
                        int B, uint64_t seed, uint64_t step, int32_t* src_out, int32_t* tgt_out, float* lab_out, cudaStream_t st, int64_t* launches);
 int unpermute_rows(const float* x, float* y, const int32_t* perm, int rows, int cols, int normalize, cudaStream_t st, int64_t* launches);
+// out[perm ? perm[r] : r] = (l2-normalised) hmat[r] M  -- projection + normalisation + un-permutation of a query batch in one launch
+bool project_rows_supported(int rows, int H, int E);
+int project_rows(const float* hmat, int ldh, const float* M, int H, int E, int rows, const int32_t* perm, int normalize, float* out,
+                 cudaStream_t st, int64_t* launches);
 // per-tile pad-prefix start of the tensor-core LSTM kernels (all null = off)
 struct PadSkip {
   const int32_t* lead_sorted = nullptr;
@@ -195,6 +199,7 @@ struct TcTower {
   float* wxp = nullptr;            // [We, 4H] permuted + scaled W_x (GEMM operand of the table build)
   bool ptable_valid = false;
   int ptable_mode = 0;             // gate-math variant the table was scaled for
+  int ptable_ew = 16;              // epilogue warps of the kernel variant the table's column order was built for
 };
 bool lstm_tc_supported(int We, int H);
 int lstm_tc_prepare(TcTower& tt, const float* K, const float* b, int We, int H, cudaStream_t st, int64_t* launches);

@@ -238,6 +238,95 @@ __global__ void unpermute_rows_kernel(const float* __restrict__ x, float* __rest
   for (int j = lane; j < cols; j += 32) yr[j] = normalize ? xr[j] * inv : xr[j];
 }
 
+// Query-batch tail of an LSTM tower in ONE launch: u = h M (reference sse_model.py:228,245,254: the [H,E] projection), the
+// optional l2-normalisation (sse_model.py:282-283) and the un-permutation of pad-prefix-sorted rows.  Block = PR_ROWS rows
+// x all E columns (thread == column e, 8 row accumulators); M streams from L2 once per block, coalesced.  Replaces
+// sgemm + l2norm_rows / unpermute_rows (two launches, ~16 us with their gaps at 600 rows) for batches up to a few thousand rows.
+constexpr int PR_ROWS = 8, PR_THREADS = 256, PR_MAXNE = 4;
+__global__ void __launch_bounds__(PR_THREADS) project_rows_kernel(const float* __restrict__ hmat, int ldh, const float* __restrict__ M, int H, int E,
+                                                                  int rows, const int32_t* __restrict__ perm, int normalize, float* __restrict__ out) {
+  extern __shared__ float4 hs4[];          // [H][2] float4: the 8 rows' h values of hidden unit k, side by side
+  __shared__ float red[PR_THREADS / 32][PR_ROWS];
+  __shared__ float inv_s[PR_ROWS];
+  float* hs = reinterpret_cast<float*>(hs4);
+  const int r0 = blockIdx.x * PR_ROWS;
+  for (int i = threadIdx.x; i < H * PR_ROWS; i += PR_THREADS) {
+    const int r = i / H, k = i - r * H;                    // coalesced over k
+    hs[k * PR_ROWS + r] = r0 + r < rows ? hmat[(size_t)(r0 + r) * ldh + k] : 0.f;
+  }
+  __syncthreads();
+  float acc[PR_MAXNE][PR_ROWS];
+#pragma unroll
+  for (int n = 0; n < PR_MAXNE; ++n)
+#pragma unroll
+    for (int r = 0; r < PR_ROWS; ++r) acc[n][r] = 0.f;
+#pragma unroll
+  for (int n = 0; n < PR_MAXNE; ++n) {
+    const int e = threadIdx.x + n * PR_THREADS;
+    if (e < E) {
+      const float* mp = M + e;
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) {
+        const float m = __ldg(mp + (size_t)k * E);
+        const float4 a = hs4[k * 2], b = hs4[k * 2 + 1];
+        acc[n][0] = fmaf(a.x, m, acc[n][0]); acc[n][1] = fmaf(a.y, m, acc[n][1]); acc[n][2] = fmaf(a.z, m, acc[n][2]); acc[n][3] = fmaf(a.w, m, acc[n][3]);
+        acc[n][4] = fmaf(b.x, m, acc[n][4]); acc[n][5] = fmaf(b.y, m, acc[n][5]); acc[n][6] = fmaf(b.z, m, acc[n][6]); acc[n][7] = fmaf(b.w, m, acc[n][7]);
+      }
+    }
+  }
+  if (normalize) {
+    float ss[PR_ROWS];
+#pragma unroll
+    for (int r = 0; r < PR_ROWS; ++r) {
+      ss[r] = 0.f;
+#pragma unroll
+      for (int n = 0; n < PR_MAXNE; ++n) ss[r] = fmaf(acc[n][r], acc[n][r], ss[r]);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ss[r] += __shfl_xor_sync(0xffffffffu, ss[r], o);
+    }
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+      for (int r = 0; r < PR_ROWS; ++r) red[threadIdx.x >> 5][r] = ss[r];
+    __syncthreads();
+    if (threadIdx.x < PR_ROWS) {
+      float t = 0.f;
+      for (int w = 0; w < PR_THREADS / 32; ++w) t += red[w][threadIdx.x];
+      t = fmaxf(t, 1e-12f);
+      float inv = rsqrtf(t);
+      inv = inv * (1.5f - 0.5f * t * inv * inv);            // one Newton step: rsqrt(max(sum x^2, 1e-12)) to fp32 accuracy
+      inv_s[threadIdx.x] = inv;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < PR_ROWS; ++r) {
+    if (r0 + r >= rows) break;
+    const float inv = normalize ? inv_s[r] : 1.f;
+    float* o = out + (size_t)(perm ? perm[r0 + r] : r0 + r) * E;
+#pragma unroll
+    for (int n = 0; n < PR_MAXNE; ++n) {
+      const int e = threadIdx.x + n * PR_THREADS;
+      if (e < E) o[e] = acc[n][r] * inv;
+    }
+  }
+}
+
+// no bucketing wanted (pad-prefix start off): a flat, coalesced range check + copy over all SMs (the one-block fused
+// kernel above is latency-bound: 17 us at 600 x 50)
+__global__ void sanitize_copy_kernel(const int32_t* __restrict__ tok, int64_t n, int V, int32_t* __restrict__ stok, int* __restrict__ bad_total) {
+  int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = __ldg(tok + i);
+    const bool oob = v < 0 || v >= V;
+    stok[i] = oob ? 0 : v;
+    bad += (int)oob;
+  }
+  if (__any_sync(0xffffffffu, bad != 0)) {
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(bad_total, bad);
+  }
+}
+
 __global__ void sanitize_inplace_kernel(int32_t* __restrict__ tok, int64_t n, int V, int* __restrict__ bad_total) {
   int bad = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -274,6 +363,13 @@ int tok_prep(const int32_t* tokens, int B, int T, int V, bool sort, void* ws, To
   int* hist = reinterpret_cast<int*>(lead_of + al((size_t)B * 4) / 4);
   out->sorted = sort;
   if (B <= 0) return SSE_OK;
+  if (!sort) {
+    const int64_t n = (int64_t)B * T;
+    sanitize_copy_kernel<<<(int)std::min<int64_t>(cdiv64(n, 256), 148 * 8), 256, 0, st>>>(tokens, n, V, out->stok, bad_total);
+    if (launches) ++*launches;
+    SSE_CUDA_OK(cudaGetLastError());
+    return SSE_OK;
+  }
   if (B <= 8192 && T <= TP_MAX_T) {
     if (B <= TP_THREADS && (T & 1) == 0 && T <= 64)
       tok_prep_fused_kernel<true><<<1, TP_THREADS, (size_t)B * 2, st>>>(tokens, B, T, V, sort ? 1 : 0, out->stok, out->perm, out->lead_sorted, bad_total);
@@ -288,6 +384,16 @@ int tok_prep(const int32_t* tokens, int B, int T, int V, bool sort, void* ws, To
     tok_scatter_kernel<<<blocks, 256, 0, st>>>(tokens, B, T, V, lead_of, hist, sort ? 1 : 0, out->stok, out->perm, out->lead_sorted);
     if (launches) *launches += 3;
   }
+  SSE_CUDA_OK(cudaGetLastError());
+  return SSE_OK;
+}
+
+bool project_rows_supported(int rows, int H, int E) { return rows <= 4096 && E <= PR_MAXNE * PR_THREADS && (size_t)H * PR_ROWS * 4 <= 48 * 1024; }
+int project_rows(const float* hmat, int ldh, const float* M, int H, int E, int rows, const int32_t* perm, int normalize, float* out,
+                 cudaStream_t st, int64_t* launches) {
+  if (rows <= 0) return SSE_OK;
+  project_rows_kernel<<<cdiv(rows, PR_ROWS), PR_THREADS, (size_t)H * PR_ROWS * 4, st>>>(hmat, ldh, M, H, E, rows, perm, normalize, out);
+  if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
   return SSE_OK;
 }
