@@ -76,7 +76,12 @@ def parse():
                     "(default: 2-stage software pipeline over steps: encoder of batch s+1 overlaps the scan of batch s)")
     ap.add_argument("--search-ctas", type=int, default=-1, help="scan grid cap when pipelining (the remaining SMs run the encoder clusters); "
                     "-1 = auto: 108 (= 148 - 5 clusters x 8 CTAs) up to 4 GPUs, uncapped beyond, 0 = uncapped")
-    ap.add_argument("--search-late", type=int, default=0, help="with a scan grid cap: extra LATE scan CTAs that start on the SMs the concurrent encoder frees mid-scan")
+    ap.add_argument("--cluster-rows", type=int, default=-1, choices=[-1, 0, 64, 128],
+                    help="batch rows per cluster of the LSTM table kernel in the timed step (0 = the library's choice: 64 when every cluster "
+                         "still gets its own SMs; -1 = 128 when the scan is capped for pipelining -- the encoder then fits the SMs the cap "
+                         "leaves free -- else 0)")
+    ap.add_argument("--search-late", type=int, default=-1, help="with a scan grid cap: extra LATE scan CTAs that start on the SMs the concurrent encoder frees mid-scan "
+                                                                   "(-1 = 32 when the cap is on: measured 1.53 -> 1.59 M q/s at the headline shape)")
     ap.add_argument("--search-late-share", type=int, default=40, help="tile share of a late scan CTA, percent of a regular one")
     ap.add_argument("--train-steps", type=int, default=5, help="timed train steps for the secondary train-step/s figure (0 = skip)")
     ap.add_argument("--train-rows", type=int, default=0, help="pair rows per GPU per train step (0 = the config's, default 1024 = 512 pos + 512 neg)")
@@ -353,6 +358,11 @@ def run_b200(args):
     state = {"primed": False, "n": 0}
     if args.search_ctas < 0:
         args.search_ctas = 108 if G <= 4 else 0
+    if args.search_late < 0:
+        args.search_late = 32 if (pipeline and args.search_ctas > 0) else 0
+    if args.cluster_rows < 0:
+        args.cluster_rows = 128 if (pipeline and args.search_ctas > 0) else 0
+    h.set_option("cluster_rows", args.cluster_rows)
     if pipeline:
         for hs in scan_handles:
             hs.set_option("search_ctas", args.search_ctas)
@@ -482,13 +492,25 @@ def run_b200(args):
     if not args.no_real_regime and not table_mode and "cnn" not in cfg["mode"]:
         cur["host"], cur["dev"] = tokens["real"]
         h.set_option("pad_skip", 1)
+        # a REAL-regime encode is a few steps long: no point reserving SMs for it (measured 1.29 M q/s with the 108-CTA cap, 1.75 M without)
+        h.set_option("cluster_rows", 0)
+        if pipeline:
+            for hs in scan_handles:
+                hs.set_option("search_ctas", 0)
+                hs.set_option("search_late_ctas", 0)
         ms_r, _ = timed(step_device, args.steps, W, args.repeats)
         ms_re, _ = timed(step_e2e, args.steps, W, args.repeats)
         real = {"value": Ql * world * args.steps / (ms_r * 1e-3), "unit": "queries/s", "ms_per_step": ms_r / args.steps,
                 "e2e": {"value": Ql * world * args.steps / (ms_re * 1e-3), "ms_per_step": ms_re / args.steps},
-                "queries": "L ~ clip(Poisson(3), 1, T-2) real tokens per row, left-padded", "pad_prefix_start": True}
+                "queries": "L ~ clip(Poisson(3), 1, T-2) real tokens per row, left-padded", "pad_prefix_start": True,
+                "pipeline": "same 2-stage pipeline, scan grid uncapped (the short encode shares the SMs)"}
         cur["host"], cur["dev"] = tokens["full"]
         h.set_option("pad_skip", 0)
+        h.set_option("cluster_rows", args.cluster_rows)
+        if pipeline:
+            for hs in scan_handles:
+                hs.set_option("search_ctas", args.search_ctas)
+                hs.set_option("search_late_ctas", args.search_late if args.search_ctas else 0)
 
     # ---- dominant kernel (the index scan) timed alone, CUDA events on the launching stream, for the roofline
     for hs in scan_handles:
@@ -507,12 +529,19 @@ def run_b200(args):
     e1.record()
     torch.cuda.synchronize()
     ms_search = e0.elapsed_time(e1) / reps
-    e0.record()
-    for _ in range(reps):
-        h.encode(sse_ffi.SIDE_SRC, cur["dev"][0], Ql, enc_local[0], True, stream)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_enc = e0.elapsed_time(e1) / reps
+    enc_alone = {}
+    for rows_opt in (0, 128):             # the encoder alone on all SMs: the library's own choice (64-row clusters for a query batch) and 128-row clusters
+        h.set_option("cluster_rows", rows_opt)
+        for _ in range(2):
+            h.encode(sse_ffi.SIDE_SRC, cur["dev"][0], Ql, enc_local[0], True, stream)
+        e0.record()
+        for _ in range(reps):
+            h.encode(sse_ffi.SIDE_SRC, cur["dev"][0], Ql, enc_local[0], True, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        enc_alone[rows_opt] = e0.elapsed_time(e1) / reps
+    h.set_option("cluster_rows", args.cluster_rows)
+    ms_enc = enc_alone[0]
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- verification (outside every timed region): the last scan's rows against the exact fp32 SIMT scan of the same shard,
@@ -606,8 +635,9 @@ def run_b200(args):
     roof["algorithmic"] = {"flops": flops, "bytes": bytes_alg}
     roof["encoder"] = {"ms": ms_enc, "rows": Ql, "flops": Ql * F_ENC, "achieved_tflops": Ql * F_ENC / (ms_enc * 1e-3) / 1e12,
                        "achieved_frac_of_bf16_peak": Ql * F_ENC / (ms_enc * 1e-3) / 1e12 / bf16_tf,
-                       "kernel": "source tower of the step, timed alone on all SMs (token pre-pass + tower + projection + l2-norm); flops = the full "
-                                 "encoder (x and h parts, all T steps)"}
+                       "ms_128_row_clusters": enc_alone[128], "cluster_rows_in_timed_step": args.cluster_rows,
+                       "kernel": "source tower of the step, timed alone on all SMs with the library's own cluster size (token check + tower + "
+                                 "projection/l2-norm); flops = the full encoder (x and h parts, all T steps)"}
 
     total_q = Ql * world * args.steps
     out = {

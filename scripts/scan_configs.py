@@ -13,6 +13,9 @@ CONFIGS = [
     ("fused pack0", {"SSE_SCAN_FUSED": "1", "SSE_SCAN_PACK": "0"}),
     ("tn64", {"SSE_SCAN_ACC1": "0"}),
     ("cluster", {"SSE_SCAN_CLUSTER": "1"}),
+    ("div8", {"SSE_SCAN_SAMPLE_DIV": "8"}),
+    ("div12", {"SSE_SCAN_SAMPLE_DIV": "12"}),
+    ("div24", {"SSE_SCAN_SAMPLE_DIV": "24"}),
     ("cost100", {"SSE_SCAN_COST": "100,1100"}),
     ("cost500", {"SSE_SCAN_COST": "500,1000"}),
     ("cost780", {"SSE_SCAN_COST": "780,1000"}),

@@ -550,6 +550,7 @@ struct LstmP2Params {
   float* h_out;               // [B, H]
   int B, T, t_start, H;
   int poll_ns;                // back-off of the MMA / exchange warps' barrier polls (0 = none)
+  int flags;                  // timing experiments (SSE_LSTM_FLAGS): 1 = producer skips its loads, 2 = producer throttled, 4 = producer fetches after the exchange
   long long* dbg;             // optional [grid][16] cycle counters, then [P2_TRACE_STEPS][8] timestamps of CTA 0
 };
 
@@ -580,27 +581,32 @@ __device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {
 // to fp16 for the recurrence anyway).
 // warps: 0..EW-1 epilogue (warp w: TMEM lane quarter w % 4, unit group w / 4) | EW: MMA issuer + TMEM alloc + weight
 // load | EW+1: slice exchange
-template <int EW, int GATE>
+// ROWS: batch rows per cluster.  128 fills every TMEM lane quarter; 64 (query batches small enough to give every cluster its own
+// SMs) halves a CTA's epilogue, gather and exchange work per step -- the M = 128 MMAs then read 64 rows of whatever follows
+// the sub-slice (finite fp16 bits feeding accumulator lanes nobody reads) and the warps of lane quarters 2 / 3 have nothing to do.
+template <int EW, int GATE, int ROWS>
 __global__ void __launch_bounds__((EW + 2) * 32, 1)
 lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_constant__ LstmP2Params P, int kb_first) {
   constexpr int NSUB = EW / 4;          // unit groups per pass
   constexpr int UPP = 16 / NSUB;        // units per thread and pass
   constexpr int UPT = 2 * UPP;          // units per thread
   constexpr int W_MMA = EW, W_XCH = EW + 1;
+  constexpr int SUB_BYTES = ROWS * 32;  // one sub-slice: [ROWS rows x 16 units] fp16, SWIZZLE_32B K-major
+  constexpr int LIVE_EW = EW * ROWS / 128;   // epilogue warps whose TMEM lane quarter holds batch rows
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KBh = P.H / KBLK;
   const int CL = P.H / 32;
   const uint32_t rank = cluster_ctarank();
-  const int row0 = (blockIdx.x / CL) * P2_ROWS;
+  const int row0 = (blockIdx.x / CL) * ROWS;
   // per-tile pad-prefix start (tok_prep.cu): rows are sorted by descending number of leading PADs, so the tile's LAST row
   // has the shortest prefix; the tile starts at t0 from the tabulated state after t0 PADs
   int t0 = P.t_start;
   const float* init_h = P.init_h;
   const float* init_c = P.init_c;
   if (P.lead_sorted) {
-    t0 = min(__ldg(P.lead_sorted + min(row0 + P2_ROWS - 1, P.B - 1)), P.T - 1);
+    t0 = min(__ldg(P.lead_sorted + min(row0 + ROWS - 1, P.B - 1)), P.T - 1);
     init_h = t0 > 0 ? P.pad_h + (size_t)(t0 - 1) * P.H : nullptr;
     init_c = t0 > 0 ? P.pad_c + (size_t)(t0 - 1) * P.H : nullptr;
   }
@@ -611,7 +617,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   // h tile = 2*CL sub-slices of 16 hidden units: sub-slice m = units [16 m, 16 m + 16) = CTA m/2's pass m%2,
   // [128 rows x 32 B] fp16, SWIZZLE_32B K-major -- exactly the A operand of k-step m.
   uint8_t* h_smem = smem;                                            // [2 tiles][2 CL sub-slices]
-  uint8_t* wh_smem = h_smem + (size_t)2 * 2 * CL * P2_SUB_BYTES;     // [KBh] tiles [128 x 64] SW128
+  uint8_t* wh_smem = h_smem + (size_t)2 * 2 * CL * SUB_BYTES;     // [KBh] tiles [128 x 64] SW128
   uint64_t* bars = reinterpret_cast<uint64_t*>(wh_smem + (size_t)KBh * W_TILE_BYTES);
   const uint32_t bar_wf = smem_u32(bars + 0);
   const uint32_t bar_accf = smem_u32(bars + 1);    // [2 accumulators]
@@ -622,7 +628,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   if (threadIdx.x == 0) {
     mbar_init(bar_wf, 1);
     for (int b = 0; b < 2; ++b) mbar_init(bar_accf + 8 * b, 1);
-    for (int b = 0; b < 4; ++b) { mbar_init(bar_hr + 8 * b, 2); mbar_init(bar_sl + 8 * b, EW); }
+    for (int b = 0; b < 4; ++b) { mbar_init(bar_hr + 8 * b, 2); mbar_init(bar_sl + 8 * b, LIVE_EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -652,13 +658,13 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
       const int hb = (s - 1) & 1;
       const uint32_t n = s == 0 ? 0u : (uint32_t)(((s - 1) >> 1) + ((hb == 1 && has_init) ? 1 : 0));
       const uint32_t d = tmem_base + (uint32_t)((s & 1) * 128);
-      const uint32_t h_lo = h_lo0 + (uint32_t)(hb * 2 * CL * (P2_SUB_BYTES >> 4));
+      const uint32_t h_lo = h_lo0 + (uint32_t)(hb * 2 * CL * (SUB_BYTES >> 4));
       for (int p = 0; p < 2; ++p) {
         // pass-p sub-slices of h_{s-1}: the k-steps m = 2 q + p can start while the peers still compute / send pass 1
         const uint32_t bar = bar_hr + 8 * (hb * 2 + p);
         if (elect_one_sync()) {
           if (s == 0) mbar_arrive(bar);
-          else mbar_expect_tx(bar, (uint32_t)(CL - 1) * P2_SUB_BYTES);
+          else mbar_expect_tx(bar, (uint32_t)(CL - 1) * SUB_BYTES);
         }
         __syncwarp();
         mbar_wait_timed<false>(bar, n & 1, w_hr, (uint32_t)P.poll_ns);
@@ -667,7 +673,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
         if (elect_one_sync()) {
           for (int q = 0; q < CL; ++q) {
             const int m = 2 * q + p;
-            tc_mma_ss3(d, h_lo + (uint32_t)(m * (P2_SUB_BYTES >> 4)), h_hi, wh_lo + (uint32_t)((m >> 2) * (W_TILE_BYTES >> 4) + 2 * (m & 3)), wh_hi, idesc,
+            tc_mma_ss3(d, h_lo + (uint32_t)(m * (SUB_BYTES >> 4)), h_hi, wh_lo + (uint32_t)((m >> 2) * (W_TILE_BYTES >> 4) + 2 * (m & 3)), wh_hi, idesc,
                        (p | q) ? 1u : 0u);
           }
           if (p == 1) tc_commit(bar_accf + 8 * (s & 1));
@@ -691,14 +697,14 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
       const uint32_t n = (uint32_t)((s >> 1) + ((tb == 1 && has_init) ? 1 : 0));
       for (int p = 0; p < 2; ++p) {
         mbar_wait<false>(bar_sl + 8 * (tb * 2 + p), n & 1, (uint32_t)P.poll_ns);
-        const uint32_t off = (uint32_t)((tb * 2 * CL + 2 * (int)rank + p) * P2_SUB_BYTES);
-        if (lane < CL && lane != (int)rank) bulk_copy_to_peer(peer_h + off, smem_u32(h_smem) + off, P2_SUB_BYTES, peer_bar + 8 * (tb * 2 + p));
+        const uint32_t off = (uint32_t)((tb * 2 * CL + 2 * (int)rank + p) * SUB_BYTES);
+        if (lane < CL && lane != (int)rank) bulk_copy_to_peer(peer_h + off, smem_u32(h_smem) + off, SUB_BYTES, peer_bar + 8 * (tb * 2 + p));
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_hr + 8 * (tb * 2 + p));
         if (trace && lane == 0 && s < P2_TRACE_STEPS) trace[s * 8 + 6 + p] = clock64();
       }
     }
-  } else {
+  } else if ((warp & 3) < ROWS / 32) {
     // ===== epilogue: thread == (batch row, UPT of this CTA's 32 hidden units), c in registers.
     //       pass p of unit group `sub` covers units 16 p + UPP sub + [0, UPP) of the slice, so that the NSUB groups of
     //       pass p together complete sub-slice 2 rank + p, which leaves for the peers while pass 1 is still computing
@@ -715,13 +721,13 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
     for (int u = 0; u < UPT; ++u) c[u] = has_init ? __ldg(init_c + rank * 32 + (u / UPP) * 16 + sub * UPP + (u % UPP)) : 0.f;
     if (has_init) {
       // the broadcast initial state is the same for every row: each CTA fills its own tile 1 (= "step -1"), all sub-slices
-      const uint32_t t1 = smem_u32(h_smem) + (uint32_t)(2 * CL * P2_SUB_BYTES) + row_off32;
+      const uint32_t t1 = smem_u32(h_smem) + (uint32_t)(2 * CL * SUB_BYTES) + row_off32;
       for (int m = sub; m < 2 * CL; m += NSUB)
         for (int j = 0; j < 2; ++j) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(init_h + m * 16 + j * 8 + 2 * e), __ldg(init_h + m * 16 + j * 8 + 2 * e + 1));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t1 + (uint32_t)m * P2_SUB_BYTES + (((uint32_t)j ^ sw32) * 16)),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t1 + (uint32_t)m * SUB_BYTES + (((uint32_t)j ^ sw32) * 16)),
                        "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -730,7 +736,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
     }
     // byte offset of this thread's UPP units inside the 32-byte row of a sub-slice (16-byte chunks are XOR-swizzled)
     const uint32_t ubyte = (uint32_t)(sub * UPP * 2);
-    const uint32_t own_sub = smem_u32(h_smem) + (2 * rank) * P2_SUB_BYTES + row_off32 + (((ubyte >> 4) ^ sw32) * 16) + (ubyte & 15);
+    const uint32_t own_sub = smem_u32(h_smem) + (2 * rank) * SUB_BYTES + row_off32 + (((ubyte >> 4) ^ sw32) * 16) + (ubyte & 15);
     const size_t pcol = (size_t)rank * 128 + sub * 4 * UPP;
     constexpr float NL2E = -1.4426950408889634f;
     long long w_accf = 0, w_math = 0, tq = 0, t_begin = clock64();
@@ -757,7 +763,7 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
       }
       if (dbgt) tq = clock64();
       if (trace && warp == 0 && lane == 0 && s < P2_TRACE_STEPS) trace[s * 8 + 0] = tq;
-      const uint32_t tile_sub = own_sub + (uint32_t)((s & 1) * 2 * CL * P2_SUB_BYTES);
+      const uint32_t tile_sub = own_sub + (uint32_t)((s & 1) * 2 * CL * SUB_BYTES);
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         uint32_t v[4][UPP];
@@ -815,10 +821,10 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
         if (!last) {
           if (UPP == 8) {
             const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]), p2 = pack_f16x2(hv[4 % UPP], hv[5 % UPP]), p3 = pack_f16x2(hv[6 % UPP], hv[7 % UPP]);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_sub + (uint32_t)(p * P2_SUB_BYTES)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_sub + (uint32_t)(p * SUB_BYTES)), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
           } else {
             const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]);
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile_sub + (uint32_t)(p * P2_SUB_BYTES)), "r"(p0), "r"(p1) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile_sub + (uint32_t)(p * SUB_BYTES)), "r"(p0), "r"(p1) : "memory");
           }
           // this pass's part of the sub-slice is in place (and, for p == 1, the accumulator fully read): publish it
           if (p == 1) tc_fence_before();
@@ -854,25 +860,368 @@ lstm_ptable_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_co
   }
 }
 
+// =====================================================================================================
+// Variant 3 ("wide"): 64 hidden units per CTA, clusters of H/64 CTAs.
+// Variant 2's step is bound by the h exchange, not by the tensor or MUFU pipes: with 8 CTAs x 32 units every CTA pushes
+// 7 x 8 KB = 56 KB of slices per step through distributed shared memory, which sustains ~17 B/cycle per SM (measured with
+// the timeline trace: 28 KB per pass land 1.65-2.0 k cycles after the copies were issued).  The bytes a CTA sends per
+// (row, unit) it computes are 2 (CL - 1), so halving the cluster halves them: here a CTA owns 64 units (256 gate columns,
+// N = 256 MMAs, W_h slice 128 KB resident), computes twice the work per step and sends 3 x 16 KB = 48 KB.
+// What makes it fit: ONE h operand tile (64 KB) instead of a ping-pong pair.  A peer may overwrite this CTA's tile with
+// h_s slices only after this CTA's MMAs of step s (which read h_{s-1}) have completed; that is published explicitly: when
+// the epilogue sees the accumulator of step s it arrives on the `free` barrier of every CTA of the cluster, and an exchange
+// warp waits for all CL arrivals of step s before it sends the first slice of h_s.  The signal is sent ~a pass before the
+// first slice is ready, so it costs nothing in steady state.
+// Four passes of 16 units per step (thread == batch row x 4 units per pass, 16 epilogue warps): pass p's sub-slice leaves
+// while passes p+1.. compute, and the k-steps of pass p of the next step start when all CL pass-p sub-slices have landed.
+// Table values are fetched two passes ahead into a two-slot register ring.
+// shared memory (H=256): h tile 64 KB | W_h slice 128 KB.  TMEM: two [128 x 256] fp32 accumulators (512 columns).
+// warps: 0-15 epilogue | 16 MMA issuer + TMEM alloc + weight load | 17 slice exchange
+// The same kernel also runs with 32 units per CTA (clusters of H/32, N = 128): the single h tile then leaves room to
+// STAGE the table rows in shared memory.  Why: the per-thread gathers (thread == batch row, every lane another table row)
+// cost ~47 L1 data-pipe wavefronts per LDG.256 -- 64 (128 with 64 units) such loads per step kept the LSU pipe busy for
+// ~3 k (~6 k) cycles per step, more than the MUFU work.  With STAGE a producer warp copies each row's run with coalesced
+// 16-byte cp.async (two whole rows per warp instruction) into a swizzled [128 rows x 256 B] region per pass, one step ahead;
+// the epilogue threads read their 64 bytes with four conflict-free LDS.128.
+constexpr int P3_EW = 16, P3_UPP = 4;
+constexpr int P3_DEFAULT_UNITS = 32;
+constexpr int P3_TAB_REGION = P2_ROWS * 256;   // one pass of staged table rows: [128 rows][16 chunks of 16 B], chunk ^ (row & 15)
+
+// column of (gate g, hidden unit `unit`) in the table of this kernel: the 16 floats a thread needs in a pass are contiguous,
+// the 64 a batch row needs in a pass (all four unit groups) too
+__host__ __device__ __forceinline__ int ptab_col_wide(int unit, int g, int units_per_cta) {
+  const int c = unit / units_per_cta, j = unit % units_per_cta;
+  return c * 4 * units_per_cta + (j >> 4) * 64 + ((j & 15) >> 2) * 16 + g * 4 + (j & 3);
+}
+
+template <int GATE, int UNITS, bool STAGE>
+__global__ void __launch_bounds__((P3_EW + 2 + (STAGE ? 1 : 0)) * 32, 1)
+lstm_wide_kernel(const __grid_constant__ CUtensorMap tmap_w2d, const __grid_constant__ LstmP2Params P, int kb_first) {
+  constexpr int EW = P3_EW, NPASS = UNITS / 16, UPP = P3_UPP, UPT = NPASS * UPP;
+  constexpr int NCOL = 4 * UNITS;                   // gate columns of the slice = MMA N = accumulator columns
+  constexpr int WK_BYTES = NCOL * KBLK * 2;         // one k-block of the slice: [NCOL gate rows x 64 k] fp16, SW128
+  constexpr int W_MMA = EW, W_XCH = EW + 1, W_TAB = EW + 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KBh = P.H / KBLK;
+  const int CL = P.H / UNITS;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int row0 = (blockIdx.x / CL) * P2_ROWS;
+  int t0 = P.t_start;
+  const float* init_h = P.init_h;
+  const float* init_c = P.init_c;
+  if (P.lead_sorted) {
+    t0 = min(__ldg(P.lead_sorted + min(row0 + P2_ROWS - 1, P.B - 1)), P.T - 1);
+    init_h = t0 > 0 ? P.pad_h + (size_t)(t0 - 1) * P.H : nullptr;
+    init_c = t0 > 0 ? P.pad_c + (size_t)(t0 - 1) * P.H : nullptr;
+  }
+  const bool has_init = init_h != nullptr;
+  const int hi = has_init ? 1 : 0;
+  const int nsteps = P.T - t0;
+  long long* trace = (P.dbg && blockIdx.x == 0) ? P.dbg + (size_t)gridDim.x * 16 : nullptr;
+
+  // h tile = H/16 sub-slices of 16 hidden units: sub-slice m = units [16 m, 16 m + 16) = CTA m/NPASS's pass m%NPASS,
+  // [128 rows x 32 B] fp16, SWIZZLE_32B K-major -- exactly the A operand of k-step m.
+  uint8_t* h_smem = smem;
+  uint8_t* wh_smem = h_smem + (size_t)(P.H / 16) * P2_SUB_BYTES;     // [KBh] tiles [NCOL x 64] SW128
+  uint8_t* tab_smem = wh_smem + (size_t)KBh * WK_BYTES;              // STAGE: [NPASS] regions
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tab_smem + (STAGE ? (size_t)NPASS * P3_TAB_REGION : 0));
+  const uint32_t bar_wf = smem_u32(bars + 0);
+  const uint32_t bar_accf = smem_u32(bars + 1);    // [2 accumulators]
+  const uint32_t bar_hr = smem_u32(bars + 3);      // [NPASS]: all CL sub-slices of that pass have landed
+  const uint32_t bar_sl = smem_u32(bars + 7);      // [NPASS]: own sub-slice written by the EW epilogue warps
+  const uint32_t bar_free = smem_u32(bars + 11);   // every CTA of the cluster has finished reading the previous h from its tile
+  const uint32_t bar_tfull = smem_u32(bars + 12);  // [NPASS] STAGE: the region holds the table rows of the coming step
+  const uint32_t bar_tempty = smem_u32(bars + 16); // [NPASS] STAGE: all epilogue warps have taken their values out of the region
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_wf, 1);
+    for (int b = 0; b < 2; ++b) mbar_init(bar_accf + 8 * b, 1);
+    for (int b = 0; b < NPASS; ++b) {
+      mbar_init(bar_hr + 8 * b, 2); mbar_init(bar_sl + 8 * b, EW);
+      mbar_init(bar_tfull + 8 * b, 32); mbar_init(bar_tempty + 8 * b, EW);
+    }
+    mbar_init(bar_free, (uint32_t)CL);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * NCOL));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (CL > 1) cluster_sync_all();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == W_MMA) {
+    // ===== W_h slice load (once) + MMA issuer =====
+    if (elect_one_sync()) {
+      mbar_expect_tx(bar_wf, (uint32_t)KBh * WK_BYTES);
+      for (int kb = 0; kb < KBh; ++kb)
+        for (int hf = 0; hf < NCOL / 128; ++hf)
+          tma_load_2d(smem_u32(wh_smem + (size_t)kb * WK_BYTES + (size_t)hf * W_TILE_BYTES), &tmap_w2d, bar_wf, (kb_first + kb) * KBLK, (int)rank * NCOL + hf * 128);
+    }
+    __syncwarp();
+    const uint32_t idesc = make_idesc_f16(128, NCOL);
+    const uint64_t whd = make_sw128_desc(smem_u32(wh_smem)), hd = make_sw32_desc(smem_u32(h_smem));
+    const uint32_t wh_lo = (uint32_t)whd, wh_hi = (uint32_t)(whd >> 32), h_lo = (uint32_t)hd, h_hi = (uint32_t)(hd >> 32);
+    long long w_hr = 0, t_begin = clock64();
+    mbar_wait<false>(bar_wf, 0);
+    for (int s = has_init ? 0 : 1; s < nsteps; ++s) {
+      const uint32_t n = (uint32_t)(s - 1 + hi);            // completion index of h_{s-1} (the initial state is index 0)
+      const uint32_t d = tmem_base + (uint32_t)((s & 1) * NCOL);
+      for (int p = 0; p < NPASS; ++p) {
+        const uint32_t bar = bar_hr + 8 * p;
+        if (elect_one_sync()) {
+          if (s == 0 || CL == 1) mbar_arrive(bar);
+          else mbar_expect_tx(bar, (uint32_t)(CL - 1) * P2_SUB_BYTES);
+        }
+        __syncwarp();
+        mbar_wait_timed<false>(bar, n & 1, w_hr, (uint32_t)P.poll_ns);
+        tc_fence_after();
+        if (trace && lane == 0 && s < P2_TRACE_STEPS && p == 0) trace[s * 8 + 4] = clock64();
+        if (trace && lane == 0 && s < P2_TRACE_STEPS && p == NPASS - 1) trace[s * 8 + 5] = clock64();
+        if (elect_one_sync()) {
+          for (int q = 0; q < CL; ++q) {
+            const int m = NPASS * q + p;
+            tc_mma_ss3(d, h_lo + (uint32_t)(m * (P2_SUB_BYTES >> 4)), h_hi, wh_lo + (uint32_t)((m >> 2) * (WK_BYTES >> 4) + 2 * (m & 3)), wh_hi, idesc,
+                       (p | q) ? 1u : 0u);
+          }
+          if (p == NPASS - 1) tc_commit(bar_accf + 8 * (s & 1));
+        }
+        __syncwarp();
+      }
+    }
+    if (P.dbg && lane == 0) { P.dbg[blockIdx.x * 16 + 0] = w_hr; P.dbg[blockIdx.x * 16 + 3] = clock64() - t_begin; }
+  } else if (warp == W_XCH) {
+    // ===== sub-slice exchange =====
+    const uint32_t peer_h = map_to_cta(smem_u32(h_smem), (uint32_t)(lane < CL ? lane : 0));
+    const uint32_t peer_bar = map_to_cta(bar_hr, (uint32_t)(lane < CL ? lane : 0));
+    if (has_init) {
+      for (int p = 0; p < NPASS; ++p) {
+        mbar_wait<false>(bar_sl + 8 * p, 0);
+        if (lane == 0) mbar_arrive(bar_hr + 8 * p);
+      }
+    }
+    for (int s = 0; s + 1 < nsteps; ++s) {
+      const uint32_t n = (uint32_t)(s + hi);
+      for (int p = 0; p < NPASS; ++p) {
+        mbar_wait<false>(bar_sl + 8 * p, n & 1, (uint32_t)P.poll_ns);
+        if (p == 0 && CL > 1) mbar_wait<true>(bar_free, (uint32_t)s & 1, (uint32_t)P.poll_ns);     // every peer's tile may be overwritten now
+        const uint32_t off = (uint32_t)((NPASS * (int)rank + p) * P2_SUB_BYTES);
+        if (lane < CL && lane != (int)rank) bulk_copy_to_peer(peer_h + off, smem_u32(h_smem) + off, P2_SUB_BYTES, peer_bar + 8 * p);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_hr + 8 * p);
+        if (trace && lane == 0 && s < P2_TRACE_STEPS && p == 0) trace[s * 8 + 6] = clock64();
+        if (trace && lane == 0 && s < P2_TRACE_STEPS && p == NPASS - 1) trace[s * 8 + 7] = clock64();
+      }
+    }
+  } else if (STAGE && warp == W_TAB) {
+    // ===== table-row producer: region p of step s is refilled as soon as every epilogue warp has taken step s-1's values out
+    const int chunk = lane & 15, rsel = lane >> 4;
+    for (int s = 0; s < nsteps; ++s) {
+      for (int p = 0; p < NPASS; ++p) {
+        if (s > 0) mbar_wait<false>(bar_tempty + 8 * p, (uint32_t)(s - 1) & 1, 64);
+        if ((P.flags & 4) && s > 0 && p == 0)      // experiment: fetch only once h_{s-1} has completely landed here (the previous step's exchange is over)
+          mbar_wait<false>(bar_hr + 8 * (NPASS - 1), (uint32_t)(s - 1 + hi) & 1, 64);
+        const uint32_t reg_base = smem_u32(tab_smem) + (uint32_t)(p * P3_TAB_REGION);
+        const float* src0 = P.ptable + (size_t)rank * NCOL + p * 64 + chunk * 4;
+        if (!(P.flags & 1)) {
+#pragma unroll 8
+          for (int i = 0; i < P2_ROWS / 2; ++i) {
+            const int row = 2 * i + rsel;
+            const int tok = __ldg(P.tokens + (size_t)min(row0 + row, P.B - 1) * P.T + t0 + s);
+            const uint32_t dst = reg_base + (uint32_t)(row * 256 + ((chunk ^ (row & 15)) << 4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src0 + (size_t)tok * 4 * P.H) : "memory");
+            if ((P.flags & 2) && (i & 7) == 7) __nanosleep(100);
+          }
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_tfull + 8 * p) : "memory");
+      }
+    }
+  } else {
+    // ===== epilogue: thread == (batch row, UPT of this CTA's UNITS hidden units: 4 per pass), c in registers
+    const int quarter = warp & 3, sub = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const int grow = row0 + r;
+    const bool valid = grow < P.B;
+    const int32_t* trow = P.tokens + (size_t)min(grow, P.B - 1) * P.T + t0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t row_off32 = (uint32_t)(r * 32);
+    const uint32_t sw32 = (uint32_t)((r >> 2) & 1);            // SWIZZLE_32B: 16-byte chunk c of row r sits at c ^ ((r >> 2) & 1)
+    const int ubase = (int)rank * UNITS + sub * UPP;           // + 16 p + i
+    float c[UPT];
+#pragma unroll
+    for (int u = 0; u < UPT; ++u) c[u] = has_init ? __ldg(init_c + ubase + (u / UPP) * 16 + (u % UPP)) : 0.f;
+    if (has_init) {
+      // the broadcast initial state is the same for every row: each CTA fills its own tile, all sub-slices
+      const uint32_t t1 = smem_u32(h_smem) + row_off32;
+      for (int m = sub; m < P.H / 16; m += EW / 4)
+        for (int j = 0; j < 2; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__ldg(init_h + m * 16 + j * 8 + 2 * e), __ldg(init_h + m * 16 + j * 8 + 2 * e + 1));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t1 + (uint32_t)m * P2_SUB_BYTES + (((uint32_t)j ^ sw32) * 16)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        for (int p = 0; p < NPASS; ++p) mbar_arrive(bar_sl + 8 * p);
+    }
+    const uint32_t ubyte = (uint32_t)(sub * UPP * 2);
+    const uint32_t own_sub = smem_u32(h_smem) + (uint32_t)(NPASS * (int)rank) * P2_SUB_BYTES + row_off32 + (((ubyte >> 4) ^ sw32) * 16) + (ubyte & 15);
+    const size_t pcol = (size_t)rank * NCOL + sub * 16;        // + 64 p: the pass's run of 16 floats (4 gates x 4 units)
+    const uint32_t tab_row = smem_u32(tab_smem) + (uint32_t)(r * 256);
+    // remote `free` barriers (one elected thread of the CTA signals all CL CTAs, itself included)
+    const bool signaller = warp == 0 && lane < CL && CL > 1;
+    const uint32_t free_remote = signaller ? map_to_cta(bar_free, (uint32_t)lane) : 0u;
+    long long w_accf = 0, w_math = 0, tq = 0, t_begin = clock64();
+    const bool dbgt = P.dbg != nullptr;
+    // !STAGE: table values come straight from global memory into a two-slot register ring, slot p & 1 holds pass p's run;
+    // it is refilled for the pass two positions later right after pass p has been published
+    float pg[2][4 * UPP];
+    int tok_cur = __ldg(trow), tok_next = nsteps > 1 ? __ldg(trow + 1) : 0;
+    if (!STAGE) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float* prow = P.ptable + (size_t)(q < NPASS ? tok_cur : tok_next) * 4 * P.H + pcol + (q % NPASS) * 64;
+#pragma unroll
+        for (int x = 0; x < 4 * UPP; x += 8) ldg_v8(prow + x, pg[q] + x);
+      }
+    }
+    for (int s = 0; s < nsteps; ++s) {
+      const bool last = s == nsteps - 1;
+      const bool has_state = s > 0 || has_init;
+      if (has_state) {
+        mbar_wait_timed<false>(bar_accf + 8 * (s & 1), (uint32_t)(((s - (has_init ? 0 : 1)) >> 1) & 1), w_accf);
+        tc_fence_after();
+      }
+      // this CTA's MMAs of step s are complete: its h tile may now be overwritten with h_s
+      if (signaller && !last) mbar_arrive_remote(free_remote);
+      if (dbgt) tq = clock64();
+      if (trace && warp == 0 && lane == 0 && s < P2_TRACE_STEPS) trace[s * 8 + 0] = tq;
+#pragma unroll
+      for (int p = 0; p < NPASS; ++p) {
+        float* pgp = pg[p & 1];
+        if (STAGE) {
+          mbar_wait<false>(bar_tfull + 8 * p, (uint32_t)s & 1);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) lds_v4(tab_row + (uint32_t)(p * P3_TAB_REGION + ((((sub << 2) + g) ^ (r & 15)) << 4)), pgp + g * UPP);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * p);
+        }
+        uint32_t v[4][UPP];
+        if (has_state) {
+          const uint32_t acc = lane_base + (uint32_t)((s & 1) * NCOL + (p >> 1) * 128 + (p & 1) * 16 + sub * UPP);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) TMEM_LD_4(acc + 32 * g, v[g]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int i = 0; i < UPP; ++i) v[g][i] = 0u;
+        }
+        float hv[UPP];
+#pragma unroll
+        for (int i = 0; i < UPP; ++i) {
+          const int u = p * UPP + i;
+          const float bi = pgp[i], bj = pgp[UPP + i], bf = pgp[2 * UPP + i], bo = pgp[3 * UPP + i];
+          const float ai = __uint_as_float(v[0][i]), aj = __uint_as_float(v[1][i]), af = __uint_as_float(v[2][i]), ao = __uint_as_float(v[3][i]);
+          if (GATE == 0) {
+            constexpr float NL2E = -1.4426950408889634f;
+            const float ei = ex2_approx(fminf(fmaf(ai, NL2E, bi), 57.f));
+            const float ej = ex2_approx(fminf(fmaf(aj, 2.f * NL2E, bj), 57.f));
+            const float ef = ex2_approx(fminf(fmaf(af, NL2E, bf), 57.f));
+            const float eo = ex2_approx(fminf(fmaf(ao, NL2E, bo), 57.f));
+            const float pj = (1.f - ej) * rcp_approx((1.f + ei) * (1.f + ej));
+            c[u] = fmaf(c[u], rcp_approx(1.f + ef), pj);
+            const float ec = ex2_approx(fminf(c[u] * (2.f * NL2E), 57.f));
+            hv[i] = (1.f - ec) * rcp_approx((1.f + ec) * (1.f + eo));
+          } else {
+            const float ti = tanh_approx(fmaf(ai, 0.5f, bi));
+            const float tj = tanh_approx(aj + bj);
+            const float tf = tanh_approx(fmaf(af, 0.5f, bf));
+            c[u] = fmaf(c[u], fmaf(0.5f, tf, 0.5f), fmaf(0.5f, ti, 0.5f) * tj);
+            if (GATE == 1) {
+              const float to = tanh_approx(fmaf(ao, 0.5f, bo));
+              hv[i] = fmaf(0.5f, to, 0.5f) * tanh_approx(c[u]);
+            } else {
+              const uint32_t t2 = tanh_f16x2(pack_f16x2(fmaf(ao, 0.5f, bo), c[u]));
+              const float2 tt = __half22float2(*reinterpret_cast<const __half2*>(&t2));
+              hv[i] = fmaf(0.5f, tt.x, 0.5f) * tt.y;
+            }
+          }
+        }
+        if (P.dump_h && grow == 0) {
+          float* dh = P.dump_h + (size_t)(t0 + s) * P.H + ubase + p * 16;
+          float* dc = P.dump_c + (size_t)(t0 + s) * P.H + ubase + p * 16;
+#pragma unroll
+          for (int i = 0; i < UPP; ++i) { dh[i] = __half2float(__float2half_rn(hv[i])); dc[i] = c[p * UPP + i]; }
+        }
+        if (!last) {
+          const uint32_t p0 = pack_f16x2(hv[0], hv[1]), p1 = pack_f16x2(hv[2], hv[3]);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(own_sub + (uint32_t)(p * P2_SUB_BYTES)), "r"(p0), "r"(p1) : "memory");
+          if (p == NPASS - 1) tc_fence_before();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sl + 8 * p);
+          if (trace && warp == 0 && lane == 0 && s < P2_TRACE_STEPS && p == 0) trace[s * 8 + 1] = clock64();
+          if (trace && warp == 0 && lane == 0 && s < P2_TRACE_STEPS && p == NPASS - 1) trace[s * 8 + 2] = clock64();
+        } else if (valid) {
+          float* ho = P.h_out + (size_t)grow * P.H + ubase + p * 16;
+          *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        }
+        if (!STAGE && (p + 2 < NPASS || !last)) {
+          // refill this slot for the pass two positions later: of this step, or of the next one
+          const int q = p + 2;
+          const float* prow = P.ptable + (size_t)(q < NPASS ? tok_cur : tok_next) * 4 * P.H + pcol + (q % NPASS) * 64;
+#pragma unroll
+          for (int x = 0; x < 4 * UPP; x += 8) ldg_v8(prow + x, pgp + x);
+        }
+      }
+      tok_cur = tok_next;
+      if (s + 2 < nsteps) tok_next = __ldg(trow + s + 2);
+      if (dbgt) w_math += clock64() - tq;
+    }
+    if (P.dbg && lane == 0 && warp == 0) {
+      long long* o = P.dbg + blockIdx.x * 16;
+      o[4] = w_accf; o[5] = clock64() - t_begin; o[7] = w_math;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NCOL));
+  }
+}
+
 // Wxp[k][col] = scale_g * K[k][g*H + 32c + j], col = ptab_col(c, g, j, upp)  (the table's column order), k < We
-__global__ void ptable_wx_kernel(const float* __restrict__ K, int We, int H, int tanh_form, int upp, float* __restrict__ Wxp) {
+__global__ void ptable_wx_kernel(const float* __restrict__ K, int We, int H, int tanh_form, int upp, int wide, float* __restrict__ Wxp) {
   const int64_t total = (int64_t)We * 4 * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i / (4 * H)), np = (int)(i - (int64_t)k * 4 * H);
     const int c = np >> 7, g = (np >> 5) & 3, j = np & 31;
     const float sc = tanh_form ? (g == 1 ? 1.f : 0.5f) : (g == 1 ? -2.885390081777927f : -1.4426950408889634f);
-    Wxp[(size_t)k * 4 * H + ptab_col(c, g, j, upp)] = sc * K[(size_t)k * 4 * H + g * H + c * 32 + j];
+    Wxp[(size_t)k * 4 * H + (wide ? ptab_col_wide(c * 32 + j, g, wide) : ptab_col(c, g, j, upp))] = sc * K[(size_t)k * 4 * H + g * H + c * 32 + j];
   }
 }
 // P[v][col] = bias_r[c*128 + g*32 + j]  (the GEMM then accumulates the projection on top)
-__global__ void ptable_bias_kernel(const float* __restrict__ bias_r, int64_t V, int H4, int tanh_form, int upp, float* __restrict__ Pt) {
+__global__ void ptable_bias_kernel(const float* __restrict__ bias_r, int64_t V, int H4, int tanh_form, int upp, int wide, float* __restrict__ Pt) {
   const int64_t total = V * H4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int np = (int)(i % H4);
     const int c = np >> 7, g = (np >> 5) & 3, j = np & 31;
     float b = bias_r[np];                       // -log2e (-2 log2e for g == 1) x (b [+1 forget])
     if (tanh_form) b *= -0.34657359027997264f;  // (-log2e)(b) -> b/2 for i,f,o and (-2 log2e)(b) -> b for j: the same factor -ln2/2
-    Pt[i - np + ptab_col(c, g, j, upp)] = b;
+    Pt[i - np + (wide ? ptab_col_wide(c * 32 + j, g, wide) : ptab_col(c, g, j, upp))] = b;
   }
 }
 
@@ -954,12 +1303,18 @@ int lstm_ptable_prepare(TcTower& tt, const float* emb, int64_t V, const float* K
   // SSE_LSTM_EW 8 / 16 epilogue warps
   const int gate_math = getenv("SSE_LSTM_GATE_MATH") ? std::max(0, std::min(2, atoi(getenv("SSE_LSTM_GATE_MATH")))) : P2_DEFAULT_GATE;
   const int ew = getenv("SSE_LSTM_EW") ? (atoi(getenv("SSE_LSTM_EW")) == 8 ? 8 : 16) : P2_DEFAULT_EW;
+  // SSE_LSTM_UNITS = 32: variant 2 (clusters of H/32 CTAs), 64: variant 3 (clusters of H/64 CTAs, half the exchange per unit)
+  // tt.ptable_wide: 0 = variant 2 (lstm_ptable_kernel), 32 / 64 = variant 3 (lstm_wide_kernel) with that many units per CTA
+  const int variant = getenv("SSE_LSTM_VARIANT") ? atoi(getenv("SSE_LSTM_VARIANT")) : 2;     // measured: variant 3 is slower in every configuration tried (see DESIGN)
+  const int units = getenv("SSE_LSTM_UNITS") ? atoi(getenv("SSE_LSTM_UNITS")) : P3_DEFAULT_UNITS;
+  const int wide = variant == 2 ? 0 : (units == 64 ? 64 : 32);
   tt.ptable_mode = gate_math;
   tt.ptable_ew = ew;
+  tt.ptable_wide = wide;
   const int upp = 64 / ew;
-  ptable_wx_kernel<<<148, 256, 0, st>>>(K, We, H, gate_math != 0, upp, wxp);
+  ptable_wx_kernel<<<148, 256, 0, st>>>(K, We, H, gate_math != 0, upp, wide, wxp);
   if (launches) ++*launches;
-  ptable_bias_kernel<<<148 * 8, 256, 0, st>>>(tt.bias_r, V, 4 * H, gate_math != 0, upp, tt.ptable);
+  ptable_bias_kernel<<<148 * 8, 256, 0, st>>>(tt.bias_r, V, 4 * H, gate_math != 0, upp, wide, tt.ptable);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
   // rows in slabs that keep the GEMM's M within int range and friendly to the SIMT kernel
@@ -972,7 +1327,7 @@ int lstm_ptable_prepare(TcTower& tt, const float* emb, int64_t V, const float* K
 }
 
 int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We, int H, const TcTower& tt, const float* init_h,
-                        const float* init_c, const PadSkip& ps, float* h_out, cudaStream_t st, int64_t* launches) {
+                        const float* init_c, const PadSkip& ps, float* h_out, cudaStream_t st, int64_t* launches, int cluster_rows, int num_sms) {
   if (B <= 0 || T - t_start <= 0) return SSE_OK;
   if (!tt.ptable_valid) { set_error("lstm_forward_ptable: table not prepared"); return SSE_ESTATE; }
   LstmP2Params p;
@@ -981,14 +1336,30 @@ int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We
   p.B = B; p.T = T; p.t_start = t_start; p.H = H; p.dbg = nullptr;
   static const int poll_ns = getenv("SSE_LSTM_POLL") ? atoi(getenv("SSE_LSTM_POLL")) : 32;
   p.poll_ns = poll_ns;
+  p.flags = getenv("SSE_LSTM_FLAGS") ? atoi(getenv("SSE_LSTM_FLAGS")) : 0;
   typedef void (*p2_fn)(const CUtensorMap, const LstmP2Params, int);
-  const int ew = tt.ptable_ew;
-  p2_fn fn = ew == 8 ? (tt.ptable_mode == 0 ? lstm_ptable_kernel<8, 0> : tt.ptable_mode == 1 ? lstm_ptable_kernel<8, 1> : lstm_ptable_kernel<8, 2>)
-                     : (tt.ptable_mode == 0 ? lstm_ptable_kernel<16, 0> : tt.ptable_mode == 1 ? lstm_ptable_kernel<16, 1> : lstm_ptable_kernel<16, 2>);
-  const int CL = H / 32, KBh = H / KBLK;
-  const int n_clusters = cdiv(B, P2_ROWS);
+  const int wide = tt.ptable_wide;
+  // 64-row clusters (variant 2, 16 epilogue warps): when every cluster then still gets its own SMs (B <= 64 * floor(SMs / CL)),
+  // unless the caller asks for 128 (cluster_rows; a concurrent scan wants the encoder on as few SMs as possible)
+  static const int env_rows = getenv("SSE_LSTM_CL_ROWS") ? atoi(getenv("SSE_LSTM_CL_ROWS")) : 0;
+  const int want_rows = env_rows ? env_rows : cluster_rows;
+  const bool rows64 = wide == 0 && tt.ptable_ew == 16 && want_rows != 128 && (want_rows == 64 || cdiv(B, 64) * (H / 32) <= num_sms);
+  static const bool stage = getenv("SSE_LSTM_STAGE") ? atoi(getenv("SSE_LSTM_STAGE")) != 0 : true;
+  const bool staged = wide == 32 && stage;
+  const int ew = wide ? P3_EW : tt.ptable_ew;
+  const int gm = tt.ptable_mode;
+  p2_fn fn = wide == 64 ? (gm == 0 ? lstm_wide_kernel<0, 64, false> : gm == 1 ? lstm_wide_kernel<1, 64, false> : lstm_wide_kernel<2, 64, false>)
+           : wide == 32 ? (staged ? (gm == 0 ? lstm_wide_kernel<0, 32, true> : gm == 1 ? lstm_wide_kernel<1, 32, true> : lstm_wide_kernel<2, 32, true>)
+                                  : (gm == 0 ? lstm_wide_kernel<0, 32, false> : gm == 1 ? lstm_wide_kernel<1, 32, false> : lstm_wide_kernel<2, 32, false>))
+           : ew == 8 ? (gm == 0 ? lstm_ptable_kernel<8, 0, 128> : gm == 1 ? lstm_ptable_kernel<8, 1, 128> : lstm_ptable_kernel<8, 2, 128>)
+                     : rows64 ? (gm == 0 ? lstm_ptable_kernel<16, 0, 64> : gm == 1 ? lstm_ptable_kernel<16, 1, 64> : lstm_ptable_kernel<16, 2, 64>)
+                              : (gm == 0 ? lstm_ptable_kernel<16, 0, 128> : gm == 1 ? lstm_ptable_kernel<16, 1, 128> : lstm_ptable_kernel<16, 2, 128>);
+  const int CL = wide ? H / wide : H / 32, KBh = H / KBLK;
+  const int rows_cl = rows64 ? 64 : P2_ROWS;
+  const int n_clusters = cdiv(B, rows_cl);
   const int grid = n_clusters * CL;
-  const size_t smem = 1024 + (size_t)2 * 2 * CL * P2_SUB_BYTES + (size_t)KBh * W_TILE_BYTES + 256;
+  const size_t smem = wide ? 1024 + (size_t)(H / 16) * P2_SUB_BYTES + (size_t)KBh * (4 * wide * KBLK * 2) + (staged ? (size_t)(wide / 16) * P3_TAB_REGION : 0) + 256
+                           : 1024 + (size_t)2 * 2 * CL * (rows_cl * 32) + (size_t)KBh * W_TILE_BYTES + 256;
   const bool want_dbg = getenv("SSE_LSTM_DEBUG") != nullptr;
   long long* d_dbg = nullptr;
   const size_t dbg_bytes = (size_t)grid * 128 + (size_t)P2_TRACE_STEPS * 64;
@@ -997,7 +1368,7 @@ int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3((unsigned)(ew + 2) * 32, 1, 1);
+  cfg.blockDim = dim3((unsigned)(ew + 2 + (staged ? 1 : 0)) * 32, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1015,7 +1386,7 @@ int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We
     cudaStreamSynchronize(st);
     cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
     cudaFree(d_dbg);
-    fprintf(stderr, "[lstm ptable dbg] variant: %d epilogue warps, gate math %d, poll back-off %d ns\n", ew, tt.ptable_mode, poll_ns);
+    fprintf(stderr, "[lstm ptable dbg] variant: %s, %d rows per cluster, %d units per CTA%s, %d epilogue warps, gate math %d, poll back-off %d ns\n", wide ? "3 (single h tile)" : "2", rows_cl, wide ? wide : 32, staged ? ", staged table rows" : "", ew, tt.ptable_mode, poll_ns);
     {   // CTA 0's timeline of a few mid-sequence steps, relative to the step's accumulator-ready time
       const long long* tr = hd.data() + (size_t)grid * 16;
       for (int s = 20; s < std::min(24, T - t_start - 1); ++s) {

@@ -28,6 +28,7 @@
 #include "sse_common.cuh"
 #include <cuda.h>
 #include <math_constants.h>
+#include <math.h>
 #include <stdlib.h>
 
 namespace sse {
@@ -1401,7 +1402,11 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   // sample = every 16th tile: tau = k-th largest sampled tile maximum - 2 eps keeps ~16 k candidates per query
   // (measured: 1/32 and 1/64 samples cost more in candidate handling than they save in the sample pass); rows whose
   // sampled threshold is loose tighten it inside the scan (compact_candidates)
-  static const int sample_div = getenv("SSE_SCAN_SAMPLE_DIV") ? std::max(1, atoi(getenv("SSE_SCAN_SAMPLE_DIV"))) : 16;
+  // The sample pass costs ~ Q N / div, the candidates it leaves ~ Q k div: the best divisor grows like sqrt(N / k).  Measured
+  // (whole search, k = 10): N = 1M: div 16 best (0.314 ms vs 0.324 at 8); N = 250k: 8 (0.329 vs 0.341 at 16); N = 125k: 8 or lower
+  // (0.373 vs 0.407 at 16).  div = 0.0506 sqrt(N / k) reproduces 16 at 1M / k = 10.
+  static const int env_sample_div = getenv("SSE_SCAN_SAMPLE_DIV") ? std::max(1, atoi(getenv("SSE_SCAN_SAMPLE_DIV"))) : 0;
+  const int sample_div = env_sample_div ? env_sample_div : std::max(4, std::min(32, (int)lrint(0.0506 * sqrt((double)N / std::max(k, 1)))));
   int n_s = (int)(N / sample_div / tn);
   if (n_s < 64) n_s = 64;
   if (n_s < 2 * k) n_s = 2 * k;
@@ -1437,7 +1442,12 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
   static const bool env_pdl = env_int("SSE_SCAN_PDL", 0) != 0;
   // spanning items (see ScanParams): whenever the groups are packed equally and the CTA budget is not a multiple of the group count
   static const int env_span = env_int("SSE_SCAN_SPAN", -1);
-  bool span = cs == 1 && !pack_full && n_groups > 1 && late_ctas == 0 && (env_span >= 0 ? env_span != 0 : true);
+  // measured (whole search, auto vs SSE_SCAN_SPAN=0): 4800 x 125k (19 groups, 7 items each = 90 % of the SMs) 0.424 vs 0.439 ms, but
+  // 2400 x 250k (10 groups, 95 %) 0.358 vs 0.349 and 1200 x 500k (5 groups, 98 %) 0.329 vs 0.305: the restaging and the second
+  // candidate slot only pay when whole items would leave more than ~7 % of the SMs idle
+  const int budget0 = std::max(num_sms, n_groups);
+  const bool span_pays = (budget0 / n_groups) * n_groups * 100 < budget0 * 93;
+  bool span = cs == 1 && !pack_full && n_groups > 1 && late_ctas == 0 && (env_span >= 0 ? env_span != 0 : span_pays);
   const bool fused = env_fused && k <= FUSED_MAX_K && cs == 1 && ti.group_ctr != nullptr && !span;
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_tilemax, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   SSE_CUDA_OK(cudaFuncSetAttribute(fn_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1663,6 +1673,16 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
     }
   }
   fp.maxc = k <= 32 ? FIN_MAXC_SMALL : FIN_MAXC_LARGE;
+  {
+    // a row's candidates = one list of <= CAND_CAP entries per candidate slot of its m-group: when few slots feed a row (many
+    // m-groups share the SMs: thousands of queries against a small shard) the sort buffers shrink with them and twice as
+    // many rows are in flight per SM (4800 rows: 4 waves of 8 blocks per SM -> 2 waves of 15)
+    int slots_max = 1;
+    for (int g = 0; g < n_groups; ++g)
+      slots_max = std::max(slots_max, span ? span_n[g] : (cs > 1 ? R : sp.group_items[g] + sp.group_late[g]));
+    const int need = (slots_max * CAND_CAP + 127) / 128 * 128;
+    if (need < fp.maxc) fp.maxc = std::max(need, 256);
+  }
   {
     static bool fin_attr = false;
     if (!fin_attr) { SSE_CUDA_OK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIN_MAXC_LARGE * 12 + FIN_MAXR * 4)); fin_attr = true; }

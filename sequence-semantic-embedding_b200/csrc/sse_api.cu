@@ -285,7 +285,7 @@ int encode_device(sse_handle* h, int side, const int32_t* tokens_in, int B, floa
       else if (!padded) { SSE_TRY(ensure_pad_table(h, side, st)); ps.pad_h = h->pad[side].h; ps.pad_c = h->pad[side].c; ps.lead_sorted = tp.lead_sorted; }
     }
     if (kern == 3) {
-      SSE_TRY(lstm_forward_ptable(tokens, B, T, 0, Wp, Hp, tt, nullptr, nullptr, ps, hout, st, &h->launches));
+      SSE_TRY(lstm_forward_ptable(tokens, B, T, 0, Wp, Hp, tt, nullptr, nullptr, ps, hout, st, &h->launches, h->opt_cluster_rows, h->num_sms));
     } else if (kern == 2) {
       SSE_TRY(lstm_forward_cluster(tokens, B, T, 0, h->emb_f16, Wp, Hp, tt, nullptr, nullptr, ps, hout, st, &h->launches));
     } else {
@@ -748,6 +748,7 @@ int sse_set_option(sse_handle* h, const char* key, int value) {
   if (!strcmp(key, "search")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_search = value; return SSE_OK; }
   if (!strcmp(key, "encoder")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_encoder = value; return SSE_OK; }
   if (!strcmp(key, "train")) { if (value < 0 || value > 2) return SSE_EINVAL; h->opt_train = value; return SSE_OK; }
+  if (!strcmp(key, "cluster_rows")) { if (value != 0 && value != 64 && value != 128) return SSE_EINVAL; h->opt_cluster_rows = value; return SSE_OK; }
   if (!strcmp(key, "pad_skip")) { h->opt_pad_skip = value != 0; return SSE_OK; }
   if (!strcmp(key, "lstm_kernel")) { if (value < 0 || value > 4) return SSE_EINVAL; h->opt_lstm_kernel = value; return SSE_OK; }
   if (!strcmp(key, "search_ctas")) { if (value < 0) return SSE_EINVAL; h->opt_search_ctas = value; return SSE_OK; }

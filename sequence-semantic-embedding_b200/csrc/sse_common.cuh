@@ -199,6 +199,7 @@ struct TcTower {
   float* wxp = nullptr;            // [We, 4H] permuted + scaled W_x (GEMM operand of the table build)
   bool ptable_valid = false;
   int ptable_mode = 0;             // gate-math variant the table was scaled for
+  int ptable_wide = 32;            // 0: table laid out for lstm_ptable_kernel; 32 / 64: for lstm_wide_kernel with that many units per CTA
   int ptable_ew = 16;              // epilogue warps of the kernel variant the table's column order was built for
 };
 bool lstm_tc_supported(int We, int H);
@@ -219,7 +220,8 @@ bool lstm_ptable_supported(int64_t V, int We, int H);
 int lstm_ptable_prepare(TcTower& tt, const float* emb, int64_t V, const float* K, int We, int H, cudaStream_t st, int64_t* launches);
 void lstm_ptable_release(TcTower& tt);
 int lstm_forward_ptable(const int32_t* tokens, int B, int T, int t_start, int We, int H, const TcTower& tt, const float* init_h,
-                        const float* init_c, const PadSkip& ps, float* h_out, cudaStream_t st, int64_t* launches);
+                        const float* init_c, const PadSkip& ps, float* h_out, cudaStream_t st, int64_t* launches, int cluster_rows = 0,
+                        int num_sms = 148);
 
 // small utilities (util.cu)
 int fill_f32(float* p, int64_t n, float v, cudaStream_t st, int64_t* launches);

@@ -66,6 +66,7 @@ struct sse_handle {
   int opt_search_ctas = 0;          // 0 = all SMs; else cap on the scan grid (leaves SMs to a concurrent encoder)
   int opt_search_late = 0;          // with a cap: extra LATE scan items for the SMs the concurrent kernel frees mid-scan ...
   int opt_search_late_share = 40;   // ... each taking this percentage of a regular item's tile range
+  int opt_cluster_rows = 0;         // batch rows per cluster of the table LSTM kernel: 0 = auto (64 when every cluster still gets its own SMs), 64, 128
   bool opt_pad_skip = true;         // per-tile pad-prefix start of the LSTM towers (tok_prep.cu)
   int64_t launches = 0;
 };
