@@ -19,8 +19,8 @@ def rows(rep):
 
 
 def main():
-    reps = sys.argv[1:] or [os.path.join(REPO, "gpurun_out", f) for f in ("prof_scan.ncu-rep", "prof_lstm.ncu-rep", "prof_lstm_tc_fullwave.ncu-rep")]
-    lines = ["# ncu --set full --clock-control none captures (B200, round 1); per kernel launch, values with units"]
+    reps = sys.argv[1:] or [os.path.join(REPO, "gpurun_out", f) for f in ("prof_scan_600.ncu-rep", "prof_lstm.ncu-rep", "prof_small.ncu-rep", "prof_scan_4800.ncu-rep")]
+    lines = ["# ncu --set full --clock-control none captures (B200, round 2); per kernel launch, values with units"]
     traffic = None
     for rep in reps:
         if not os.path.exists(rep):
@@ -38,10 +38,10 @@ def main():
             if "scan_kernel<1" in d[ki] and "dram__bytes_read.sum" in vals:
                 tot = sum(float(vals[m][0].replace(",", "")) * UNIT.get(vals[m][1], 1.0) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
                 traffic = int(tot)
-    open(os.path.join(REPO, "profiles", "r01_ncu_full_summary.txt"), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(REPO, "profiles", "r02_ncu_full_summary.txt"), "w").write("\n".join(lines) + "\n")
     if traffic:
         json.dump({"targets_per_gpu": 1000000, "queries": 600, "scan_filter_dram_bytes": traffic,
-                   "source": "profiles/r01_ncu_full_summary.txt: ncu --set full of scan_kernel<FILTER>, dram__bytes_read.sum + dram__bytes_write.sum per launch"},
+                   "source": "profiles/r02_ncu_full_summary.txt: ncu --set full of scan_kernel<FILTER>, dram__bytes_read.sum + dram__bytes_write.sum per launch"},
                   open(os.path.join(REPO, "profiles", "traffic.json"), "w"))
     print("\n".join(lines[:60]))
 
