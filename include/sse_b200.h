@@ -221,11 +221,14 @@ int sse_debug_gemm_tc(sse_handle* h, const float* a_dev, const float* b_dev, int
                       float alpha, float beta, float* d_dev, void* stream);
 /* number of kernels this library launched on the handle since creation */
 int64_t sse_launch_count(sse_handle* h);
-/* select kernel variants at run time: key in {"search", "encoder", "lstm_kernel", "pad_skip", "search_ctas", "search_late_ctas", "search_late_share", "train"};
+/* select kernel variants at run time: key in {"search", "encoder", "lstm_kernel", "cluster_rows", "pad_skip", "search_ctas", "search_late_ctas", "search_late_share", "train"};
  * search: 0 auto, 1 simt-fp32, 2 tcgen05-fp16;  encoder: 0 auto, 1 simt-fp32, 2 tcgen05;
  * lstm_kernel (tcgen05 encoder only): 0 auto, 1 weight-streaming kernel, 2 cluster kernel (weights resident in
  * the shared memory of a thread-block cluster), 3 cluster kernel with the input projection tabulated per
  * vocabulary entry (V x 4H fp32 table, rebuilt when parameters change; the default when it fits in 2 GiB);
+ * cluster_rows: batch rows per thread-block cluster of the table LSTM kernel: 0 (default) = 64 when every cluster still gets its own
+ * SMs (query batches: half the per-step work per SM, lowest latency), else 128; 64 / 128 force (128 keeps a 600-row batch on 40 SMs
+ * for a step that overlaps it with a capped scan);
  * pad_skip: 1 (default) rows are bucketed by their number of leading PADs on the device and every kernel tile starts
  * from the tabulated pad-prefix state instead of running the PAD steps (all entry points), 0 off;  search_ctas: cap on the scan grid (0 = all SMs),
  * so that an encoder launched on another stream can run concurrently on the remaining SMs;  search_late_ctas /
