@@ -13,6 +13,9 @@ CONFIGS = [
     ("fused pack0", {"SSE_SCAN_FUSED": "1", "SSE_SCAN_PACK": "0"}),
     ("tn64", {"SSE_SCAN_ACC1": "0"}),
     ("cluster", {"SSE_SCAN_CLUSTER": "1"}),
+    ("nofollow", {"SSE_SCAN_FOLLOW": "0"}),
+    ("follow_cost650", {"SSE_SCAN_COST": "650,1000"}),
+    ("follow_cost500", {"SSE_SCAN_COST": "500,1000"}),
     ("div8", {"SSE_SCAN_SAMPLE_DIV": "8"}),
     ("div12", {"SSE_SCAN_SAMPLE_DIV": "12"}),
     ("div24", {"SSE_SCAN_SAMPLE_DIV": "24"}),

@@ -90,6 +90,12 @@ struct ScanParams {
   // CTAs to groups (19 groups on 148 SMs: 7 items per group used 133 SMs).  A piece that crosses a group boundary has two
   // SEGMENTS: the CTA restages its queries (TMEM A operand) between them and keeps a separate candidate slot per segment.
   int span;
+  // FOLLOWING last group (filter pass, full packing, cs == 1): the remainder m-group (one live m-tile) does not sweep its own
+  // contiguous tile ranges -- that reads the whole index from HBM a second time -- but walks the tiles of the FIRST group's
+  // regular items in the order those items reach them (unit q = (round, lead item): tile = lead item's first tile + round;
+  // the group's regular items take the units round-robin), so that its reads find the tiles in L2.  Its late items split the
+  // tail [n_reg_lead, n_j) that the leader's late items cover.
+  int follow;
   int n_early;                       // items [0, n_early) are regular, [n_early, grid) late
   int group_first_late[MAX_GROUPS];
   int group_late[MAX_GROUPS];
@@ -486,6 +492,27 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
     j0 = (int)(((int64_t)P.n_j * w0) / wsum);
     j1 = (int)(((int64_t)P.n_j * w1) / wsum);
   }
+  // following group (see ScanParams::follow): leader = group 0; lead item i owns tiles [lead_j0(i), lead_j0(i + 1))
+  const bool follower = MODE == MODE_FILTER && P.follow && g == P.n_groups - 1 && !P.span && cs == 1;
+  const int lead_R = P.group_items[0];
+  const int64_t lead_wsum = (int64_t)lead_R * 256 + (int64_t)P.group_late[0] * P.late_share;
+  auto lead_j0 = [&](int i) { return (int)(((int64_t)P.n_j * ((int64_t)i * 256)) / lead_wsum); };
+  const int n_reg_lead = lead_j0(lead_R);
+  int f_rounds = 0;
+  if (follower) {
+    if (!late) {
+      // rounds = longest lead range (ranges differ by at most one tile); units of the last round that do not exist are
+      // scanned as an out-of-range tile (TMA zero fill, every column masked)
+      f_rounds = n_reg_lead / lead_R + 1;
+      const int64_t U = (int64_t)f_rounds * lead_R;
+      j0 = 0;
+      j1 = (int)((U - r_in_g + R - 1) / R);          // units r_in_g, r_in_g + R, ... < U
+    } else {
+      const int tail = P.n_j - n_reg_lead;
+      j0 = n_reg_lead + (int)(((int64_t)tail * r_in_g) / max(R_late, 1));
+      j1 = n_reg_lead + (int)(((int64_t)tail * (r_in_g + 1)) / max(R_late, 1));
+    }
+  }
   const int na = j1 - j0;             // tiles of the first segment
   // fused scan: this item first visits its share of the SAMPLE tiles (tile maxima), then -- after the per-group barrier
   // and the threshold selection in the epilogue -- its share of all tiles (filter)
@@ -493,7 +520,16 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_idx, const __grid_constant_
   const int js1 = (MODE == MODE_FUSED && !late) ? (int)(((int64_t)P.n_s * (r_in_g + 1)) / R) : 0;
   const int ns_loc = js1 - js0;
   const int n_loc = ns_loc + na + (k1 - k0);
+  // (32-bit arithmetic: every role evaluates this once per tile, and 64-bit divisions cost the epilogue ~600 cycles per tile;
+  // the host enables `follow` only when n_j * items * 256 fits)
+  const uint32_t lead_wsum32 = (uint32_t)lead_wsum, lead_nj256 = (uint32_t)P.n_j * 256u;
   auto tile_of = [&](int jj) {
+    if (follower && !late) {
+      const uint32_t q = (uint32_t)jj * (uint32_t)R + (uint32_t)r_in_g;
+      const uint32_t rd = q / (uint32_t)lead_R, i = q - rd * (uint32_t)lead_R;
+      const uint32_t t0 = (lead_nj256 * i) / lead_wsum32, t1 = (lead_nj256 * (i + 1)) / lead_wsum32;
+      return (int)(t0 + rd < t1 ? t0 + rd : (uint32_t)P.n_j);          // P.n_j = one past the last tile: out of range
+    }
     return jj < ns_loc ? (js0 + jj) * P.s_step : (jj - ns_loc < na ? (j0 + jj - ns_loc) * P.tile_step : (k0 + jj - ns_loc - na) * P.tile_step);
   };
   const int KB = KBT ? KBT : P.kb, NG = P.n_stages, TN = TNT ? TNT : P.tn;   // n_stages = number of TILE slots in the ring
@@ -1549,6 +1585,12 @@ int search_tc(const float* q, int Q, int E, const float* index_f32, TcIndex& ti,
     total_slots = slot;
   }
   sp.cs = cs; sp.R = R;
+  // SSE_SCAN_FOLLOW=1 (experiment, off): measured at 600 x 1M -- DRAM reads of the filter scan 0.95 -> 0.67 GB, L2 hit 42 -> 51 %, but
+  // the whole search 0.325 -> 0.342 ms: the strided order costs the remainder group's roles two integer divisions per tile and its
+  // items still run ~18 % behind the heavy groups; HBM (3.8 TB/s of 6.5) was not what the heavy groups wait for
+  static const int env_follow = env_int("SSE_SCAN_FOLLOW", 0);
+  sp.follow = (env_follow && pack_full && cs == 1 && !span && n_groups >= 2 && sp.group_mt[n_groups - 1] < mtg && sp.group_mt[0] == mtg &&
+               (sp.group_late[0] > 0) == (sp.group_late[n_groups - 1] > 0) && (int64_t)n_tiles * 256 * (items + 2) < (int64_t)1 << 31) ? 1 : 0;
   lcfg.gridDim = dim3(items, 1, 1);
   const int list_items = span ? total_slots : items;      // candidate lists to allocate / walk
 
