@@ -19,7 +19,7 @@ def rows(rep):
 
 
 def main():
-    reps = sys.argv[1:] or [os.path.join(REPO, "gpurun_out", f) for f in ("prof_scan_600.ncu-rep", "prof_lstm.ncu-rep", "prof_small.ncu-rep", "prof_scan_4800.ncu-rep")]
+    reps = sys.argv[1:] or [os.path.join(REPO, "gpurun_out", f) for f in ("prof_scan_600.ncu-rep", "prof_lstm.ncu-rep", "prof_small.ncu-rep", "prof_scan_4800.ncu-rep", "prof_fin_4800.ncu-rep")]
     lines = ["# ncu --set full --clock-control none captures (B200, round 2); per kernel launch, values with units"]
     traffic = None
     for rep in reps:
@@ -35,7 +35,7 @@ def main():
                     i = hdr.index(m)
                     lines.append("   %-78s %s %s" % (m, d[i], units[i]))
                     vals[m] = (d[i], units[i])
-            if "scan_kernel<1" in d[ki] and "dram__bytes_read.sum" in vals:
+            if "scan_kernel<1" in d[ki] and "dram__bytes_read.sum" in vals and "prof_scan_600" in rep:
                 tot = sum(float(vals[m][0].replace(",", "")) * UNIT.get(vals[m][1], 1.0) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
                 traffic = int(tot)
     open(os.path.join(REPO, "profiles", "r02_ncu_full_summary.txt"), "w").write("\n".join(lines) + "\n")

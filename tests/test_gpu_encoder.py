@@ -219,3 +219,83 @@ def test_tc_lstm_gemm_per_step_tower_within_tolerance(mode, We, H, E, T, B, forc
         err = np.abs(got - want).max()
         assert 0 < err < TOL_TC, (name, err)
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# round-2 variants of the table kernel: the cluster size must not change a single bit, the optional variants must stay in tolerance
+@pytest.mark.parametrize("B", [1, 77, 600, 1300])
+def test_tc_lstm_cluster_rows_64_and_128_are_bit_identical(B):
+    mode, V, We, H, E, T = "dual-encoder", 5000, 256, 256, 256, 50
+    h, p = make(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
+    h.set_option("encoder", 2)
+    h.set_option("lstm_kernel", 3)
+    rng = np.random.default_rng(B)
+    tok = np.concatenate([O.synth_tokens(rng, B - B // 2, T, V, "full"), O.synth_tokens(rng, B // 2, T, V, "real", 4.0)]) \
+        if B > 1 else O.synth_tokens(rng, 1, T, V, "full")
+    outs = {}
+    for rows in (64, 128, 0):
+        h.set_option("cluster_rows", rows)
+        for skip in (0, 1):
+            h.set_option("pad_skip", skip)
+            outs[(rows, skip)] = h.encode_host(sse_ffi.SIDE_SRC, tok, True)
+    ref = outs[(128, 0)]
+    assert np.abs(ref - O.encode(p, mode, "src", tok, True)).max() < TOL_TC
+    for key, got in outs.items():
+        assert np.array_equal(got, ref), key
+    with pytest.raises(Exception):
+        h.set_option("cluster_rows", 96)
+    h.close()
+
+
+def test_query_batch_projection_matches_the_index_build_projection():
+    """Query batches run projection + l2-norm in one launch (project_rows_kernel), larger batches the SIMT GEMM + l2norm_rows:
+    the same rows must come out equal to fp32 rounding through both."""
+    mode, V, We, H, E, T = "dual-encoder", 3000, 64, 128, 96, 20
+    h, p = make(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
+    rng = np.random.default_rng(5)
+    tok = O.synth_tokens(rng, 4500, T, V, "real", 5.0)            # > 4096 rows: GEMM path
+    big = h.encode_host(sse_ffi.SIDE_TGT, tok, True)
+    small = h.encode_host(sse_ffi.SIDE_TGT, tok[:700], True)     # fused path
+    raw_big = h.encode_host(sse_ffi.SIDE_TGT, tok, False)
+    raw_small = h.encode_host(sse_ffi.SIDE_TGT, tok[:700], False)
+    assert np.abs(big[:700] - small).max() < 2e-6
+    assert np.abs(raw_big[:700] - raw_small).max() < 2e-5 * max(1.0, np.abs(raw_big).max())
+    assert np.abs(small - O.encode(p, mode, "tgt", tok[:700], True)).max() < TOL_TC
+    h.close()
+
+
+_VARIANT_PROBE = r"""
+import os, sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import sse_ffi, sse_oracle as O
+mode, V, We, H, E, T, B = "dual-encoder", 4000, 256, 256, 256, 30, 333
+p = O.init_params(mode, V, We, E, H, H, seed=3)
+h = sse_ffi.Handle(mode, V, We, E, H, H, T, precision=sse_ffi.PRECISION_TC)
+h.set_params(p); h.set_option("encoder", 2); h.set_option("lstm_kernel", 3)
+rng = np.random.default_rng(9)
+tok = np.concatenate([O.synth_tokens(rng, B - B // 2, T, V, "full"), O.synth_tokens(rng, B // 2, T, V, "real", 4.0)])
+want = O.encode(p, mode, "src", tok, True)
+errs = []
+for skip in (0, 1):
+    h.set_option("pad_skip", skip)
+    errs.append(float(np.abs(h.encode_host(0, tok, True) - want).max()))
+print("ERR", max(errs))
+"""
+
+
+@pytest.mark.parametrize("env", [{"SSE_LSTM_VARIANT": "3", "SSE_LSTM_UNITS": "64"},
+                                 {"SSE_LSTM_VARIANT": "3", "SSE_LSTM_UNITS": "32", "SSE_LSTM_STAGE": "1"},
+                                 {"SSE_LSTM_VARIANT": "3", "SSE_LSTM_UNITS": "32", "SSE_LSTM_STAGE": "0"},
+                                 {"SSE_LSTM_VARIANT": "2", "SSE_LSTM_EW": "8", "SSE_LSTM_GATE_MATH": "0"},
+                                 {"SSE_LSTM_VARIANT": "2", "SSE_LSTM_GATE_MATH": "2"}])
+def test_optional_table_kernel_variants_stay_within_tolerance(env):
+    """The variants selected through the environment (read once per process, hence the subprocess): single-h-tile kernel with 64
+    units per CTA / with staged table rows, 8 epilogue warps with the ex2 gate form, the f16x2 gate form."""
+    import os, subprocess, sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, "-c", _VARIANT_PROBE, os.path.join(repo, "sequence-semantic-embedding_b200"), os.path.join(repo, "oracle")],
+                       env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    err = float([l for l in r.stdout.splitlines() if l.startswith("ERR")][0].split()[1])
+    assert 0 < err < TOL_TC, (env, err)

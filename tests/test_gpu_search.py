@@ -200,3 +200,33 @@ def test_query_host_end_to_end_matches_oracle():
         assert (i == wi).mean() > 0.98
         assert np.abs(s - ws).max() < 2e-3 * max(1.0, np.abs(ws).max())
     h.close()
+
+
+_FOLLOW_PROBE = r"""
+import os, sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import sse_ffi
+E, k, Q, N = 256, 10, 600, 300000
+h = sse_ffi.Handle("dual-encoder", 50, 8, E, 8, 8, 8, precision=sse_ffi.PRECISION_TC)
+g = torch.Generator(device="cuda").manual_seed(11)
+idx = torch.randn(N, E, device="cuda", generator=g); idx /= idx.norm(dim=1, keepdim=True)
+h.index_set(idx, N, 0)
+q = torch.randn(Q, E, device="cuda", generator=g); q /= q.norm(dim=1, keepdim=True)
+s = torch.empty(Q, k, device="cuda"); i = torch.empty(Q, k, device="cuda", dtype=torch.int32)
+h.search(q, Q, k, s, i); torch.cuda.synchronize()
+ref = (q.double() @ idx.double().T).topk(k, dim=1)
+print("SAME", float((ref.indices.int() == i).float().mean()), float((ref.values.float() - s).abs().max()))
+"""
+
+
+@pytest.mark.parametrize("env", [{"SSE_SCAN_FOLLOW": "1"}, {"SSE_SCAN_FOLLOW": "1", "SSE_SCAN_COST": "300,1000"}, {"SSE_SCAN_SAMPLE_DIV": "5"}])
+def test_scan_work_decomposition_knobs_do_not_change_results(env):
+    """The remainder m-group walking the heavy groups' tile order (strided units, out-of-range filler tiles), other item splits and
+    sample fractions: same top-k as float64 (600 rows = 256 + 256 + 88 exercises the full-packing path)."""
+    import os, subprocess, sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, "-c", _FOLLOW_PROBE, os.path.join(repo, "sequence-semantic-embedding_b200")], env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    same, serr = [float(x) for x in [l for l in r.stdout.splitlines() if l.startswith("SAME")][0].split()[1:]]
+    assert same == 1.0 and serr < 1e-5, (env, same, serr)
