@@ -16,6 +16,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <stdlib.h>
+#include <algorithm>
 
 namespace sse {
 
@@ -347,8 +349,36 @@ int transpose_to_16(const float* src, int rows, int cols, int64_t lds, uint16_t*
   SSE_CUDA_OK(cudaGetLastError());
   return SSE_OK;
 }
+// the common case (We = ld, multiple of 8, 16-byte aligned rows): 8 elements per thread -- two float4 loads, one 16-byte store
+__global__ void gather_rows_16_vec_kernel(const int32_t* __restrict__ tokens, int64_t n_tok, const float* __restrict__ emb, int We,
+                                          uint16_t* __restrict__ out, int fmt) {
+  const int per_row = We >> 3;
+  const int64_t total = n_tok * per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / per_row;
+    const int e = (int)(i - r * per_row) << 3;
+    const float* src = emb + (size_t)__ldg(tokens + r) * We + e;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    uint4 o;
+    if (fmt == 1) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w), p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+      o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1); o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    } else {
+      __half2 p0 = __floats2half2_rn(a.x, a.y), p1 = __floats2half2_rn(a.z, a.w), p2 = __floats2half2_rn(b.x, b.y), p3 = __floats2half2_rn(b.z, b.w);
+      o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1); o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)r * We + e) = o;
+  }
+}
+
 int gather_rows_16(const int32_t* tokens, int64_t n_tok, const float* emb, int We, int ld, uint16_t* out, int fmt, cudaStream_t st, int64_t* launches) {
   if (n_tok <= 0) return SSE_OK;
+  if (ld == We && (We & 7) == 0 && ((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    gather_rows_16_vec_kernel<<<(int)std::min<int64_t>(cdiv64(n_tok * (We >> 3), 256), 148 * 16), 256, 0, st>>>(tokens, n_tok, emb, We, out, fmt);
+    if (launches) ++*launches;
+    SSE_CUDA_OK(cudaGetLastError());
+    return SSE_OK;
+  }
   gather_rows_16_kernel<<<(int)std::min<int64_t>(cdiv64(n_tok * ld, 256), 148 * 16), 256, 0, st>>>(tokens, n_tok, emb, We, ld, out, fmt);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
@@ -356,6 +386,20 @@ int gather_rows_16(const int32_t* tokens, int64_t n_tok, const float* emb, int W
 }
 
 // D[M,N] = alpha * A[M,K] B[N,K]^T (+ beta D); split_k > 1: partial sums are atomically ADDED to D (beta is taken as 1)
+// One CTA computes one output tile and nothing overlaps its prologue (barriers, TMEM allocation, first TMA round trip) and
+// its epilogue with a mainloop -- unless a second CTA lives on the same SM.  A grid of several waves therefore runs with a
+// 3-stage ring (<= 113 KB of shared memory per CTA: two CTAs per SM, 128 TMEM columns each) instead of the deepest ring that
+// fits alone.  SSE_GEMM_STAGES=n forces the ring depth (experiments).
+static int multiwave_stages(int n_stages, int64_t n_ctas, size_t stage_bytes) {
+  static const int env = getenv("SSE_GEMM_STAGES") ? atoi(getenv("SSE_GEMM_STAGES")) : 0;
+  if (env > 0) return std::max(2, std::min(G_STAGES_MAX, std::min(env, n_stages)));
+  if (n_ctas > 148) {
+    const int fit2 = (int)((113 * 1024 - 1024 - 256) / stage_bytes);
+    if (fit2 >= 2) return std::min(n_stages, fit2);
+  }
+  return n_stages;
+}
+
 int gemm_tc(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int M, int N, int K, float alpha, float beta, float* D, int64_t ldd,
             int fmt, int split_k, uint16_t* D16, int64_t ldd16, cudaStream_t st, int64_t* launches) {
   if (M <= 0 || N <= 0) return SSE_OK;
@@ -374,8 +418,9 @@ int gemm_tc(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int 
   split_k = cdiv(nkb, p.kb_per_split);
   const size_t stage = (size_t)128 * KBLK * 2 + (size_t)BN * KBLK * 2;
   p.n_stages = std::min(G_STAGES_MAX, std::max(2, p.kb_per_split));
-  const size_t smem = 1024 + (size_t)p.n_stages * stage + 256;
   dim3 grid(cdiv(N, BN), cdiv(M, 128), split_k);
+  p.n_stages = multiwave_stages(p.n_stages, (int64_t)grid.x * grid.y * grid.z, stage);
+  const size_t smem = 1024 + (size_t)p.n_stages * stage + 256;
   const bool atomic = split_k > 1;
 #define LAUNCH_GEMM(BN_, EPI_)                                                                                               \
   do {                                                                                                                        \
@@ -427,8 +472,9 @@ int cnn_conv_pool_tc(const uint16_t* X, int n_seq, int T, int ldx, int kf, const
   p.kb_per_split = nkb;
   const size_t stage = (size_t)128 * KBLK * 2 + (size_t)BN * KBLK * 2;
   p.n_stages = std::min(G_STAGES_MAX, std::max(2, nkb));
-  const size_t smem = 1024 + (size_t)p.n_stages * stage + 256;
   dim3 grid(cdiv(F, BN), cdiv(n_seq, 128 / rps), 1);
+  p.n_stages = multiwave_stages(p.n_stages, (int64_t)grid.x * grid.y, stage);
+  const size_t smem = 1024 + (size_t)p.n_stages * stage + 256;
   if (BN == 64) LAUNCH_GEMM(64, EPI_POOL); else LAUNCH_GEMM(128, EPI_POOL);
   if (launches) ++*launches;
   SSE_CUDA_OK(cudaGetLastError());
