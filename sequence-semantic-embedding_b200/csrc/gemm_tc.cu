@@ -405,7 +405,11 @@ int gemm_tc(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, int 
   if (M <= 0 || N <= 0) return SSE_OK;
   if (K <= 0) { set_error("gemm_tc: K must be positive"); return SSE_EINVAL; }
   CUtensorMap ta, tb;
-  const int BN = N <= 64 ? 64 : 128;
+  // 64-column tiles when 128-column tiles would leave SMs without a CTA (the per-step GEMMs of the train step and of the wide
+  // LSTM tower: 96 / 80 tiles): twice the CTAs, half the epilogue each, and two of them fit an SM.  SSE_GEMM_BN=128 restores.
+  static const int env_bn = getenv("SSE_GEMM_BN") ? atoi(getenv("SSE_GEMM_BN")) : 0;
+  const int64_t tiles128 = (int64_t)cdiv(N, 128) * cdiv(M, 128) * std::max(1, split_k);
+  const int BN = N <= 64 ? 64 : (env_bn == 128 ? 128 : (env_bn == 64 || tiles128 < 148 ? 64 : 128));
   SSE_TRY(make_map_2d(&ta, A, M, K, lda, 128, fmt));
   SSE_TRY(make_map_2d(&tb, B, N, K, ldb, BN, fmt));
   GemmParams p;
