@@ -446,6 +446,10 @@ int sse_destroy(sse_handle* h) {
   if (!h) return SSE_OK;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
+  if (h->train_graph) cudaGraphExecDestroy(h->train_graph);
+  if (h->train_side) cudaStreamDestroy(h->train_side);
+  if (h->train_main) cudaStreamDestroy(h->train_main);
+  for (int i = 0; i < 6; ++i) if (h->train_ev[i]) cudaEventDestroy(h->train_ev[i]);
   for (auto& p : h->params) if (p.dev) cudaFree(p.dev);
   h->enc_ws.release(); h->search_ws.release(); h->io_ws.release(); h->train_ws.release();
   h->pad[0].buf.release(); h->pad[1].buf.release();

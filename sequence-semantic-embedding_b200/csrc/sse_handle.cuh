@@ -50,6 +50,16 @@ struct sse_handle {
 
   // workspaces
   sse::Scratch enc_ws, search_ws, io_ws, train_ws, train_tc_ws, tok_ws, proj_ws;
+  cudaStream_t train_side = nullptr;        // the target tower of the tensor-core train step runs here, next to the source tower
+  cudaStream_t train_main = nullptr;        // ... and the source tower + loss here (forked from / joined into the caller's stream, so that the
+                                            // step can be captured into a graph even when the caller uses the legacy default stream)
+  cudaEvent_t train_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // the tensor-core train step as a CUDA graph (SSE_TRAIN_GRAPH=1): replayed while batch size and every buffer address stay the same
+  cudaGraphExec_t train_graph = nullptr;
+  unsigned long long train_graph_key[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long train_seen_key[6] = {0, 0, 0, 0, 0, 0};
+  long long train_graph_launches = 0;
+  bool train_graph_failed = false;
   int* tok_bad = nullptr;           // device counter: out-of-range token ids seen by the pre-pass (sticky until read)
   float* grad_arena = nullptr;      // dense gradients, laid out by Param::grad_off, then the dense embedding gradient
   int64_t grad_floats = 0;          // dense (non-embedding) part

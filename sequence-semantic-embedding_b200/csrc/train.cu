@@ -511,34 +511,121 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
   } else if (want_tc) {
     const int64_t TB = (int64_t)T * B;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-    size_t need = al((size_t)TB * 4 * Hmax * 4) + al((size_t)4 * Hmax * (We + Hmax) * 2) * 2 + 2 * al((size_t)B * E * 4) + 3 * al((size_t)B * 4);
+    size_t need = 2 * (al((size_t)TB * 4 * Hmax * 4) + al((size_t)4 * Hmax * (We + Hmax) * 2) * 2) + 2 * al((size_t)B * E * 4) + 3 * al((size_t)B * 4);
     for (int s2 = 0; s2 < 2; ++s2) {
       const int H = h->lstm[s2].H;
       need += al((size_t)TB * 5 * H * 4) + al((size_t)TB * H * 4) + al((size_t)B * E * 4) + al((size_t)B * H * 4) + al((size_t)TB * H * 2) + al((size_t)TB * We * 2) + al((size_t)TB * 4);
     }
     const int64_t ldT = (TB + 7) / 8 * 8;
-    need += al((size_t)TB * 4 * Hmax * 2) + al((size_t)4 * Hmax * ldT * 2) + al((size_t)We * ldT * 2) + al((size_t)Hmax * ldT * 2) + al((size_t)TB * We * 4) +
-            al((size_t)2 * B * Hmax * 4) + al((size_t)B * Hmax * 4) + 4096;
+    const size_t bwd_bytes = al((size_t)TB * 4 * Hmax * 2) + al((size_t)4 * Hmax * ldT * 2) + al((size_t)We * ldT * 2) + al((size_t)Hmax * ldT * 2) + al((size_t)TB * We * 4) +
+                             al((size_t)2 * B * Hmax * 4) + al((size_t)B * Hmax * 4) + 4096;
+    need += 2 * bwd_bytes;
     SSE_TRY(h->train_tc_ws.ensure(need));
     uint8_t* tw8 = h->train_tc_ws.as<uint8_t>();
     size_t o2 = 0;
     auto carve8 = [&](size_t bytes) { size_t o = o2; o2 = al(o2 + bytes); return tw8 + o; };
-    float* zx = reinterpret_cast<float*>(carve8((size_t)TB * 4 * Hmax * 4));
-    uint16_t* kT16 = reinterpret_cast<uint16_t*>(carve8((size_t)4 * Hmax * (We + Hmax) * 2));
-    uint16_t* k16 = reinterpret_cast<uint16_t*>(carve8((size_t)4 * Hmax * (We + Hmax) * 2));
+    // The two towers are independent chains of 2T small dependent launches each (GEMM + gate kernel per step): they run side by
+    // side on two streams (fork after the token check, join before the pair loss, fork / join again around the backward), each
+    // with its own scratch.  SSE_TRAIN_STREAMS=1 puts both back on the caller's stream.
+    static const bool two_streams = !(getenv("SSE_TRAIN_STREAMS") && atoi(getenv("SSE_TRAIN_STREAMS")) == 1);
+    if (two_streams && !h->train_side) {
+      SSE_CUDA_OK(cudaStreamCreateWithFlags(&h->train_side, cudaStreamNonBlocking));
+      SSE_CUDA_OK(cudaStreamCreateWithFlags(&h->train_main, cudaStreamNonBlocking));
+      for (int i = 0; i < 6; ++i) SSE_CUDA_OK(cudaEventCreateWithFlags(&h->train_ev[i], cudaEventDisableTiming));
+    }
+    cudaStream_t const st_user = st;
+    if (two_streams) {                 // the step runs on the library's own pair of streams, forked from the caller's stream ...
+      SSE_CUDA_OK(cudaEventRecord(h->train_ev[4], st_user));
+      SSE_CUDA_OK(cudaStreamWaitEvent(h->train_main, h->train_ev[4], 0));
+      st = h->train_main;
+    }
+    cudaStream_t st2[2] = {st, two_streams ? h->train_side : st};
+    float* zx_s[2];
+    uint16_t *kT16_s[2], *k16_s[2];
+    for (int s2 = 0; s2 < 2; ++s2) {
+      zx_s[s2] = reinterpret_cast<float*>(carve8((size_t)TB * 4 * Hmax * 4));
+      kT16_s[s2] = reinterpret_cast<uint16_t*>(carve8((size_t)4 * Hmax * (We + Hmax) * 2));
+      k16_s[s2] = reinterpret_cast<uint16_t*>(carve8((size_t)4 * Hmax * (We + Hmax) * 2));
+    }
     float* du_tc[2] = {reinterpret_cast<float*>(carve8((size_t)B * E * 4)), reinterpret_cast<float*>(carve8((size_t)B * E * 4))};
     float* rl = reinterpret_cast<float*>(carve8((size_t)B * 4));
     float* rp = reinterpret_cast<float*>(carve8((size_t)B * 4));
     float* rn = reinterpret_cast<float*>(carve8((size_t)B * 4));
+    // everything below addresses fixed buffers (workspace, arena, weights): with SSE_TRAIN_GRAPH=1 the ~530 launches of a step are
+    // captured once per (batch size, buffer addresses) and replayed -- the step is bound by the host's launch rate otherwise
+    auto issue = [&]() -> int {
     TcTowerState tst[2];
-    for (int s2 = 0; s2 < 2; ++s2)
-      SSE_TRY(train_tc_forward(h, s2, s2 == 0 ? d_src : d_tgt, B, tw8, &o2, &tst[s2], kT16, zx, st));
-    pair_loss_kernel<<<cdiv(B, 8), 256, 0, st>>>(tst[0].u, tst[1].u, d_lab, B, E, 1.0f / (float)B_global, du_tc[0], du_tc[1], rl, rp, rn, nullptr);
-    ++h->launches;
-    reduce_rows_kernel<<<1, 256, 0, st>>>(rl, rp, rn, B, scalars);
-    ++h->launches;
-    for (int s2 = 0; s2 < 2; ++s2)
-      SSE_TRY(train_tc_backward(h, s2, s2 == 0 ? d_src : d_tgt, B, tst[s2], du_tc[s2], tw8, o2, k16, G, touched, scalars, st));
+      if (two_streams) {
+        SSE_CUDA_OK(cudaEventRecord(h->train_ev[0], st));                 // tokens, labels and the zeroed arena are in place
+        SSE_CUDA_OK(cudaStreamWaitEvent(h->train_side, h->train_ev[0], 0));
+      }
+      for (int s2 = 0; s2 < 2; ++s2)
+        SSE_TRY(train_tc_forward(h, s2, s2 == 0 ? d_src : d_tgt, B, tw8, &o2, &tst[s2], kT16_s[s2], zx_s[s2], st2[s2]));
+      if (two_streams) {
+        SSE_CUDA_OK(cudaEventRecord(h->train_ev[1], h->train_side));
+        SSE_CUDA_OK(cudaStreamWaitEvent(st, h->train_ev[1], 0));
+      }
+      pair_loss_kernel<<<cdiv(B, 8), 256, 0, st>>>(tst[0].u, tst[1].u, d_lab, B, E, 1.0f / (float)B_global, du_tc[0], du_tc[1], rl, rp, rn, nullptr);
+      ++h->launches;
+      reduce_rows_kernel<<<1, 256, 0, st>>>(rl, rp, rn, B, scalars);
+      ++h->launches;
+      if (two_streams) {
+        SSE_CUDA_OK(cudaEventRecord(h->train_ev[2], st));
+        SSE_CUDA_OK(cudaStreamWaitEvent(h->train_side, h->train_ev[2], 0));
+      }
+      const size_t o_bwd = o2;
+      for (int s2 = 0; s2 < 2; ++s2)      // each tower's backward scratch: its own region behind the forward state
+        SSE_TRY(train_tc_backward(h, s2, s2 == 0 ? d_src : d_tgt, B, tst[s2], du_tc[s2], tw8, o_bwd + (size_t)s2 * bwd_bytes, k16_s[s2], G, touched, scalars, st2[s2]));
+      if (two_streams) {
+        SSE_CUDA_OK(cudaEventRecord(h->train_ev[3], h->train_side));
+        SSE_CUDA_OK(cudaStreamWaitEvent(st, h->train_ev[3], 0));
+      }
+      return SSE_OK;
+    };
+    static const bool env_graph = !(getenv("SSE_TRAIN_GRAPH") && atoi(getenv("SSE_TRAIN_GRAPH")) == 0);      // default on; =0 disables
+    const bool use_graph = env_graph && !h->train_graph_failed;
+    const unsigned long long key[6] = {(unsigned long long)B, (unsigned long long)(uintptr_t)tw8, (unsigned long long)(uintptr_t)arena,
+                                       (unsigned long long)(uintptr_t)d_src, (unsigned long long)(uintptr_t)d_lab, (unsigned long long)B_global};
+    bool same_graph = h->train_graph != nullptr, seen = true;
+    for (int i = 0; i < 6; ++i) { same_graph = same_graph && h->train_graph_key[i] == key[i]; seen = seen && h->train_seen_key[i] == key[i]; }
+    if (use_graph && two_streams && same_graph) {
+      SSE_CUDA_OK(cudaGraphLaunch(h->train_graph, st));
+      h->launches += h->train_graph_launches;
+    } else if (use_graph && two_streams && seen) {
+      // second call with this key (the first ran eagerly: every lazy one-time set-up has happened): capture
+      if (h->train_graph) { cudaGraphExecDestroy(h->train_graph); h->train_graph = nullptr; }
+      const long long l0 = h->launches;
+      SSE_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      const size_t o2_before = o2;
+      const int rc = issue();
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(st, &g);
+      cudaError_t ie = cudaErrorUnknown;
+      if (rc == SSE_OK && ce == cudaSuccess && g) ie = cudaGraphInstantiate(&h->train_graph, g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (ie == cudaSuccess) {
+        h->train_graph_launches = h->launches - l0;
+        for (int i = 0; i < 6; ++i) h->train_graph_key[i] = key[i];
+        SSE_CUDA_OK(cudaGraphLaunch(h->train_graph, st));
+      } else {
+        // capture is an optimisation only: whatever went wrong (a context that does not allow it, an invalidated capture),
+        // this handle runs its steps eagerly from now on
+        h->train_graph = nullptr;
+        h->train_graph_failed = true;
+        cudaGetLastError();
+        h->launches = l0;
+        o2 = o2_before;
+        SSE_TRY(issue());
+      }
+    } else {
+      for (int i = 0; i < 6; ++i) h->train_seen_key[i] = key[i];
+      SSE_TRY(issue());
+    }
+    if (two_streams) {                 // ... and joined back into it
+      SSE_CUDA_OK(cudaEventRecord(h->train_ev[5], st));
+      SSE_CUDA_OK(cudaStreamWaitEvent(st_user, h->train_ev[5], 0));
+      st = st_user;
+    }
     SSE_CUDA_OK(cudaGetLastError());
     if (loss_host || acc_host) {
       float sc[4];
