@@ -449,6 +449,7 @@ int sse_destroy(sse_handle* h) {
   if (h->train_graph) cudaGraphExecDestroy(h->train_graph);
   if (h->train_side) cudaStreamDestroy(h->train_side);
   if (h->train_main) cudaStreamDestroy(h->train_main);
+  for (int i = 0; i < 2; ++i) { if (h->train_chain[i]) cudaStreamDestroy(h->train_chain[i]); for (int j = 0; j < 4; ++j) if (h->train_ev2[i][j]) cudaEventDestroy(h->train_ev2[i][j]); }
   for (int i = 0; i < 6; ++i) if (h->train_ev[i]) cudaEventDestroy(h->train_ev[i]);
   for (auto& p : h->params) if (p.dev) cudaFree(p.dev);
   h->enc_ws.release(); h->search_ws.release(); h->io_ws.release(); h->train_ws.release();

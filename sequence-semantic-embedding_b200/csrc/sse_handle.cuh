@@ -54,6 +54,8 @@ struct sse_handle {
   cudaStream_t train_main = nullptr;        // ... and the source tower + loss here (forked from / joined into the caller's stream, so that the
                                             // step can be captured into a graph even when the caller uses the legacy default stream)
   cudaEvent_t train_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t train_chain[2] = {nullptr, nullptr};   // second row-half chain of each tower's recurrence
+  cudaEvent_t train_ev2[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
   // the tensor-core train step as a CUDA graph (SSE_TRAIN_GRAPH=1): replayed while batch size and every buffer address stay the same
   cudaGraphExec_t train_graph = nullptr;
   unsigned long long train_graph_key[6] = {0, 0, 0, 0, 0, 0};

@@ -336,8 +336,10 @@ struct TcTowerState {
   uint16_t* x16;                   // [T,B,We] bf16
 };
 
+// `st_b` (optional): the recurrence of the second half of the batch rows runs there -- rows are independent, so a tower's T-step
+// chain of small dependent launches becomes two chains that fill each other's bubbles (ev: fork / join events)
 int train_tc_forward(sse_handle* h, int s, const int32_t* tok, int B, uint8_t* ws, size_t* ws_off, TcTowerState* ts, uint16_t* kT16,
-                     float* zx, cudaStream_t st) {
+                     float* zx, cudaStream_t st, cudaStream_t st_b = nullptr, cudaEvent_t* ev = nullptr) {
   const sse_config& c = h->cfg;
   const int T = c.max_seq_length, We = c.embedding_size, E = c.encoding_size;
   const LstmTower& tw = h->lstm[s];
@@ -358,15 +360,24 @@ int train_tc_forward(sse_handle* h, int s, const int32_t* tok, int B, uint8_t* w
   SSE_TRY(transpose_to_16(tw.K, ld, 4 * H, 4 * H, kT16, ld, 1, st, &h->launches));
   // ZX = X Wx^T over all T*B rows
   SSE_TRY(gemm_tc(ts->x16, We, kT16, ld, (int)TB, 4 * H, We, 1.f, 0.f, zx, 4 * H, 1, 1, nullptr, 0, st, &h->launches));
+  const bool chains = st_b != nullptr && ev != nullptr && B >= 32;
+  const int nrow[2] = {chains ? (B / 2 + 7) / 8 * 8 : B, chains ? B - (B / 2 + 7) / 8 * 8 : 0};
+  cudaStream_t cst[2] = {st, chains ? st_b : st};
+  if (chains) { SSE_CUDA_OK(cudaEventRecord(ev[0], st)); SSE_CUDA_OK(cudaStreamWaitEvent(st_b, ev[0], 0)); }
   for (int t = 0; t < T; ++t) {
-    float* z_t = zx + (size_t)t * B * 4 * H;
-    if (t > 0)   // z_t += h_{t-1} Wh^T
-      SSE_TRY(gemm_tc(ts->h16 + (size_t)(t - 1) * B * H, H, kT16 + We, ld, B, 4 * H, H, 1.f, 1.f, z_t, 4 * H, 1, 1, nullptr, 0, st, &h->launches));
-    lstm_fwd_gates_kernel<<<cdiv(B * H, 256), 256, 0, st>>>(z_t, tw.b, t > 0 ? ts->sc + (size_t)(t - 1) * B * H : nullptr, B, H,
-                                                            ts->sg + (size_t)t * B * 5 * H, ts->sc + (size_t)t * B * H,
-                                                            ts->h16 + (size_t)t * B * H, t == T - 1 ? ts->hlast : nullptr);
-    ++h->launches;
+    for (int cix = 0; cix < (chains ? 2 : 1); ++cix) {
+      const size_t b0 = cix ? (size_t)nrow[0] : 0;
+      const int nb = nrow[cix];
+      float* z_t = zx + ((size_t)t * B + b0) * 4 * H;
+      if (t > 0)   // z_t += h_{t-1} Wh^T
+        SSE_TRY(gemm_tc(ts->h16 + ((size_t)(t - 1) * B + b0) * H, H, kT16 + We, ld, nb, 4 * H, H, 1.f, 1.f, z_t, 4 * H, 1, 1, nullptr, 0, cst[cix], &h->launches));
+      lstm_fwd_gates_kernel<<<cdiv(nb * H, 256), 256, 0, cst[cix]>>>(z_t, tw.b, t > 0 ? ts->sc + ((size_t)(t - 1) * B + b0) * H : nullptr, nb, H,
+                                                                  ts->sg + ((size_t)t * B + b0) * 5 * H, ts->sc + ((size_t)t * B + b0) * H,
+                                                                  ts->h16 + ((size_t)t * B + b0) * H, t == T - 1 ? ts->hlast + b0 * H : nullptr);
+      ++h->launches;
+    }
   }
+  if (chains) { SSE_CUDA_OK(cudaEventRecord(ev[1], st_b)); SSE_CUDA_OK(cudaStreamWaitEvent(st, ev[1], 0)); }
   if (project_rows_supported(B, H, E))       // u = h_T M in one launch (the SIMT GEMM takes 68 us for 1536 x 256 x 256)
     SSE_TRY(project_rows(ts->hlast, H, tw.M, H, E, B, nullptr, 0, ts->u, st, &h->launches));
   else
@@ -376,7 +387,7 @@ int train_tc_forward(sse_handle* h, int s, const int32_t* tok, int B, uint8_t* w
 }
 
 int train_tc_backward(sse_handle* h, int s, const int32_t* tok, int B, const TcTowerState& ts, const float* du, uint8_t* ws, size_t ws_off,
-                      uint16_t* k16, float* G, float* touched, float* scalars, cudaStream_t st) {
+                      uint16_t* k16, float* G, float* touched, float* scalars, cudaStream_t st, cudaStream_t st_b = nullptr, cudaEvent_t* ev = nullptr) {
   const sse_config& c = h->cfg;
   const int T = c.max_seq_length, We = c.embedding_size, E = c.encoding_size;
   const LstmTower& tw = h->lstm[s];
@@ -403,16 +414,24 @@ int train_tc_backward(sse_handle* h, int s, const int32_t* tok, int B, const TcT
   SSE_TRY(convert_to_16(tw.K, ld, 4 * H, 4 * H, k16, 4 * H, 1, st, &h->launches));
   float* dh_cur = dh;
   float* dh_next = dh + (size_t)B * H;
+  const bool chains = st_b != nullptr && ev != nullptr && B >= 32;
+  const int nrow[2] = {chains ? (B / 2 + 7) / 8 * 8 : B, chains ? B - (B / 2 + 7) / 8 * 8 : 0};
+  cudaStream_t cst[2] = {st, chains ? st_b : st};
+  if (chains) { SSE_CUDA_OK(cudaEventRecord(ev[2], st)); SSE_CUDA_OK(cudaStreamWaitEvent(st_b, ev[2], 0)); }
   for (int t = T - 1; t >= 0; --t) {
-    uint16_t* dz_t = dz16 + (size_t)t * B * 4 * H;
-    lstm_bwd_gates16_kernel<<<cdiv(B * H, 256), 256, 0, st>>>(dh_cur, H, dc, ts.sg + (size_t)t * B * 5 * H,
-                                                              t > 0 ? ts.sc + (size_t)(t - 1) * B * H : nullptr, B, H, dz_t);
-    ++h->launches;
-    if (t > 0) {   // dh_{t-1} = dz_t K[We:]^T
-      SSE_TRY(gemm_tc(dz_t, 4 * H, k16 + (size_t)We * 4 * H, 4 * H, B, H, 4 * H, 1.f, 0.f, dh_next, H, 1, 1, nullptr, 0, st, &h->launches));
-      std::swap(dh_cur, dh_next);
+    for (int cix = 0; cix < (chains ? 2 : 1); ++cix) {
+      const size_t b0 = cix ? (size_t)nrow[0] : 0;
+      const int nb = nrow[cix];
+      uint16_t* dz_t = dz16 + ((size_t)t * B + b0) * 4 * H;
+      lstm_bwd_gates16_kernel<<<cdiv(nb * H, 256), 256, 0, cst[cix]>>>(dh_cur + b0 * H, H, dc + b0 * H, ts.sg + ((size_t)t * B + b0) * 5 * H,
+                                                                    t > 0 ? ts.sc + ((size_t)(t - 1) * B + b0) * H : nullptr, nb, H, dz_t);
+      ++h->launches;
+      if (t > 0)    // dh_{t-1} = dz_t K[We:]^T
+        SSE_TRY(gemm_tc(dz_t, 4 * H, k16 + (size_t)We * 4 * H, 4 * H, nb, H, 4 * H, 1.f, 0.f, dh_next + b0 * H, H, 1, 1, nullptr, 0, cst[cix], &h->launches));
     }
+    if (t > 0) std::swap(dh_cur, dh_next);
   }
+  if (chains) { SSE_CUDA_OK(cudaEventRecord(ev[3], st_b)); SSE_CUDA_OK(cudaStreamWaitEvent(st, ev[3], 0)); }
   // dX = dZ K[:We]^T over all rows; embedding IndexedSlices from it
   SSE_TRY(gemm_tc(dz16, 4 * H, k16, 4 * H, (int)TB, We, 4 * H, 1.f, 0.f, dx, We, 1, 1, nullptr, 0, st, &h->launches));
   embed_scatter_kernel<<<148 * 4, 256, 0, st>>>(tok, B, T, dx, We, We, G, touched, scalars);
@@ -531,6 +550,10 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
     if (two_streams && !h->train_side) {
       SSE_CUDA_OK(cudaStreamCreateWithFlags(&h->train_side, cudaStreamNonBlocking));
       SSE_CUDA_OK(cudaStreamCreateWithFlags(&h->train_main, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        SSE_CUDA_OK(cudaStreamCreateWithFlags(&h->train_chain[i], cudaStreamNonBlocking));
+        for (int j = 0; j < 4; ++j) SSE_CUDA_OK(cudaEventCreateWithFlags(&h->train_ev2[i][j], cudaEventDisableTiming));
+      }
       for (int i = 0; i < 6; ++i) SSE_CUDA_OK(cudaEventCreateWithFlags(&h->train_ev[i], cudaEventDisableTiming));
     }
     cudaStream_t const st_user = st;
@@ -540,6 +563,10 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
       st = h->train_main;
     }
     cudaStream_t st2[2] = {st, two_streams ? h->train_side : st};
+    // SSE_TRAIN_CHAINS=2: additionally split each tower's recurrence into two row-half chains (measured 374 -> 377 steps/s at 1024
+    // rows, 289 -> 297 at 1536: the two towers already saturate the GPU; off by default)
+    static const bool env_chains = getenv("SSE_TRAIN_CHAINS") && atoi(getenv("SSE_TRAIN_CHAINS")) == 2;
+    const bool row_chains = two_streams && env_chains;
     float* zx_s[2];
     uint16_t *kT16_s[2], *k16_s[2];
     for (int s2 = 0; s2 < 2; ++s2) {
@@ -560,7 +587,7 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
         SSE_CUDA_OK(cudaStreamWaitEvent(h->train_side, h->train_ev[0], 0));
       }
       for (int s2 = 0; s2 < 2; ++s2)
-        SSE_TRY(train_tc_forward(h, s2, s2 == 0 ? d_src : d_tgt, B, tw8, &o2, &tst[s2], kT16_s[s2], zx_s[s2], st2[s2]));
+        SSE_TRY(train_tc_forward(h, s2, s2 == 0 ? d_src : d_tgt, B, tw8, &o2, &tst[s2], kT16_s[s2], zx_s[s2], st2[s2], row_chains ? h->train_chain[s2] : nullptr, h->train_ev2[s2]));
       if (two_streams) {
         SSE_CUDA_OK(cudaEventRecord(h->train_ev[1], h->train_side));
         SSE_CUDA_OK(cudaStreamWaitEvent(st, h->train_ev[1], 0));
@@ -575,7 +602,7 @@ int sse_train_grads(sse_handle* h, const int32_t* src, const int32_t* tgt, const
       }
       const size_t o_bwd = o2;
       for (int s2 = 0; s2 < 2; ++s2)      // each tower's backward scratch: its own region behind the forward state
-        SSE_TRY(train_tc_backward(h, s2, s2 == 0 ? d_src : d_tgt, B, tst[s2], du_tc[s2], tw8, o_bwd + (size_t)s2 * bwd_bytes, k16_s[s2], G, touched, scalars, st2[s2]));
+        SSE_TRY(train_tc_backward(h, s2, s2 == 0 ? d_src : d_tgt, B, tst[s2], du_tc[s2], tw8, o_bwd + (size_t)s2 * bwd_bytes, k16_s[s2], G, touched, scalars, st2[s2], row_chains ? h->train_chain[s2] : nullptr, h->train_ev2[s2]));
       if (two_streams) {
         SSE_CUDA_OK(cudaEventRecord(h->train_ev[3], h->train_side));
         SSE_CUDA_OK(cudaStreamWaitEvent(st, h->train_ev[3], 0));
