@@ -81,7 +81,7 @@ def parse():
                          "still gets its own SMs; -1 = 128 when the scan is capped for pipelining -- the encoder then fits the SMs the cap "
                          "leaves free -- else 0)")
     ap.add_argument("--search-late", type=int, default=-1, help="with a scan grid cap: extra LATE scan CTAs that start on the SMs the concurrent encoder frees mid-scan "
-                                                                   "(-1 = 32 when the cap is on: measured 1.53 -> 1.59 M q/s at the headline shape)")
+                                                                   "(-1 = one per SM the cap leaves to the encoder: measured 1.53 -> 1.60 M q/s at the headline shape)")
     ap.add_argument("--search-late-share", type=int, default=40, help="tile share of a late scan CTA, percent of a regular one")
     ap.add_argument("--train-steps", type=int, default=5, help="timed train steps for the secondary train-step/s figure (0 = skip)")
     ap.add_argument("--train-rows", type=int, default=0, help="pair rows per GPU per train step (0 = the config's, default 1024 = 512 pos + 512 neg)")
@@ -358,8 +358,9 @@ def run_b200(args):
     state = {"primed": False, "n": 0}
     if args.search_ctas < 0:
         args.search_ctas = 108 if G <= 4 else 0
-    if args.search_late < 0:
-        args.search_late = 32 if (pipeline and args.search_ctas > 0) else 0
+    if args.search_late < 0:        # one late scan CTA per SM the cap reserves for the encoder (measured: 0 -> 1.53, 32 -> 1.57, 40 -> 1.60 M q/s)
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        args.search_late = max(0, n_sm - args.search_ctas) if (pipeline and args.search_ctas > 0) else 0
     if args.cluster_rows < 0:
         args.cluster_rows = 128 if (pipeline and args.search_ctas > 0) else 0
     h.set_option("cluster_rows", args.cluster_rows)
