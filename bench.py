@@ -518,6 +518,10 @@ def run_b200(args):
         hs.set_option("search_ctas", 0)
         hs.set_option("search_late_ctas", 0)
     torch.cuda.synchronize()
+    # The GPU runs these kernels under its power cap, and the cap's controller remembers the load before: right after the timed
+    # regions above the same search measures 8-15 % slower than after a pause (0.337 vs 0.369 ms on one box).  The roofline
+    # denominator is the BURST figure of MEASURED_PEAKS.json (a kernel timed alone after idle), so the kernel is timed the same way.
+    time.sleep(2.0)
     encode_all(0, enc2[0], enc_local[0], stream)
     for _ in range(3):
         scan_handle().search(enc2[0], Q, k, sc, ix, stream)
@@ -531,6 +535,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     ms_search = e0.elapsed_time(e1) / reps
     enc_alone = {}
+    time.sleep(1.0)
     for rows_opt in (0, 128):             # the encoder alone on all SMs: the library's own choice (64-row clusters for a query batch) and 128-row clusters
         h.set_option("cluster_rows", rows_opt)
         for _ in range(2):
@@ -633,6 +638,7 @@ def run_b200(args):
     roof["peak_source"] = src
     roof["kernel"] = "search (prep+sample scan+select_tau+filter scan+finalize)" if use_tc else "search_simt_kernel+merge"
     roof["ms_per_launch"] = ms_search
+    roof["timing"] = "CUDA events around %d back-to-back searches on the launching stream, after 3 warm-up searches and a 2 s idle (burst conditions, like the peak it is divided by)" % reps
     roof["algorithmic"] = {"flops": flops, "bytes": bytes_alg}
     roof["encoder"] = {"ms": ms_enc, "rows": Ql, "flops": Ql * F_ENC, "achieved_tflops": Ql * F_ENC / (ms_enc * 1e-3) / 1e12,
                        "achieved_frac_of_bf16_peak": Ql * F_ENC / (ms_enc * 1e-3) / 1e12 / bf16_tf,
